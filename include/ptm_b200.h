@@ -1,0 +1,176 @@
+/* ptm_b200.h -- C ABI of the B200-native PTM log-density hot path.
+ *
+ * Drop-in boundary for liesel-devs/liesel-ptm's data-parallel hot path (SURVEY.md
+ * section 8b).  Plain C: no C++ types, no exceptions across the boundary.  Every
+ * per-call pointer is a DEVICE pointer owned by the caller; only
+ * ptm_problem_create() takes HOST pointers (it copies the static data into HBM
+ * once).  All work is enqueued on the caller's stream (a cudaStream_t passed as
+ * void*), with no hidden synchronisation and no allocation after create /
+ * workspace sizing.  Return value 0 = OK, non-zero = PtmStatus; the message of
+ * the last failure on the calling thread is ptm_last_error().
+ *
+ * Reference interfaces replaced (paths under /root/reference/liesel_ptm/):
+ *   ptm_logp_* / ptm_logp_grad_*   model.log_prob(state) and jax.grad of it as the
+ *                                  MCMC kernels call them: logprob.py:36-41,50-69,
+ *                                  104-140; iwls_fixed.py:91-116,159-186; the
+ *                                  density itself is dist.py:185-188,339-395,
+ *                                  718-740 over bspline/util.py:91-103,
+ *                                  bspline/ptm.py:412-478, bspline/approx.py:
+ *                                  418-522, gam/var.py:157-162, predictor.py:
+ *                                  19-21,369-371,583-585, gam/dist.py:56-70,
+ *                                  var.py:77-82,106-115.
+ *   ptm_basis_*                    Basis.bspline / basis_matrix: bspline/approx.py:
+ *                                  74-210 (called at gam/var.py:1001-1002).
+ *   ptm_transform_*                TransformationSpline.dot_and_deriv_n_fullbatch:
+ *                                  bspline/util.py:91-103.
+ *   ptm_xtwx_* / ptm_loc_precision_*  GaussianLocCholInfo.working_weights /
+ *                                  precision / chol_info: iwls_proposals.py:55-89
+ *                                  (scale terms, W == 2: 118-144).
+ *   ptm_quadform_*                 beta' K beta of the Gibbs scale updates:
+ *                                  gam/kernel.py:29-39, kernel.py:99-111.
+ *
+ * Parameter vector of ONE chain (row of the [C, P] row-major `params` array, the
+ * layout JAX hands over after ravel_pytree):
+ *     [ beta0, gamma0,                     loc / log-scale intercepts
+ *       beta_0[p_0], ..., beta_{T-1}[p_{T-1}],   smooth-term coefficients
+ *       delta_z[nparam-1],                 latent transformation coefficients
+ *       tau_0, ..., tau_{T-1},             smoothing scales of the terms
+ *       tau_delta ]                        scale of the delta_z prior
+ * `grad` has the same layout.  logp = sum_i loglik_i + sum_t prior(beta_t | tau_t)
+ * + prior(delta_z | tau_delta); the O(1)-per-chain hyper-priors on tau^2 stay in
+ * host JAX.
+ */
+#ifndef PTM_B200_H_
+#define PTM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PTM_OK = 0,
+  PTM_ERR_NULL = 1,       /* null pointer argument */
+  PTM_ERR_SHAPE = 2,      /* invalid / unsupported shape */
+  PTM_ERR_DTYPE = 3,      /* entry point does not match the problem's dtype */
+  PTM_ERR_RANGE = 4,      /* covariate outside its interior knot range (the
+                             reference raises ValueError, approx.py:197-206) */
+  PTM_ERR_CUDA = 5,       /* a CUDA call failed; see ptm_last_error() */
+  PTM_ERR_WORKSPACE = 6   /* workspace too small */
+} PtmStatus;
+
+enum { PTM_F32 = 0, PTM_F64 = 1 };
+enum { PTM_LOC = 0, PTM_SCALE = 1 };
+enum { PTM_MAX_TERMS = 24, PTM_MAX_NBASES = 32, PTM_MAX_NPARAM = 40 };
+
+/* Static data of one model.  All pointers are HOST pointers; element type is
+ * float when dtype == PTM_F32 and double when dtype == PTM_F64. */
+typedef struct {
+  int32_t dtype;               /* PTM_F32 | PTM_F64 */
+  int64_t n;                   /* observations */
+  const void* y;               /* [n] response */
+  int32_t n_terms;             /* T smooth terms (<= PTM_MAX_TERMS) */
+  const void* const* x;        /* [T] -> [n] covariate of term t */
+  const int32_t* nbases;       /* [T] nb_t: B-spline bases (4 <= nb_t <= 32) */
+  const int32_t* ncoef;        /* [T] p_t: columns of Z_t */
+  const int32_t* predictor;    /* [T] PTM_LOC | PTM_SCALE */
+  const void* const* knots;    /* [T] -> [nb_t + 4] equidistant knots */
+  const void* const* Z;        /* [T] -> [nb_t, p_t] row-major reparam matrix */
+  const void* const* K;        /* [T] -> [p_t, p_t] penalty after reparams */
+  const int32_t* rank;         /* [T] rank of K_t */
+  int32_t nparam;              /* shape parameters of h (J = nparam + 1 bases) */
+  const void* trafo_knots;     /* [nparam + 5] PTMKnots(a, b, nparam).knots */
+  const void* trafo_Z;         /* [nparam, nparam - 1] delta = Z delta_z */
+  double trafo_lambda;         /* PTMSpline eps: transition width / (b - a) */
+  const void* trafo_grid;      /* [1002] BSplineApprox.grid, or NULL to rebuild it
+                                  with the restated jnp.linspace formula */
+} PtmProblemDesc;
+
+typedef struct PtmProblem PtmProblem; /* opaque, immutable after create */
+
+int ptm_problem_create(const PtmProblemDesc* desc, PtmProblem** out);
+int ptm_problem_destroy(PtmProblem* prob);
+
+/* P = 2 + sum_t p_t + (nparam - 1) + T + 1. */
+int64_t ptm_num_params(const PtmProblem* prob);
+/* Offsets into one chain's parameter row; any output pointer may be NULL.
+ * beta_off has T entries, tau_off has T entries. */
+int ptm_param_layout(const PtmProblem* prob, int64_t* beta0_off, int64_t* gamma0_off,
+                     int64_t* beta_off, int64_t* delta_z_off, int64_t* tau_off,
+                     int64_t* tau_delta_off);
+
+/* Bytes of caller-owned device scratch needed for C chains (any entry point). */
+size_t ptm_workspace_bytes(const PtmProblem* prob, int64_t n_chains);
+
+/* Restrict the observation range this handle evaluates to [obs_begin, obs_end):
+ * observation-axis sharding across GPUs.  With add_priors == 0 the
+ * per-chain prior terms are left out of logp/grad so that exactly one rank adds
+ * them before/after the allreduce.  Default: [0, n), add_priors = 1. */
+int ptm_problem_set_shard(PtmProblem* prob, int64_t obs_begin, int64_t obs_end,
+                          int32_t add_priors);
+
+/* logp[c] for C chains.  params [C, P] row-major, logp [C]. */
+int ptm_logp_f64(const PtmProblem* prob, const double* params, int64_t n_chains,
+                 double* logp, void* workspace, size_t workspace_bytes, void* stream);
+int ptm_logp_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
+                 float* logp, void* workspace, size_t workspace_bytes, void* stream);
+
+/* logp[c] and grad[c, :] in one fused pass over the observations. */
+int ptm_logp_grad_f64(const PtmProblem* prob, const double* params, int64_t n_chains,
+                      double* logp, double* grad, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int ptm_logp_grad_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
+                      float* logp, float* grad, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* Banded design of term `term`: interval[i] = j with knots[j] <= x_i < knots[j+1]
+ * (int32, bit-exact with the reference's order-0 indicator) and the four non-zero
+ * cubic values of columns j-3..j in values[i, 0..3]. */
+int ptm_basis_f64(const PtmProblem* prob, int32_t term, int32_t* interval,
+                  double* values, void* stream);
+int ptm_basis_f32(const PtmProblem* prob, int32_t term, int32_t* interval,
+                  float* values, void* stream);
+
+/* h(r) and h'(r) of the transformation for raw shape coefficients delta
+ * [C, nparam] at r [m]: z, dz are [C, m].  cell (optional, [C? no: m]) receives
+ * the grid-cell index searchsorted(grid, r, 'right') - 1 for core points and -1
+ * elsewhere. */
+int ptm_transform_f64(const PtmProblem* prob, const double* delta, int64_t n_chains,
+                      const double* r, int64_t m, double* z, double* dz,
+                      int32_t* cell, void* stream);
+int ptm_transform_f32(const PtmProblem* prob, const float* delta, int64_t n_chains,
+                      const float* r, int64_t m, float* z, float* dz,
+                      int32_t* cell, void* stream);
+
+/* Chain-batched IWLS information of a LOC term: xtwx [C, p, p] = X' diag(w) X and
+ * xtr [C, p] = X' (w * resid-free score weights) with w_i = 1/max(sigma_i,
+ * sqrt(eps))^2 and X = B_t Z_t (iwls_proposals.py:55-74).  For a SCALE term w == 2.
+ * Either output may be NULL. */
+int ptm_xtwx_f64(const PtmProblem* prob, int32_t term, const double* params,
+                 int64_t n_chains, double* xtwx, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int ptm_xtwx_f32(const PtmProblem* prob, int32_t term, const float* params,
+                 int64_t n_chains, float* xtwx, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* precision [C, p, p] = XtWX + K / max(tau, sqrt(eps))^2 + 1e-6 mean(diag) I and
+ * its lower Cholesky factor chol [C, p, p] (iwls_proposals.py:61-89). */
+int ptm_loc_precision_f64(const PtmProblem* prob, int32_t term, const double* params,
+                          int64_t n_chains, double* precision, double* chol,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int ptm_loc_precision_f32(const PtmProblem* prob, int32_t term, const float* params,
+                          int64_t n_chains, float* precision, float* chol,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels the last logp / logp_grad call on this thread launched. */
+int ptm_last_launch_count(void);
+
+const char* ptm_last_error(void);
+const char* ptm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTM_B200_H_ */

@@ -1,0 +1,594 @@
+// ptm_capi.cu -- C ABI (include/ptm_b200.h) over the kernels in ptm_kernels.cuh.
+// Host side only: problem set-up (copies the static data into HBM once), launch
+// planning, and the extern "C" entry points.  No torch types, no exceptions across
+// the boundary, no allocation or synchronisation inside the per-call entry points.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ptm_b200.h"
+#include "ptm_kernels.cuh"
+#include "ptm_xtwx.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PTM_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess)                                                          \
+      return fail(PTM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Plan {
+  int CG, M, n_items, grid, NSLOT, To, S, Rsub;
+  long long chunk_len;
+  size_t smem_main;
+  size_t off_gamma, off_cc, off_partial, off_xt, total;
+};
+
+}  // namespace
+
+struct PtmProblem {
+  int dtype = PTM_F64;
+  long long n = 0;
+  int T = 0, T_loc = 0, T_scale = 0;
+  int nparam = 0, J = 0, KK = 0, P = 0;
+  int nb[ptm::kMaxTerms] = {0}, p[ptm::kMaxTerms] = {0}, pred[ptm::kMaxTerms] = {0};
+  int rank[ptm::kMaxTerms] = {0}, qidx[ptm::kMaxTerms] = {0};
+  int zoff[ptm::kMaxTerms] = {0}, koff[ptm::kMaxTerms] = {0}, boff[ptm::kMaxTerms] = {0};
+  int goff[ptm::kMaxTerms] = {0};
+  double inv_dk[ptm::kMaxTerms] = {0};
+  int sum_nb = 0, max_nb = 0, max_p = 0;
+  int dz_off = 0, tau_off = 0, taud_off = 0;
+  long long obs_begin = 0, obs_end = 0;
+  int add_priors = 1;
+  int num_sms = 148;
+  int device = 0;
+  // device buffers (element type by dtype)
+  void* d_y = nullptr;
+  void* d_X = nullptr;
+  void* d_knots = nullptr;
+  void* d_grid = nullptr;
+  void* d_Zall = nullptr;
+  void* d_Kall = nullptr;
+  void* d_Zd = nullptr;
+  void* d_tc = nullptr;
+  ptm::TrafoConst<double> tc64;  // host copy (double); cast for f32
+};
+
+namespace {
+
+template <typename R>
+R get(const void* p, long long i) { return reinterpret_cast<const R*>(p)[i]; }
+
+// B-spline basis row at x for the transformation knots, in double.
+void host_basis_row(const std::vector<double>& k, int nbases, double x, std::vector<double>& row) {
+  row.assign(nbases, 0.0);
+  const double inv_dk = (double)(k.size() - 1) / (k.back() - k.front());
+  int j = ptm::find_interval<double>(x, k.data(), nbases, inv_dk);
+  double b[4];
+  ptm::bspline4<double>(x, k.data(), j, b);
+  for (int m = 0; m < 4; ++m)
+    if (j - 3 + m < nbases) row[j - 3 + m] = b[m];
+}
+
+template <typename R>
+void fill_tc(const ptm::TrafoConst<double>& s, ptm::TrafoConst<R>& d) {
+  d.KK = s.KK; d.a = (R)s.a; d.b = (R)s.b; d.inv_dk = (R)s.inv_dk; d.w = (R)s.w;
+  d.inv_w = (R)s.inv_w; d.min_eps = (R)s.min_eps; d.max_eps = (R)s.max_eps;
+  d.inv_h = (R)s.inv_h; d.kap_scale = (R)s.kap_scale; d.ratio = (R)s.ratio;
+  d.frac_eps = sizeof(R) == 8 ? (R)1e-6 : (R)2e-2;
+  d.nparam = s.nparam; d.J = s.J; d.dk = (R)s.dk; d.log_dk = (R)s.log_dk; d.k1 = (R)s.k1;
+  d.log_KK = (R)s.log_KK;
+  for (int i = 0; i < ptm::kMaxJ; ++i) d.Bk[i] = (R)s.Bk[i];
+  for (int i = 0; i < ptm::kMaxNparam; ++i) d.wts[i] = (R)s.wts[i];
+}
+
+template <typename R>
+int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
+  const long long n = d->n;
+  const int T = d->n_terms;
+  // ---- validate + offsets -------------------------------------------------------
+  int zo = 0, ko = 0, bo = 2, go = 0;
+  for (int t = 0; t < T; ++t) {
+    const int nb = d->nbases[t], p = d->ncoef[t];
+    if (nb < 4 || nb > PTM_MAX_NBASES) return fail(PTM_ERR_SHAPE, "nbases must be in [4, 32]");
+    if (p < 1 || p > nb) return fail(PTM_ERR_SHAPE, "ncoef must be in [1, nbases]");
+    if (d->predictor[t] != PTM_LOC && d->predictor[t] != PTM_SCALE)
+      return fail(PTM_ERR_SHAPE, "predictor must be PTM_LOC or PTM_SCALE");
+    if (!d->x[t] || !d->knots[t] || !d->Z[t] || !d->K[t]) return fail(PTM_ERR_NULL, "null term array");
+    pr->nb[t] = nb; pr->p[t] = p; pr->pred[t] = d->predictor[t]; pr->rank[t] = d->rank[t];
+    pr->qidx[t] = d->predictor[t] == PTM_LOC ? pr->T_loc++ : pr->T_scale++;
+    pr->zoff[t] = zo; zo += nb * p;
+    pr->koff[t] = ko; ko += p * p;
+    pr->boff[t] = bo; bo += p;
+    pr->goff[t] = go; go += nb;
+    pr->max_nb = std::max(pr->max_nb, nb);
+    pr->max_p = std::max(pr->max_p, p);
+    const R* kn = reinterpret_cast<const R*>(d->knots[t]);
+    for (int i = 0; i + 1 < nb + 4; ++i)
+      if (!(kn[i] < kn[i + 1])) return fail(PTM_ERR_SHAPE, "knots must be strictly increasing");
+    pr->inv_dk[t] = (double)(nb + 3) / ((double)kn[nb + 3] - (double)kn[0]);
+    // the reference raises when a covariate leaves [knots[3], knots[nb]]
+    // (bspline/approx.py:197-206); NaN fails the comparison like jnp.min would
+    const R* xv = reinterpret_cast<const R*>(d->x[t]);
+    const R lo = kn[3], hi = kn[nb];
+    for (long long i = 0; i < n; ++i)
+      if (!(xv[i] >= lo && xv[i] <= hi)) {
+        char buf[200];
+        snprintf(buf, sizeof buf,
+                 "Values of x are not inside the range of interior knots, [%g, %g] (term %d, obs %lld)",
+                 (double)lo, (double)hi, t, i);
+        return fail(PTM_ERR_RANGE, buf);
+      }
+  }
+  pr->sum_nb = go;
+  pr->T = T;
+  pr->n = n;
+  pr->nparam = d->nparam;
+  pr->J = d->nparam + 1;
+  pr->KK = pr->J - 3;
+  pr->dz_off = bo;
+  pr->tau_off = bo + d->nparam - 1;
+  pr->taud_off = pr->tau_off + T;
+  pr->P = pr->taud_off + 1;
+  pr->obs_begin = 0;
+  pr->obs_end = n;
+
+  // ---- transformation constants (double, then cast) -----------------------------
+  const int J = pr->J, L = J + 4;
+  std::vector<double> tk(L);
+  for (int i = 0; i < L; ++i) tk[i] = (double)get<R>(d->trafo_knots, i);
+  for (int i = 0; i + 1 < L; ++i)
+    if (!(tk[i] < tk[i + 1])) return fail(PTM_ERR_SHAPE, "trafo knots must be strictly increasing");
+  ptm::TrafoConst<double>& tc = pr->tc64;
+  memset(&tc, 0, sizeof tc);
+  tc.nparam = d->nparam; tc.J = J; tc.KK = J - 3;
+  tc.a = tk[3]; tc.b = tk[J];
+  double dsum = 0;
+  for (int i = 0; i + 1 < L; ++i) dsum += tk[i + 1] - tk[i];
+  tc.dk = dsum / (L - 1);
+  tc.log_dk = std::log(tc.dk);
+  tc.inv_dk = 1.0 / tc.dk;
+  tc.k1 = tk[3];
+  double eps = d->trafo_lambda;
+  if (eps < 1e-6) return fail(PTM_ERR_SHAPE, "eps is < 1e-6; that is numerically unstable.");
+  tc.w = eps * (tc.b - tc.a);
+  tc.inv_w = 1.0 / tc.w;
+  tc.min_eps = tc.a - tc.w;
+  tc.max_eps = tc.b + tc.w;
+  tc.inv_h = (double)(ptm::kGridN - 1) / (tc.b - tc.a);
+  tc.kap_scale = (double)ptm::kGridN / (double)(ptm::kGridN - 1);
+  tc.ratio = (double)tc.KK / (double)(ptm::kGridN - 1);
+  tc.log_KK = std::log((double)(J - 3));
+  {
+    std::vector<double> row;
+    host_basis_row(tk, J, tk[3], row);
+    double run = 0;
+    for (int j = J - 1; j >= 0; --j) { run += row[j]; tc.Bk[j] = run; }
+    for (int j = 0; j < d->nparam; ++j) tc.wts[j] = 1.0;
+    tc.wts[0] = 1.0 / 6.0; tc.wts[1] = 1.0 / 6.0 + 2.0 / 3.0;
+    tc.wts[d->nparam - 1] = 1.0 / 6.0; tc.wts[d->nparam - 2] = 2.0 / 3.0 + 1.0 / 6.0;
+  }
+
+  // ---- device copies ---------------------------------------------------------------
+  PTM_CUDA(cudaGetDevice(&pr->device));
+  PTM_CUDA(cudaDeviceGetAttribute(&pr->num_sms, cudaDevAttrMultiProcessorCount, pr->device));
+  const size_t es = sizeof(R);
+  PTM_CUDA(cudaMalloc(&pr->d_y, std::max<size_t>(n, 1) * es));
+  PTM_CUDA(cudaMemcpy(pr->d_y, d->y, n * es, cudaMemcpyHostToDevice));
+  PTM_CUDA(cudaMalloc(&pr->d_X, std::max<size_t>((size_t)T * n, 1) * es));
+  for (int t = 0; t < T; ++t)
+    PTM_CUDA(cudaMemcpy((char*)pr->d_X + (size_t)t * n * es, d->x[t], n * es, cudaMemcpyHostToDevice));
+  {
+    std::vector<R> kn((size_t)std::max(T, 1) * ptm::kKnotStride, R(0));
+    for (int t = 0; t < T; ++t)
+      for (int i = 0; i < pr->nb[t] + 4; ++i) kn[(size_t)t * ptm::kKnotStride + i] = get<R>(d->knots[t], i);
+    PTM_CUDA(cudaMalloc(&pr->d_knots, kn.size() * es));
+    PTM_CUDA(cudaMemcpy(pr->d_knots, kn.data(), kn.size() * es, cudaMemcpyHostToDevice));
+    std::vector<R> zall(std::max(zo, 1)), kall(std::max(ko, 1));
+    for (int t = 0; t < T; ++t) {
+      for (int i = 0; i < pr->nb[t] * pr->p[t]; ++i) zall[pr->zoff[t] + i] = get<R>(d->Z[t], i);
+      for (int i = 0; i < pr->p[t] * pr->p[t]; ++i) kall[pr->koff[t] + i] = get<R>(d->K[t], i);
+    }
+    PTM_CUDA(cudaMalloc(&pr->d_Zall, zall.size() * es));
+    PTM_CUDA(cudaMemcpy(pr->d_Zall, zall.data(), zall.size() * es, cudaMemcpyHostToDevice));
+    PTM_CUDA(cudaMalloc(&pr->d_Kall, kall.size() * es));
+    PTM_CUDA(cudaMemcpy(pr->d_Kall, kall.data(), kall.size() * es, cudaMemcpyHostToDevice));
+    const size_t nzd = (size_t)d->nparam * (d->nparam - 1);
+    PTM_CUDA(cudaMalloc(&pr->d_Zd, nzd * es));
+    PTM_CUDA(cudaMemcpy(pr->d_Zd, d->trafo_Z, nzd * es, cudaMemcpyHostToDevice));
+    // grid: as the reference built it (data), or the restated jnp.linspace formula
+    std::vector<R> grid(ptm::kGridN + 2);
+    if (d->trafo_grid) {
+      for (int i = 0; i < ptm::kGridN + 2; ++i) grid[i] = get<R>(d->trafo_grid, i);
+    } else {
+      const R a = (R)tk[3], b = (R)tk[J];
+      const R step = (b - a) / R(ptm::kGridN);
+      grid[0] = a - step;
+      for (int i = 0; i < ptm::kGridN - 1; ++i) {
+        const R s = R(i) / R(ptm::kGridN - 1);
+        grid[1 + i] = a * (R(1) - s) + b * s;
+      }
+      grid[ptm::kGridN] = b;
+      grid[ptm::kGridN + 1] = b + step;
+    }
+    PTM_CUDA(cudaMalloc(&pr->d_grid, grid.size() * es));
+    PTM_CUDA(cudaMemcpy(pr->d_grid, grid.data(), grid.size() * es, cudaMemcpyHostToDevice));
+    ptm::TrafoConst<R> tcr;
+    memset(&tcr, 0, sizeof tcr);
+    fill_tc<R>(tc, tcr);
+    PTM_CUDA(cudaMalloc(&pr->d_tc, sizeof tcr));
+    PTM_CUDA(cudaMemcpy(pr->d_tc, &tcr, sizeof tcr, cudaMemcpyHostToDevice));
+  }
+  return PTM_OK;
+}
+
+template <typename R>
+Plan make_plan(const PtmProblem* pr, long long C) {
+  Plan pl;
+  const int T = pr->T;
+  pl.S = std::max(1, std::max(pr->T_loc, pr->T_scale));
+  pl.CG = (int)((C + 31) / 32);
+  pl.NSLOT = ptm::kRegSlots + pr->KK * 5 + pr->sum_nb;
+  const int NCC = pr->KK * 5 + 6;
+  auto smem_for = [&](int To) {
+    size_t b = 0;
+    b += (size_t)NCC * 32 * sizeof(R);
+    b += (size_t)ptm::kNTW * pr->KK * 5 * 32 * sizeof(R);
+    b += (size_t)2 * To * 2 * 32 * sizeof(R);
+    b += (size_t)T * 3 * To * 4 * sizeof(R);
+    b += (size_t)T * ptm::kKnotStride * sizeof(R);
+    b += (size_t)ptm::kNTW * ptm::kRegSlots * 32 * sizeof(R);
+    b += (size_t)T * 3 * To * sizeof(int);
+    return b;
+  };
+  pl.Rsub = std::max(1, 40 / pl.S);
+  while (pl.Rsub > 1 && smem_for(pl.S * pl.Rsub) > 220 * 1024) --pl.Rsub;
+  pl.To = pl.S * pl.Rsub;
+  pl.smem_main = smem_for(pl.To);
+  const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
+  const long long target_items = 8LL * pr->num_sms;
+  long long M = std::max<long long>(1, target_items / pl.CG);
+  const long long max_m = std::max<long long>(1, len / ((long long)pl.To * 16));
+  M = std::min(M, max_m);
+  long long chunk = (len + M - 1) / M;
+  chunk = std::max<long long>(pl.To, (chunk + pl.To - 1) / pl.To * pl.To);
+  M = std::max<long long>(1, (len + chunk - 1) / chunk);
+  pl.M = (int)M;
+  pl.chunk_len = chunk;
+  pl.n_items = pl.CG * pl.M;
+  pl.grid = std::min(pl.n_items, pr->num_sms);
+  size_t off = 0;
+  pl.off_gamma = off; off = align_up(off + (size_t)std::max(T, 1) * ptm::kMaxNbases * C * sizeof(R), 256);
+  pl.off_cc = off;    off = align_up(off + (size_t)NCC * C * sizeof(R), 256);
+  pl.off_partial = off; off = align_up(off + (size_t)pl.n_items * pl.NSLOT * 32 * sizeof(R), 256);
+  pl.off_xt = off;    off = align_up(off + ptm::xtwx_workspace_bytes<R>(pr->max_nb, C), 256);
+  pl.total = off;
+  return pl;
+}
+
+template <typename R, int NB, bool GRAD>
+int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
+  auto kern = ptm::k_main<R, NB, GRAD, 512>;
+  PTM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_main));
+  kern<<<pl.grid, 32 * (T + ptm::kNTW), pl.smem_main, st>>>(a);
+  PTM_CUDA(cudaGetLastError());
+  return PTM_OK;
+}
+
+template <typename R>
+int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* grad, void* ws,
+              size_t ws_bytes, void* stream) {
+  if (!pr || !params || !logp || !ws) return fail(PTM_ERR_NULL, "null argument");
+  if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  if (C < 1) return fail(PTM_ERR_SHAPE, "n_chains must be >= 1");
+  if (pr->T > 12) return fail(PTM_ERR_SHAPE, "fused kernel supports at most 12 smooth terms");
+  const Plan pl = make_plan<R>(pr, C);
+  if (ws_bytes < pl.total) return fail(PTM_ERR_WORKSPACE, "workspace too small");
+  if (pl.smem_main > 227 * 1024) return fail(PTM_ERR_SHAPE, "shared-memory budget exceeded");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* wsb = reinterpret_cast<char*>(ws);
+  R* Gamma = reinterpret_cast<R*>(wsb + pl.off_gamma);
+  R* cc = reinterpret_cast<R*>(wsb + pl.off_cc);
+  R* partial = reinterpret_cast<R*>(wsb + pl.off_partial);
+  const bool want_grad = grad != nullptr;
+  g_launches = 0;
+
+  ptm::PreArgs<R> pa;
+  memset(&pa, 0, sizeof pa);
+  pa.params = params; pa.Gamma = Gamma; pa.cc = cc;
+  pa.Zall = reinterpret_cast<const R*>(pr->d_Zall);
+  pa.Zd = reinterpret_cast<const R*>(pr->d_Zd);
+  pa.tc = reinterpret_cast<const ptm::TrafoConst<R>*>(pr->d_tc);
+  pa.C = (int)C; pa.P = pr->P; pa.T = pr->T; pa.dz_off = pr->dz_off;
+  for (int t = 0; t < pr->T; ++t) {
+    pa.nb[t] = pr->nb[t]; pa.p[t] = pr->p[t]; pa.zoff[t] = pr->zoff[t]; pa.boff[t] = pr->boff[t];
+  }
+  ptm::k_pre<R><<<(unsigned)C, 128, pr->P * sizeof(R), st>>>(pa);
+  PTM_CUDA(cudaGetLastError());
+  ++g_launches;
+
+  ptm::MainArgs<R> ma;
+  memset(&ma, 0, sizeof ma);
+  ma.y = reinterpret_cast<const R*>(pr->d_y);
+  ma.X = reinterpret_cast<const R*>(pr->d_X);
+  ma.knots = reinterpret_cast<const R*>(pr->d_knots);
+  ma.grid = reinterpret_cast<const R*>(pr->d_grid);
+  ma.Gamma = Gamma; ma.cc = cc; ma.partial = partial;
+  ma.n = pr->n; ma.obs_begin = pr->obs_begin; ma.obs_end = pr->obs_end;
+  ma.chunk_len = pl.chunk_len;
+  ma.C = (int)C; ma.CG = pl.CG; ma.M = pl.M; ma.n_items = pl.n_items;
+  ma.NSLOT = want_grad ? pl.NSLOT : 3;
+  ma.KK = pr->KK;
+  ma.T = pr->T; ma.T_loc = pr->T_loc; ma.T_scale = pr->T_scale;
+  ma.S = pl.S; ma.Rsub = pl.Rsub; ma.To = pl.To;
+  for (int t = 0; t < pr->T; ++t) {
+    ma.nb[t] = pr->nb[t]; ma.pred[t] = pr->pred[t]; ma.qidx[t] = pr->qidx[t];
+    ma.goff[t] = pr->goff[t]; ma.inv_dk[t] = (R)pr->inv_dk[t];
+  }
+  {
+    ptm::TrafoConst<R> tcr;
+    fill_tc<R>(pr->tc64, tcr);
+    ma.ts = tcr;
+  }
+  int rc;
+  if (pr->max_nb <= 20)
+    rc = want_grad ? launch_main<R, 20, true>(ma, pl, pr->T, st) : launch_main<R, 20, false>(ma, pl, pr->T, st);
+  else
+    rc = want_grad ? launch_main<R, 32, true>(ma, pl, pr->T, st) : launch_main<R, 32, false>(ma, pl, pr->T, st);
+  if (rc != PTM_OK) return rc;
+  ++g_launches;
+
+  ptm::PostArgs<R> po;
+  memset(&po, 0, sizeof po);
+  po.params = params; po.partial = partial; po.logp = logp; po.grad = grad;
+  po.Zall = reinterpret_cast<const R*>(pr->d_Zall);
+  po.Kall = reinterpret_cast<const R*>(pr->d_Kall);
+  po.Zd = reinterpret_cast<const R*>(pr->d_Zd);
+  po.tc = reinterpret_cast<const ptm::TrafoConst<R>*>(pr->d_tc);
+  po.C = (int)C; po.P = pr->P; po.T = pr->T; po.M = pl.M; po.NSLOT = ma.NSLOT; po.KK = pr->KK;
+  for (int t = 0; t < pr->T; ++t) {
+    po.nb[t] = pr->nb[t]; po.p[t] = pr->p[t]; po.zoff[t] = pr->zoff[t]; po.koff[t] = pr->koff[t];
+    po.boff[t] = pr->boff[t]; po.goff[t] = pr->goff[t]; po.rank[t] = pr->rank[t];
+  }
+  po.dz_off = pr->dz_off; po.tau_off = pr->tau_off; po.taud_off = pr->taud_off;
+  po.n_obs = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
+  po.add_priors = pr->add_priors;
+  const size_t smem_post = ((size_t)ma.NSLOT * 32 + 32) * sizeof(R);
+  if (want_grad) {
+    auto kp = ptm::k_post<R, true>;
+    PTM_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_post));
+    kp<<<pl.CG, 256, smem_post, st>>>(po);
+  } else {
+    auto kp = ptm::k_post<R, false>;
+    kp<<<pl.CG, 256, smem_post, st>>>(po);
+  }
+  PTM_CUDA(cudaGetLastError());
+  ++g_launches;
+  return PTM_OK;
+}
+
+template <typename R>
+int basis_impl(const PtmProblem* pr, int term, int32_t* interval, R* values, void* stream) {
+  if (!pr || !interval || !values) return fail(PTM_ERR_NULL, "null argument");
+  if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  if (term < 0 || term >= pr->T) return fail(PTM_ERR_SHAPE, "term index out of range");
+  if (pr->n == 0) return PTM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = (int)std::min<long long>((pr->n + 255) / 256, 148LL * 16);
+  ptm::k_basis<R><<<blocks, 256, 0, st>>>(
+      reinterpret_cast<const R*>(pr->d_X) + (size_t)term * pr->n, pr->n,
+      reinterpret_cast<const R*>(pr->d_knots) + (size_t)term * ptm::kKnotStride, pr->nb[term],
+      (R)pr->inv_dk[term], interval, values);
+  PTM_CUDA(cudaGetLastError());
+  return PTM_OK;
+}
+
+template <typename R>
+int transform_impl(const PtmProblem* pr, const R* delta, long long C, const R* r, long long m, R* z,
+                   R* dz, int32_t* cell, void* stream) {
+  if (!pr || !delta || !r || !z || !dz) return fail(PTM_ERR_NULL, "null argument");
+  if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  if (C < 1 || m < 0) return fail(PTM_ERR_SHAPE, "bad shape");
+  if (m == 0) return PTM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ptm::k_transform<R><<<(unsigned)C, 256, 0, st>>>(
+      delta, (int)C, r, m, reinterpret_cast<const ptm::TrafoConst<R>*>(pr->d_tc),
+      reinterpret_cast<const R*>(pr->d_grid), z, dz, cell);
+  PTM_CUDA(cudaGetLastError());
+  return PTM_OK;
+}
+
+template <typename R>
+int xtwx_impl(const PtmProblem* pr, int term, const R* params, long long C, R* xtwx, R* precision,
+              R* chol, void* ws, size_t ws_bytes, void* stream) {
+  if (!pr || !params || !ws) return fail(PTM_ERR_NULL, "null argument");
+  if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  if (term < 0 || term >= pr->T) return fail(PTM_ERR_SHAPE, "term index out of range");
+  if (C < 1) return fail(PTM_ERR_SHAPE, "n_chains must be >= 1");
+  const Plan pl = make_plan<R>(pr, C);
+  if (ws_bytes < pl.total) return fail(PTM_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* wsb = reinterpret_cast<char*>(ws);
+  R* Gamma = reinterpret_cast<R*>(wsb + pl.off_gamma);
+  R* cc = reinterpret_cast<R*>(wsb + pl.off_cc);
+  R* xt = reinterpret_cast<R*>(wsb + pl.off_xt);
+  // gamma of the SCALE terms (sigma depends on them) via the shared prologue
+  ptm::PreArgs<R> pa;
+  memset(&pa, 0, sizeof pa);
+  pa.params = params; pa.Gamma = Gamma; pa.cc = cc;
+  pa.Zall = reinterpret_cast<const R*>(pr->d_Zall);
+  pa.Zd = reinterpret_cast<const R*>(pr->d_Zd);
+  pa.tc = reinterpret_cast<const ptm::TrafoConst<R>*>(pr->d_tc);
+  pa.C = (int)C; pa.P = pr->P; pa.T = pr->T; pa.dz_off = pr->dz_off;
+  for (int t = 0; t < pr->T; ++t) {
+    pa.nb[t] = pr->nb[t]; pa.p[t] = pr->p[t]; pa.zoff[t] = pr->zoff[t]; pa.boff[t] = pr->boff[t];
+  }
+  g_launches = 0;
+  ptm::k_pre<R><<<(unsigned)C, 128, pr->P * sizeof(R), st>>>(pa);
+  PTM_CUDA(cudaGetLastError());
+  ++g_launches;
+  ptm::XtwxArgs<R> xa;
+  memset(&xa, 0, sizeof xa);
+  xa.X = reinterpret_cast<const R*>(pr->d_X);
+  xa.knots = reinterpret_cast<const R*>(pr->d_knots);
+  xa.Gamma = Gamma; xa.cc = cc; xa.params = params;
+  xa.Zall = reinterpret_cast<const R*>(pr->d_Zall);
+  xa.Kall = reinterpret_cast<const R*>(pr->d_Kall);
+  xa.n = pr->n; xa.obs_begin = pr->obs_begin; xa.obs_end = pr->obs_end;
+  xa.C = (int)C; xa.P = pr->P; xa.T = pr->T; xa.term = term; xa.KK = pr->KK;
+  xa.tau_off = pr->tau_off;
+  for (int t = 0; t < pr->T; ++t) {
+    xa.nb[t] = pr->nb[t]; xa.p[t] = pr->p[t]; xa.pred[t] = pr->pred[t];
+    xa.zoff[t] = pr->zoff[t]; xa.koff[t] = pr->koff[t]; xa.inv_dk[t] = (R)pr->inv_dk[t];
+  }
+  xa.add_penalty = pr->add_priors;
+  const int rc = ptm::xtwx_launch<R>(xa, xt, xtwx, precision, chol, pr->num_sms, st, &g_launches);
+  if (rc != 0) return fail(PTM_ERR_CUDA, std::string("xtwx launch: ") + cudaGetErrorString((cudaError_t)rc));
+  return PTM_OK;
+}
+
+void free_all(PtmProblem* p) {
+  cudaFree(p->d_y); cudaFree(p->d_X); cudaFree(p->d_knots); cudaFree(p->d_grid);
+  cudaFree(p->d_Zall); cudaFree(p->d_Kall); cudaFree(p->d_Zd); cudaFree(p->d_tc);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptm_problem_create(const PtmProblemDesc* d, PtmProblem** out) {
+  if (!d || !out) return fail(PTM_ERR_NULL, "null argument");
+  *out = nullptr;
+  if (d->dtype != PTM_F32 && d->dtype != PTM_F64) return fail(PTM_ERR_DTYPE, "dtype must be PTM_F32 or PTM_F64");
+  if (d->n < 0) return fail(PTM_ERR_SHAPE, "n must be >= 0");
+  if (d->n_terms < 0 || d->n_terms > PTM_MAX_TERMS) return fail(PTM_ERR_SHAPE, "n_terms out of range");
+  if (d->nparam < 4 || d->nparam > PTM_MAX_NPARAM) return fail(PTM_ERR_SHAPE, "nparam must be in [4, 40]");
+  if (!d->y && d->n > 0) return fail(PTM_ERR_NULL, "y is null");
+  if (!d->trafo_knots || !d->trafo_Z) return fail(PTM_ERR_NULL, "trafo arrays are null");
+  if (d->n_terms > 0 && (!d->x || !d->nbases || !d->ncoef || !d->predictor || !d->knots || !d->Z || !d->K || !d->rank))
+    return fail(PTM_ERR_NULL, "term arrays are null");
+  PtmProblem* pr = new (std::nothrow) PtmProblem();
+  if (!pr) return fail(PTM_ERR_CUDA, "out of host memory");
+  pr->dtype = d->dtype;
+  const int rc = d->dtype == PTM_F64 ? create_impl<double>(d, pr) : create_impl<float>(d, pr);
+  if (rc != PTM_OK) {
+    free_all(pr);
+    delete pr;
+    return rc;
+  }
+  *out = pr;
+  return PTM_OK;
+}
+
+int ptm_problem_destroy(PtmProblem* p) {
+  if (!p) return PTM_OK;
+  free_all(p);
+  delete p;
+  return PTM_OK;
+}
+
+int64_t ptm_num_params(const PtmProblem* p) { return p ? p->P : -1; }
+
+int ptm_param_layout(const PtmProblem* p, int64_t* beta0_off, int64_t* gamma0_off, int64_t* beta_off,
+                     int64_t* delta_z_off, int64_t* tau_off, int64_t* tau_delta_off) {
+  if (!p) return fail(PTM_ERR_NULL, "null problem");
+  if (beta0_off) *beta0_off = 0;
+  if (gamma0_off) *gamma0_off = 1;
+  if (beta_off) for (int t = 0; t < p->T; ++t) beta_off[t] = p->boff[t];
+  if (delta_z_off) *delta_z_off = p->dz_off;
+  if (tau_off) for (int t = 0; t < p->T; ++t) tau_off[t] = p->tau_off + t;
+  if (tau_delta_off) *tau_delta_off = p->taud_off;
+  return PTM_OK;
+}
+
+size_t ptm_workspace_bytes(const PtmProblem* p, int64_t C) {
+  if (!p || C < 1) return 0;
+  return p->dtype == PTM_F64 ? make_plan<double>(p, C).total : make_plan<float>(p, C).total;
+}
+
+int ptm_problem_set_shard(PtmProblem* p, int64_t b, int64_t e, int32_t add_priors) {
+  if (!p) return fail(PTM_ERR_NULL, "null problem");
+  if (b < 0 || e > p->n || b > e) return fail(PTM_ERR_SHAPE, "shard must satisfy 0 <= begin <= end <= n");
+  p->obs_begin = b;
+  p->obs_end = e;
+  p->add_priors = add_priors ? 1 : 0;
+  return PTM_OK;
+}
+
+int ptm_logp_f64(const PtmProblem* p, const double* params, int64_t C, double* logp, void* ws, size_t wsb, void* st) {
+  return eval_impl<double>(p, params, C, logp, nullptr, ws, wsb, st);
+}
+int ptm_logp_f32(const PtmProblem* p, const float* params, int64_t C, float* logp, void* ws, size_t wsb, void* st) {
+  return eval_impl<float>(p, params, C, logp, nullptr, ws, wsb, st);
+}
+int ptm_logp_grad_f64(const PtmProblem* p, const double* params, int64_t C, double* logp, double* grad, void* ws,
+                      size_t wsb, void* st) {
+  if (!grad) return fail(PTM_ERR_NULL, "grad is null");
+  return eval_impl<double>(p, params, C, logp, grad, ws, wsb, st);
+}
+int ptm_logp_grad_f32(const PtmProblem* p, const float* params, int64_t C, float* logp, float* grad, void* ws,
+                      size_t wsb, void* st) {
+  if (!grad) return fail(PTM_ERR_NULL, "grad is null");
+  return eval_impl<float>(p, params, C, logp, grad, ws, wsb, st);
+}
+
+int ptm_basis_f64(const PtmProblem* p, int32_t term, int32_t* interval, double* values, void* st) {
+  return basis_impl<double>(p, term, interval, values, st);
+}
+int ptm_basis_f32(const PtmProblem* p, int32_t term, int32_t* interval, float* values, void* st) {
+  return basis_impl<float>(p, term, interval, values, st);
+}
+
+int ptm_transform_f64(const PtmProblem* p, const double* delta, int64_t C, const double* r, int64_t m, double* z,
+                      double* dz, int32_t* cell, void* st) {
+  return transform_impl<double>(p, delta, C, r, m, z, dz, cell, st);
+}
+int ptm_transform_f32(const PtmProblem* p, const float* delta, int64_t C, const float* r, int64_t m, float* z,
+                      float* dz, int32_t* cell, void* st) {
+  return transform_impl<float>(p, delta, C, r, m, z, dz, cell, st);
+}
+
+int ptm_xtwx_f64(const PtmProblem* p, int32_t term, const double* params, int64_t C, double* xtwx, void* ws,
+                 size_t wsb, void* st) {
+  if (!xtwx) return fail(PTM_ERR_NULL, "xtwx is null");
+  return xtwx_impl<double>(p, term, params, C, xtwx, nullptr, nullptr, ws, wsb, st);
+}
+int ptm_xtwx_f32(const PtmProblem* p, int32_t term, const float* params, int64_t C, float* xtwx, void* ws,
+                 size_t wsb, void* st) {
+  if (!xtwx) return fail(PTM_ERR_NULL, "xtwx is null");
+  return xtwx_impl<float>(p, term, params, C, xtwx, nullptr, nullptr, ws, wsb, st);
+}
+int ptm_loc_precision_f64(const PtmProblem* p, int32_t term, const double* params, int64_t C, double* precision,
+                          double* chol, void* ws, size_t wsb, void* st) {
+  if (!precision) return fail(PTM_ERR_NULL, "precision is null");
+  return xtwx_impl<double>(p, term, params, C, nullptr, precision, chol, ws, wsb, st);
+}
+int ptm_loc_precision_f32(const PtmProblem* p, int32_t term, const float* params, int64_t C, float* precision,
+                          float* chol, void* ws, size_t wsb, void* st) {
+  if (!precision) return fail(PTM_ERR_NULL, "precision is null");
+  return xtwx_impl<float>(p, term, params, C, nullptr, precision, chol, ws, wsb, st);
+}
+
+int ptm_last_launch_count(void) { return g_launches; }
+const char* ptm_last_error(void) { return g_err.c_str(); }
+const char* ptm_version(void) { return "ptm_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

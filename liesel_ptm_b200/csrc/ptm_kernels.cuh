@@ -1,0 +1,701 @@
+// ptm_kernels.cuh -- device kernels of the PTM hot path (sm_100a).
+//
+// Layout and roles (DESIGN.md has the full story):
+//   * lane = chain.  A CTA owns one group of 32 chains and streams a chunk of
+//     observations through a 3-stage software pipeline.
+//   * "term warps" (one per smooth term) keep that term's nb spline coefficients
+//     gamma_t = Z_t beta_t and the nb gradient accumulators of their 32 chains IN
+//     REGISTERS.  The knot interval of an observation is warp-uniform, so a
+//     switch() on it turns the banded gather/scatter into register-indexed FMAs:
+//     no shared-memory traffic for coefficients, no atomics.
+//   * "trafo warps" do the point-wise part: sigma = exp(eta_sigma), r, the
+//     transformation h (grid-lerp semantics of the reference, evaluated from the
+//     cubic pieces), log-Jacobian, Normal logpdf, and the backward weights.
+//   * eta / dl/deta travel between the two kinds of warps through a double
+//     buffered shared-memory tile [obs][predictor][lane] (conflict-free).
+//   * every (chain group, chunk) work item writes its partial sums to HBM; a small
+//     epilogue kernel reduces them in a fixed order (deterministic) and applies
+//     Z_t', the coefficient-map chain rule and the priors.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ptm_math.cuh"
+
+namespace ptm {
+
+constexpr int kMaxTerms = 24;
+constexpr int kKnotStride = kMaxNbases + 4;  // knots per term in the packed table
+constexpr int kNTW = 4;                      // trafo warps per CTA
+constexpr int kRegSlots = 9;                 // per-lane scalar accumulators
+enum Slot { SL_Z2 = 0, SL_LS, SL_LOGD, SL_GB0, SL_GG0, SL_GVL, SL_GDL, SL_GVR, SL_GDR };
+
+template <typename R>
+struct MainArgs {
+  const R* y;        // [n]
+  const R* X;        // [T][n]
+  const R* knots;    // [T][kKnotStride]
+  const R* grid;     // [1002]
+  const R* Gamma;    // [T][kMaxNbases][C]  gamma_t = Z_t beta_t, chain fastest
+  const R* cc;       // [KK*5 + 6][C]       cubic pieces, boundary values, intercepts
+  R* partial;        // [n_items][NSLOT][32]
+  long long n;
+  long long obs_begin, obs_end;
+  long long chunk_len;
+  int C, CG, M, n_items, NSLOT, KK;
+  int T, T_loc, T_scale, S, Rsub, To;
+  int nb[kMaxTerms];
+  int pred[kMaxTerms];
+  int qidx[kMaxTerms];   // index of the term inside its predictor group
+  int goff[kMaxTerms];   // offset of the term's gamma-gradient block in the slots
+  R inv_dk[kMaxTerms];
+  TrafoScal<R> ts;
+};
+
+// CTA-wide barrier issued from role-specific code (whole warps take one role).
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void term_bar(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// mantissa / exponent split of a positive normal number: x = mant * 2^ex
+__device__ __forceinline__ void split_mant(double x, double& mant, int& ex) {
+  const long long bits = __double_as_longlong(x);
+  ex = (int)((bits >> 52) & 0x7ff) - 1023;
+  mant = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+}
+__device__ __forceinline__ void split_mant(float x, float& mant, int& ex) {
+  const int bits = __float_as_int(x);
+  ex = ((bits >> 23) & 0xff) - 127;
+  mant = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+}
+
+#define PTM_REP29(X)                                                              \
+  X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) \
+  X(15) X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28)
+
+// v += b . g[jj .. jj+3] with a warp-uniform jj: register-indexed via a jump table.
+template <typename R, int NB>
+__device__ __forceinline__ R gather4(const R (&g)[NB], int jj, R b0, R b1, R b2, R b3, R v) {
+#define PTM_FWD_CASE(J)                                        \
+  case J:                                                      \
+    if constexpr (J + 3 < NB) {                                \
+      v = fma(b0, g[J], v);                                    \
+      v = fma(b1, g[J + 1], v);                                \
+      v = fma(b2, g[J + 2], v);                                \
+      v = fma(b3, g[J + 3], v);                                \
+    }                                                          \
+    break;
+  switch (jj) { PTM_REP29(PTM_FWD_CASE) default: break; }
+#undef PTM_FWD_CASE
+  return v;
+}
+
+template <typename R, int NB>
+__device__ __forceinline__ void scatter4(R (&acc)[NB], int jj, R b0, R b1, R b2, R b3, R gv) {
+#define PTM_BWD_CASE(J)                                        \
+  case J:                                                      \
+    if constexpr (J + 3 < NB) {                                \
+      acc[J] = fma(b0, gv, acc[J]);                            \
+      acc[J + 1] = fma(b1, gv, acc[J + 1]);                    \
+      acc[J + 2] = fma(b2, gv, acc[J + 2]);                    \
+      acc[J + 3] = fma(b3, gv, acc[J + 3]);                    \
+    }                                                          \
+    break;
+  switch (jj) { PTM_REP29(PTM_BWD_CASE) default: break; }
+#undef PTM_BWD_CASE
+}
+
+// ------------------------------------------------------------------------------
+// K_main: fused logp (+ gradient) sweep.  blockDim = 32 * (T + kNTW).
+// ------------------------------------------------------------------------------
+template <typename R, int NB, bool GRAD, int MAXTHREADS>
+__global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int T = a.T, To = a.To, KK = a.KK;
+  const int NCC = KK * 5 + 6;
+
+  // ---- shared memory carve-up --------------------------------------------------
+  R* s_cc = reinterpret_cast<R*>(smem_raw);                 // [NCC][32]
+  R* s_gc = s_cc + NCC * 32;                                // [kNTW][KK*5][32]
+  R* s_h = s_gc + (GRAD ? kNTW * KK * 5 * 32 : 0);          // [2][To][2][32]
+  R* s_b = s_h + 2 * To * 2 * 32;                           // [T][3][To][4]
+  R* s_kn = s_b + T * 3 * To * 4;                           // [T][kKnotStride]
+  R* s_red = s_kn + T * kKnotStride;                        // [kNTW][kRegSlots][32]
+  int* s_j = reinterpret_cast<int*>(s_red + kNTW * kRegSlots * 32);  // [T][3][To]
+
+  const bool is_term = warp < T;
+  const int tw = warp - T;  // trafo warp index when !is_term
+  const int term_threads = T * 32;
+
+  // term-warp constants
+  int t_nb = 0, t_pred = 0, t_q = 0, t_Tg = 1;
+  R t_invdk = R(0);
+  const R* t_x = nullptr;
+  if (is_term) {
+    t_nb = a.nb[warp];
+    t_pred = a.pred[warp];
+    t_q = a.qidx[warp];
+    t_Tg = t_pred == 0 ? a.T_loc : a.T_scale;
+    t_invdk = a.inv_dk[warp];
+    t_x = a.X + (long long)warp * a.n;
+    for (int i = lane; i < t_nb + 4; i += 32) s_kn[warp * kKnotStride + i] = a.knots[warp * kKnotStride + i];
+  }
+  const TrafoScal<R> ts = a.ts;
+  const bool has_loc = a.T_loc > 0, has_scale = a.T_scale > 0;
+  __syncthreads();
+
+  for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const int cg = item / a.M;
+    const int mchunk = item - cg * a.M;
+    const long long o_begin = a.obs_begin + (long long)mchunk * a.chunk_len;
+    long long o_end = o_begin + a.chunk_len;
+    if (o_end > a.obs_end) o_end = a.obs_end;
+    const long long len = o_end > o_begin ? o_end - o_begin : 0;
+    const int ntiles = (int)((len + To - 1) / To);
+    int chain = cg * 32 + lane;
+    if (chain >= a.C) chain = a.C - 1;
+
+    R* pout = a.partial + (long long)item * a.NSLOT * 32;
+    if (is_term) {
+      // =========================== term warp ========================================
+      R g[NB];
+      R acc[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        g[j] = (j < t_nb) ? a.Gamma[((long long)warp * kMaxNbases + j) * a.C + chain] : R(0);
+        acc[j] = R(0);
+      }
+      cta_bar();
+      for (int s = 0; s < ntiles + 2; ++s) {
+        // (1) backward of tile s-2: acc += b * dl/deta
+        if (GRAD && s >= 2) {
+          const int tile = s - 2;
+          const long long base = o_begin + (long long)tile * To;
+          const int slot = tile % 3;
+          const R* bp = s_b + ((warp * 3 + slot) * To) * 4;
+          const int* jp = s_j + (warp * 3 + slot) * To;
+          const R* hp = s_h + (((s & 1) * To) * 2 + t_pred) * 32 + lane;
+          const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
+#pragma unroll 2
+          for (int o = 0; o < cnt; ++o) {
+            const R b0 = bp[o * 4 + 0], b1 = bp[o * 4 + 1], b2 = bp[o * 4 + 2], b3 = bp[o * 4 + 3];
+            const int jj = jp[o];
+            const R gv = hp[o * 64];
+            scatter4<R, NB>(acc, jj, b0, b1, b2, b3, gv);
+          }
+        }
+        // (2) stage tile s: knot interval + four basis values per observation
+        if (s < ntiles) {
+          const long long base = o_begin + (long long)s * To;
+          const int slot = s % 3;
+          R* bp = s_b + ((warp * 3 + slot) * To) * 4;
+          int* jp = s_j + (warp * 3 + slot) * To;
+          for (int o = lane; o < To; o += 32) {
+            const long long gi = base + o;
+            if (gi < o_end) {
+              R bb[4];
+              const int jj = basis_window(t_x[gi], s_kn + warp * kKnotStride, t_nb, t_invdk, bb);
+              bp[o * 4 + 0] = bb[0];
+              bp[o * 4 + 1] = bb[1];
+              bp[o * 4 + 2] = bb[2];
+              bp[o * 4 + 3] = bb[3];
+              jp[o] = jj;
+            }
+          }
+          __syncwarp();
+        }
+        term_bar(term_threads);  // all reads of buffer (s&1) done before it is rewritten
+        // (3) forward of tile s: rotate over the S sub-tiles so that the warps of one
+        //     predictor never touch the same sub-tile in the same sub-step
+        for (int sp = 0; sp < a.S; ++sp) {
+          if (sp > 0) term_bar(term_threads);
+          if (s < ntiles) {
+            int bsub = t_q + sp;
+            if (bsub >= a.S) bsub -= a.S;
+            const bool first = (sp == 0) || (t_q == t_Tg - 1 && sp <= a.S - t_Tg);
+            const long long base = o_begin + (long long)s * To;
+            const int slot = s % 3;
+            const R* bp = s_b + ((warp * 3 + slot) * To) * 4;
+            const int* jp = s_j + (warp * 3 + slot) * To;
+            R* hp = s_h + (((s & 1) * To) * 2 + t_pred) * 32 + lane;
+            const int o0 = bsub * a.Rsub;
+            int o1 = o0 + a.Rsub;
+            const long long rem = o_end - base;
+            if (o1 > rem) o1 = (int)rem;
+#pragma unroll 2
+            for (int o = o0; o < o1; ++o) {
+              const R b0 = bp[o * 4 + 0], b1 = bp[o * 4 + 1], b2 = bp[o * 4 + 2], b3 = bp[o * 4 + 3];
+              const int jj = jp[o];
+              R v = first ? R(0) : hp[o * 64];
+              v = gather4<R, NB>(g, jj, b0, b1, b2, b3, v);
+              hp[o * 64] = v;
+            }
+          }
+        }
+        cta_bar();
+      }
+      if (GRAD) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (j < t_nb) pout[(kRegSlots + KK * 5 + a.goff[warp] + j) * 32 + lane] = acc[j];
+      }
+    } else {
+      // =========================== trafo warp =======================================
+      for (int s = tw; s < NCC; s += kNTW) s_cc[s * 32 + lane] = a.cc[(long long)s * a.C + chain];
+      if (GRAD)
+        for (int s = 0; s < KK * 5; ++s) s_gc[(tw * KK * 5 + s) * 32 + lane] = R(0);
+      ChainBoundary<R> cb;
+      make_boundary(ts, a.cc[(long long)(KK * 5 + 0) * a.C + chain],
+                    a.cc[(long long)(KK * 5 + 1) * a.C + chain],
+                    a.cc[(long long)(KK * 5 + 2) * a.C + chain],
+                    a.cc[(long long)(KK * 5 + 3) * a.C + chain], cb);
+      const R beta0 = a.cc[(long long)(KK * 5 + 4) * a.C + chain];
+      const R gamma0 = a.cc[(long long)(KK * 5 + 5) * a.C + chain];
+      const R cLe = cL_of(ts, ts.min_eps);
+      const R cRe = cR_of(ts, ts.max_eps);
+      R a_z2 = R(0), a_ls = R(0), a_pm = R(1), a_gb0 = R(0), a_gg0 = R(0);
+      R a_gvl = R(0), a_gdl = R(0), a_gvr = R(0), a_gdr = R(0);
+      int a_pe = 0;
+      cta_bar();
+      for (int s = 0; s < ntiles + 2; ++s) {
+        const int tile = s - 1;
+        if (tile >= 0 && tile < ntiles) {
+          const long long base = o_begin + (long long)tile * To;
+          R* hb = s_h + (((tile & 1) * To) * 2) * 32 + lane;
+          const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
+          for (int o = tw; o < cnt; o += kNTW) {
+            const R yv = a.y[base + o];
+            R em = beta0, es = gamma0;
+            if (has_loc) em += hb[o * 64];
+            if (has_scale) es += hb[o * 64 + 32];
+            const R einv = exp(-es);
+            const R r = (yv - em) * einv;
+            const int code = region_code(ts, r);
+            R z, d, dzdr, dddr;
+            CoreEval<R> ev;
+            if (code == 2) {
+              int m;
+              R frac;
+              grid_cell(ts, a.grid, r, m, frac);
+              core_locate(ts, m, frac, ev);
+              const R* cp = s_cc + (ev.kk * 5) * 32 + lane;
+              core_eval(ts, cp[0], cp[32], cp[64], cp[96], cp[128], ev);
+              z = ev.z; d = ev.d; dzdr = ev.d; dddr = ev.d2;
+            } else if (code == 1) {
+              const R poly = r * ts.a - R(0.5) * r * r;
+              z = (ts.inv_w * poly + cb.dL * (r - poly * ts.inv_w)) + cb.constL;
+              const R q = (ts.a - r) * ts.inv_w;
+              d = (R(1) - q) * cb.dL + q;
+              dzdr = d; dddr = (cb.dL - R(1)) * ts.inv_w;
+            } else if (code == 3) {
+              const R poly = R(0.5) * r * r - r * ts.b;
+              z = (ts.inv_w * poly + cb.dR * (r - poly * ts.inv_w)) + cb.constR;
+              const R q = (r - ts.b) * ts.inv_w;
+              d = (R(1) - q) * cb.dR + q;
+              dzdr = d; dddr = (R(1) - cb.dR) * ts.inv_w;
+            } else if (code == 0) {
+              z = cb.ztailL - (ts.min_eps - r);
+              d = R(1); dzdr = R(1); dddr = R(0);
+            } else {
+              z = cb.ztailR + (r - ts.max_eps);
+              d = R(1); dzdr = R(1); dddr = R(0);
+            }
+            const R tiny = tiny_of<R>();
+            const bool above = d > tiny;
+            const R dcl = above ? d : tiny;
+            a_z2 = fma(z, z, a_z2);
+            a_ls += es;
+            {
+              R mant; int ex;
+              split_mant(dcl, mant, ex);
+              a_pm *= mant;
+              a_pe += ex;
+            }
+            if (GRAD) {
+              const R lz = -z;
+              const R ld = above ? R(1) / dcl : R(0);
+              const R gr = fma(lz, dzdr, ld * dddr);
+              const R gmu = -gr * einv;
+              const R gls = fma(-gr, r, R(-1));
+              if (has_loc) hb[o * 64] = gmu;
+              if (has_scale) hb[o * 64 + 32] = gls;
+              a_gb0 += gmu;
+              a_gg0 += gls;
+              if (code == 2) {
+                R w[5];
+                core_backward(ts, ev, lz, ld, w);
+                R* gp = s_gc + ((tw * KK + ev.kk) * 5) * 32 + lane;
+                gp[0] += w[0];
+                gp[32] += w[1];
+                gp[64] += w[2];
+                gp[96] += w[3];
+                gp[128] += w[4];
+              } else if (code == 1) {
+                const R q = (ts.a - r) * ts.inv_w;
+                a_gvl += lz;
+                a_gdl += fma(lz, cL_of(ts, r), ld * (R(1) - q));
+              } else if (code == 3) {
+                const R q = (r - ts.b) * ts.inv_w;
+                a_gvr += lz;
+                a_gdr += fma(lz, cR_of(ts, r), ld * (R(1) - q));
+              } else if (code == 0) {
+                a_gvl += lz;
+                a_gdl = fma(lz, cLe, a_gdl);
+              } else {
+                a_gvr += lz;
+                a_gdr = fma(lz, cRe, a_gdr);
+              }
+            }
+          }
+          // renormalise the running mantissa product once per tile
+          {
+            R mant; int ex;
+            split_mant(a_pm, mant, ex);
+            a_pm = mant;
+            a_pe += ex;
+          }
+        }
+        cta_bar();
+      }
+      R* rp = s_red + (tw * kRegSlots) * 32 + lane;
+      rp[SL_Z2 * 32] = a_z2;
+      rp[SL_LS * 32] = a_ls;
+      rp[SL_LOGD * 32] = log(a_pm) + R(a_pe) * R(0.69314718055994530942);
+      rp[SL_GB0 * 32] = a_gb0;
+      rp[SL_GG0 * 32] = a_gg0;
+      rp[SL_GVL * 32] = a_gvl;
+      rp[SL_GDL * 32] = a_gdl;
+      rp[SL_GVR * 32] = a_gvr;
+      rp[SL_GDR * 32] = a_gdr;
+    }
+    // ---- item epilogue: cross-warp sums of the trafo partials to HBM ------------
+    __syncthreads();
+    {
+      const int nreg = GRAD ? kRegSlots : 3;
+      for (int idx = tid; idx < nreg * 32; idx += blockDim.x) {
+        R v = R(0);
+        for (int w = 0; w < kNTW; ++w) v += s_red[w * kRegSlots * 32 + idx];
+        pout[idx] = v;
+      }
+      if (GRAD) {
+        for (int idx = tid; idx < KK * 5 * 32; idx += blockDim.x) {
+          R v = R(0);
+          for (int w = 0; w < kNTW; ++w) v += s_gc[w * KK * 5 * 32 + idx];
+          pout[kRegSlots * 32 + idx] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------
+// K_pre: per-chain prologue.  One block per chain.
+//   gamma_t = Z_t beta_t (gam/var.py:157-162 rewritten as B (Z beta)),
+//   delta = Z_delta delta_z (var.py:112-115), coefficient map (ptm.py:155-230),
+//   cubic pieces + boundary values of h.
+// ------------------------------------------------------------------------------
+template <typename R>
+struct PreArgs {
+  const R* params;   // [C][P]
+  R* Gamma;          // [T][kMaxNbases][C]
+  R* cc;             // [KK*5+6][C]
+  const R* Zall;     // packed Z_t, row-major [nb_t][p_t]
+  const R* Zd;       // [nparam][nparam-1]
+  const TrafoConst<R>* tc;
+  int C, P, T;
+  int nb[kMaxTerms], p[kMaxTerms], zoff[kMaxTerms], boff[kMaxTerms];
+  int dz_off;
+};
+
+template <typename R>
+__global__ void k_pre(const PreArgs<R> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R* s_par = reinterpret_cast<R*>(smem_raw);  // [P]
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < a.P; i += blockDim.x) s_par[i] = a.params[(long long)c * a.P + i];
+  __syncthreads();
+  for (int idx = tid; idx < a.T * kMaxNbases; idx += blockDim.x) {
+    const int t = idx / kMaxNbases, j = idx - t * kMaxNbases;
+    if (j < a.nb[t]) {
+      const R* zr = a.Zall + a.zoff[t] + j * a.p[t];
+      const R* b = s_par + a.boff[t];
+      R v = R(0);
+      for (int k = 0; k < a.p[t]; ++k) v = fma(zr[k], b[k], v);
+      a.Gamma[((long long)t * kMaxNbases + j) * a.C + c] = v;
+    }
+  }
+  if (tid == 0) {
+    const TrafoConst<R>& tc = *a.tc;
+    const int np_ = tc.nparam, KK = tc.KK;
+    R delta[kMaxNparam], e[kMaxNparam], sm[kMaxNparam], vt[kMaxJ];
+    const R* dz = s_par + a.dz_off;
+    for (int j = 0; j < np_; ++j) {
+      R v = R(0);
+      for (int k = 0; k < np_ - 1; ++k) v = fma(a.Zd[j * (np_ - 1) + k], dz[k], v);
+      delta[j] = v;
+    }
+    coef_map_forward(tc, delta, e, sm, vt);
+    R cfirst[5], clast[5];
+    for (int kk = 0; kk < KK; ++kk) {
+      R cq[5];
+      piece_coefs(vt, kk, KK, cq);
+      for (int q = 0; q < 5; ++q) a.cc[(long long)(kk * 5 + q) * a.C + c] = cq[q];
+      if (kk == 0) for (int q = 0; q < 5; ++q) cfirst[q] = cq[q];
+      if (kk == KK - 1) for (int q = 0; q < 5; ++q) clast[q] = cq[q];
+    }
+    a.cc[(long long)(KK * 5 + 0) * a.C + c] = cfirst[0];
+    a.cc[(long long)(KK * 5 + 1) * a.C + c] = cfirst[1] * tc.inv_dk;
+    a.cc[(long long)(KK * 5 + 2) * a.C + c] = ((clast[0] + clast[1]) + clast[2]) + clast[3];
+    a.cc[(long long)(KK * 5 + 3) * a.C + c] = (clast[1] + R(2) * clast[2] + R(3) * clast[3]) * tc.inv_dk;
+    a.cc[(long long)(KK * 5 + 4) * a.C + c] = s_par[0];
+    a.cc[(long long)(KK * 5 + 5) * a.C + c] = s_par[1];
+  }
+}
+
+// ------------------------------------------------------------------------------
+// K_post: fixed-order reduction of the partials + chain rule + priors.
+// One block per chain group.
+// ------------------------------------------------------------------------------
+template <typename R>
+struct PostArgs {
+  const R* params;   // [C][P]
+  const R* partial;  // [CG*M][NSLOT][32]
+  R* logp;           // [C]
+  R* grad;           // [C][P] or null
+  const R* Zall;
+  const R* Kall;     // packed K_t [p_t][p_t]
+  const R* Zd;
+  const TrafoConst<R>* tc;
+  int C, P, T, M, NSLOT, KK;
+  int nb[kMaxTerms], p[kMaxTerms], zoff[kMaxTerms], koff[kMaxTerms], boff[kMaxTerms];
+  int goff[kMaxTerms], rank[kMaxTerms];
+  int dz_off, tau_off, taud_off;
+  long long n_obs;
+  int add_priors;
+};
+
+template <typename R, bool GRAD>
+__global__ void k_post(const PostArgs<R> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R* red = reinterpret_cast<R*>(smem_raw);  // [NSLOT][32]
+  R* s_lp = red + a.NSLOT * 32;             // [32] prior accumulator per chain
+  const int cg = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int KK = a.KK;
+  for (int idx = tid; idx < a.NSLOT * 32; idx += blockDim.x) {
+    R v = R(0);
+    const R* pp = a.partial + ((long long)cg * a.M * a.NSLOT) * 32 + idx;
+    for (int m = 0; m < a.M; ++m) v += pp[(long long)m * a.NSLOT * 32];
+    red[idx] = v;
+  }
+  if (tid < 32) s_lp[tid] = R(0);
+  __syncthreads();
+  const R half_log_2pi = R(0.91893853320467274178);
+
+  // smooth-term priors and gradients: one thread per (lane, term)
+  for (int idx = tid; idx < 32 * a.T; idx += blockDim.x) {
+    const int lane = idx & 31, t = idx >> 5;
+    const int c = cg * 32 + lane;
+    if (c >= a.C) continue;
+    const R* par = a.params + (long long)c * a.P;
+    const R* b = par + a.boff[t];
+    const R* Kt = a.Kall + a.koff[t];
+    const int p = a.p[t];
+    const R tau = par[a.tau_off + t];
+    R quad = R(0);
+    for (int i = 0; i < p; ++i) {
+      R kb = R(0);
+      for (int k = 0; k < p; ++k) kb = fma(Kt[i * p + k], b[k], kb);
+      quad = fma(b[i], kb, quad);
+    }
+    const R it2 = R(1) / (tau * tau);
+    if (a.add_priors) {
+      atomicAdd(&s_lp[lane], -(log(tau) * R(a.rank[t]) + R(0.5) * quad * it2));
+      if (GRAD) a.grad[(long long)c * a.P + a.tau_off + t] = -R(a.rank[t]) / tau + quad * it2 / tau;
+    } else if (GRAD) {
+      a.grad[(long long)c * a.P + a.tau_off + t] = R(0);
+    }
+  }
+  if (GRAD) {
+    // grad beta_t[k] = sum_j Z_t[j][k] Ggamma_t[j] - (K_t beta_t)[k] / tau_t^2
+    for (int t = 0; t < a.T; ++t) {
+      const int p = a.p[t], nb = a.nb[t];
+      const R* Zt = a.Zall + a.zoff[t];
+      const R* Kt = a.Kall + a.koff[t];
+      for (int idx = tid; idx < 32 * p; idx += blockDim.x) {
+        const int lane = idx & 31, k = idx >> 5;
+        const int c = cg * 32 + lane;
+        if (c >= a.C) continue;
+        const R* par = a.params + (long long)c * a.P;
+        const R* gg = red + (kRegSlots + KK * 5 + a.goff[t]) * 32 + lane;
+        R v = R(0);
+        for (int j = 0; j < nb; ++j) v = fma(Zt[j * p + k], gg[j * 32], v);
+        if (a.add_priors) {
+          const R tau = par[a.tau_off + t];
+          const R* b = par + a.boff[t];
+          R kb = R(0);
+          for (int i = 0; i < p; ++i) kb = fma(Kt[k * p + i], b[i], kb);
+          v -= kb / (tau * tau);
+        }
+        a.grad[(long long)c * a.P + a.boff[t] + k] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // transformation block + logp: one thread per chain
+  if (tid < 32) {
+    const int lane = tid;
+    const int c = cg * 32 + lane;
+    if (c < a.C) {
+      const TrafoConst<R>& tc = *a.tc;
+      const int np_ = tc.nparam;
+      const R* par = a.params + (long long)c * a.P;
+      const R* dz = par + a.dz_off;
+      const R taud = par[a.taud_off];
+      R ss = R(0);
+      for (int k = 0; k < np_ - 1; ++k) ss = fma(dz[k], dz[k], ss);
+      R lp = R(-0.5) * red[SL_Z2 * 32 + lane] + red[SL_LOGD * 32 + lane] - red[SL_LS * 32 + lane] -
+             R(a.n_obs) * half_log_2pi;
+      if (a.add_priors) {
+        lp += s_lp[lane];
+        lp += R(-0.5) * ss / (taud * taud) - R(np_ - 1) * (log(taud) + half_log_2pi);
+      }
+      a.logp[c] = lp;
+      if (GRAD) {
+        R* go = a.grad + (long long)c * a.P;
+        go[0] = red[SL_GB0 * 32 + lane];
+        go[1] = red[SL_GG0 * 32 + lane];
+        go[a.taud_off] = a.add_priors ? ss / (taud * taud * taud) - R(np_ - 1) / taud : R(0);
+        // boundary gradients fold into the first / last piece
+        R delta[kMaxNparam], e[kMaxNparam], sm[kMaxNparam], vt[kMaxJ], gvt[kMaxJ], gdelta[kMaxNparam];
+        for (int j = 0; j < np_; ++j) {
+          R v = R(0);
+          for (int k = 0; k < np_ - 1; ++k) v = fma(a.Zd[j * (np_ - 1) + k], dz[k], v);
+          delta[j] = v;
+        }
+        coef_map_forward(tc, delta, e, sm, vt);
+        for (int j = 0; j <= np_; ++j) gvt[j] = R(0);
+        const R gvl = red[SL_GVL * 32 + lane], gdl = red[SL_GDL * 32 + lane];
+        const R gvr = red[SL_GVR * 32 + lane], gdr = red[SL_GDR * 32 + lane];
+        for (int kk = 0; kk < KK; ++kk) {
+          R gc[5];
+          for (int q = 0; q < 5; ++q) gc[q] = red[(kRegSlots + kk * 5 + q) * 32 + lane];
+          if (kk == 0) {
+            gc[0] += gvl;
+            gc[1] += gdl * tc.inv_dk;
+          }
+          if (kk == KK - 1) {
+            gc[0] += gvr;
+            gc[1] += gvr + gdr * tc.inv_dk;
+            gc[2] += gvr + R(2) * gdr * tc.inv_dk;
+            gc[3] += gvr + R(3) * gdr * tc.inv_dk;
+          }
+          piece_coefs_backward(gc, kk, KK, gvt);
+        }
+        coef_map_backward(tc, gvt, e, sm, gdelta);
+        for (int k = 0; k < np_ - 1; ++k) {
+          R v = R(0);
+          for (int j = 0; j < np_; ++j) v = fma(a.Zd[j * (np_ - 1) + k], gdelta[j], v);
+          if (a.add_priors) v -= dz[k] / (taud * taud);
+          go[a.dz_off + k] = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------
+// K1: banded design of one term (test / inspection entry; the fused kernel calls
+// the same device function inline).
+// ------------------------------------------------------------------------------
+template <typename R>
+__global__ void k_basis(const R* __restrict__ x, long long n, const R* __restrict__ knots, int nb,
+                        R inv_dk, int* __restrict__ interval, R* __restrict__ values) {
+  __shared__ R s_kn[kKnotStride];
+  for (int i = threadIdx.x; i < nb + 4; i += blockDim.x) s_kn[i] = knots[i];
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const R xv = x[i];
+    const int j = find_interval(xv, s_kn, nb, inv_dk);
+    R bb[4];
+    bspline4(xv, s_kn, j, bb);
+    interval[i] = j;
+    values[i * 4 + 0] = bb[0];
+    values[i * 4 + 1] = bb[1];
+    values[i * 4 + 2] = bb[2];
+    values[i * 4 + 3] = bb[3];
+  }
+}
+
+// ------------------------------------------------------------------------------
+// h(r), h'(r) for raw shape coefficients delta [C][nparam] (bspline/util.py:91-103).
+// One block per chain; the chain's pieces live in shared memory.
+// ------------------------------------------------------------------------------
+template <typename R>
+__global__ void k_transform(const R* __restrict__ delta, int C, const R* __restrict__ r, long long m,
+                            const TrafoConst<R>* tcp, const R* __restrict__ grid, R* __restrict__ z,
+                            R* __restrict__ dz, int* __restrict__ cell) {
+  __shared__ R s_c[(kMaxJ) * 5];
+  __shared__ ChainBoundary<R> s_cb;
+  const int c = blockIdx.x;
+  const TrafoConst<R>& tc = *tcp;
+  if (threadIdx.x == 0) {
+    R e[kMaxNparam], sm[kMaxNparam], vt[kMaxJ];
+    coef_map_forward(tc, delta + (long long)c * tc.nparam, e, sm, vt);
+    R cl[5] = {0, 0, 0, 0, 0}, cf[5] = {0, 0, 0, 0, 0};
+    for (int kk = 0; kk < tc.KK; ++kk) {
+      R cq[5];
+      piece_coefs(vt, kk, tc.KK, cq);
+      for (int q = 0; q < 5; ++q) s_c[kk * 5 + q] = cq[q];
+      if (kk == 0) for (int q = 0; q < 5; ++q) cf[q] = cq[q];
+      if (kk == tc.KK - 1) for (int q = 0; q < 5; ++q) cl[q] = cq[q];
+    }
+    make_boundary<R>(tc, cf[0], cf[1] * tc.inv_dk, ((cl[0] + cl[1]) + cl[2]) + cl[3],
+                     (cl[1] + R(2) * cl[2] + R(3) * cl[3]) * tc.inv_dk, s_cb);
+  }
+  __syncthreads();
+  const TrafoScal<R> ts = tc;
+  const ChainBoundary<R> cb = s_cb;
+  for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+    const R rv = r[i];
+    const int code = region_code(ts, rv);
+    R zv, dv;
+    int cellv = -1;
+    if (code == 2) {
+      int mi; R frac;
+      grid_cell(ts, grid, rv, mi, frac);
+      CoreEval<R> ev;
+      core_locate(ts, mi, frac, ev);
+      const R* cp = s_c + ev.kk * 5;
+      core_eval(ts, cp[0], cp[1], cp[2], cp[3], cp[4], ev);
+      zv = ev.z; dv = ev.d; cellv = mi + 1;
+    } else if (code == 1) {
+      const R poly = rv * ts.a - R(0.5) * rv * rv;
+      zv = (ts.inv_w * poly + cb.dL * (rv - poly * ts.inv_w)) + cb.constL;
+      const R q = (ts.a - rv) * ts.inv_w;
+      dv = (R(1) - q) * cb.dL + q;
+    } else if (code == 3) {
+      const R poly = R(0.5) * rv * rv - rv * ts.b;
+      zv = (ts.inv_w * poly + cb.dR * (rv - poly * ts.inv_w)) + cb.constR;
+      const R q = (rv - ts.b) * ts.inv_w;
+      dv = (R(1) - q) * cb.dR + q;
+    } else if (code == 0) {
+      zv = cb.ztailL - (ts.min_eps - rv);
+      dv = R(1);
+    } else {
+      zv = cb.ztailR + (rv - ts.max_eps);
+      dv = R(1);
+    }
+    z[(long long)c * m + i] = zv;
+    dz[(long long)c * m + i] = dv;
+    if (cell != nullptr && c == 0) cell[i] = cellv;
+  }
+}
+
+}  // namespace ptm
