@@ -1,0 +1,389 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+``LocScalePTM`` keeps the reference's construction surface
+(model/model.py:279-383: ``LocScalePTM.new_ptm(response, nparam, a, b, ...)``,
+``model.loc += term.f_ig(ps(x, nbases=20, xname="x"))``, ``model.build()``) and
+exposes what the MCMC kernels call on it:
+
+* ``log_prob`` / ``log_prob_and_grad``     -> logprob.py:36-69, 104-140 (``LogProb``,
+  ``FlatLogProb``: log_prob, grad) and iwls_fixed.py:91-116
+* ``GaussianLocCholInfo`` / ``GaussianScaleCholInfo`` -> iwls_proposals.py:13-144
+* ``basis`` / ``transform``                -> Basis.bspline (bspline/approx.py:116-210),
+  dot_and_deriv_n_fullbatch (bspline/util.py:91-103)
+
+All numerics run in the CUDA library through the C ABI (``include/ptm_b200.h``).
+torch is used only for device memory and streams.  Chain states travel as one
+``[C, P]`` array per call -- the layout ``ravel_pytree`` gives the JAX side.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .spline import Basis, PTMKnots, approx_grid, term, trafo_reparam
+
+_NP = {torch.float64: np.float64, torch.float32: np.float32}
+
+
+class _Predictor:
+    """``model.loc`` / ``model.scale``: supports ``+=`` with a term (predictor.py:23-60)."""
+
+    def __init__(self, kind: int, name: str) -> None:
+        self.kind = kind
+        self.name = name
+        self.terms: dict[str, term] = {}
+
+    def __iadd__(self, other):
+        items = other if isinstance(other, (list, tuple)) else [other]
+        for t in items:
+            if not isinstance(t, term):
+                raise TypeError(f"expected a term, got {type(t)}")
+            if t.name in self.terms:
+                raise RuntimeError(f"{self} already contains a term of name {t.name}.")
+            self.terms[t.name] = t
+        return self
+
+
+class LocScalePTM:
+    """Location-scale penalized transformation model, B200 hot path."""
+
+    def __init__(self, response, knots, trafo_lambda: float = 0.1, to_float32: bool = True,
+                 device: str | torch.device = "cuda") -> None:
+        self.to_float32 = to_float32
+        self.dtype = torch.float32 if to_float32 else torch.float64
+        self.np_dtype = _NP[self.dtype]
+        self.response = np.ascontiguousarray(np.asarray(response), dtype=self.np_dtype)
+        self.knots = np.ascontiguousarray(np.asarray(knots), dtype=self.np_dtype)
+        self.nparam = self.knots.shape[0] - 5
+        self.trafo_lambda = float(trafo_lambda)
+        self._loc = _Predictor(_lib.PTM_LOC, "$\\mu$")
+        self._scale = _Predictor(_lib.PTM_SCALE, "$\\sigma$")
+        self.device = torch.device(device)
+        self._handle = None
+        self._ws = None
+        self._ws_chains = 0
+        self.is_built = False
+
+    @classmethod
+    def new_ptm(cls, response, nparam: int = 20, a: float = -4.0, b: float = 4.0,
+                trafo_lambda: float = 0.1, to_float32: bool = True, device="cuda"):
+        """Shortcut for convenient model setup (model/model.py:341-383)."""
+        dtype = np.float32 if to_float32 else np.float64
+        knots = PTMKnots(a, b, nparam=nparam, dtype=dtype)
+        return cls(response, knots.knots, trafo_lambda=trafo_lambda, to_float32=to_float32,
+                   device=device)
+
+    # -- reference surface: model.loc += ..., model.scale += ... ------------------------
+    @property
+    def loc(self):
+        return self._loc
+
+    @loc.setter
+    def loc(self, value):
+        if value is not self._loc:
+            raise ValueError("Cannot overwrite .loc attribute.")
+
+    @property
+    def scale(self):
+        return self._scale
+
+    @scale.setter
+    def scale(self, value):
+        if value is not self._scale:
+            raise ValueError("Cannot overwrite .scale attribute.")
+
+    # -- build: copy the static data into HBM once ---------------------------------------
+    def build(self) -> "LocScalePTM":
+        if self.is_built:
+            raise ValueError("Graph was already built.")
+        lib = _lib.load()
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("liesel_ptm_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        torch.cuda.set_device(self.device)
+        nd = self.np_dtype
+        self.terms = self.all_terms()
+        T = len(self.terms)
+        keep = []  # keep numpy arrays alive during create
+
+        def arr(a, dt=nd):
+            a = np.ascontiguousarray(np.asarray(a), dtype=dt)
+            keep.append(a)
+            return a
+
+        def ptr_array(arrays):
+            pa = (C.c_void_p * max(len(arrays), 1))()
+            for i, a in enumerate(arrays):
+                pa[i] = a.ctypes.data
+            keep.append(pa)
+            return C.cast(pa, C.POINTER(C.c_void_p))
+
+        def i32_array(vals):
+            a = arr(np.asarray(vals, dtype=np.int32).reshape(-1), np.int32)
+            return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+        n = self.response.shape[0]
+        for t, _ in self.terms:
+            if t.basis.x.shape[0] != n:
+                raise ValueError(f"term {t.name}: covariate has {t.basis.x.shape[0]} rows, response {n}")
+        d = _lib.PtmProblemDesc()
+        d.dtype = _lib.PTM_F64 if self.dtype == torch.float64 else _lib.PTM_F32
+        d.n = n
+        d.y = arr(self.response).ctypes.data
+        d.n_terms = T
+        d.x = ptr_array([arr(t.basis.x) for t, _ in self.terms])
+        d.nbases = i32_array([t.basis.nbases for t, _ in self.terms] or [0])
+        d.ncoef = i32_array([t.basis.ncoef for t, _ in self.terms] or [0])
+        d.predictor = i32_array([k for _, k in self.terms] or [0])
+        d.knots = ptr_array([arr(t.basis.knots) for t, _ in self.terms])
+        d.Z = ptr_array([arr(t.basis.Z) for t, _ in self.terms])
+        d.K = ptr_array([arr(t.penalty) for t, _ in self.terms])
+        d.rank = i32_array([t.penalty_rank for t, _ in self.terms] or [0])
+        d.nparam = self.nparam
+        d.trafo_knots = arr(self.knots).ctypes.data
+        self.trafo_Z = trafo_reparam(self.nparam, nd)
+        d.trafo_Z = arr(self.trafo_Z).ctypes.data
+        d.trafo_lambda = self.trafo_lambda
+        self.grid = approx_grid(self.knots)
+        d.trafo_grid = arr(self.grid).ctypes.data
+        h = C.c_void_p()
+        _lib.check(lib.ptm_problem_create(C.byref(d), C.byref(h)))
+        self._handle = h
+        self._lib = lib
+        self.n = n
+        self.num_params = int(lib.ptm_num_params(h))
+        T_ = max(T, 1)
+        b0, g0, dz, td = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        boff, toff = (C.c_int64 * T_)(), (C.c_int64 * T_)()
+        _lib.check(lib.ptm_param_layout(h, C.byref(b0), C.byref(g0), boff, C.byref(dz), toff, C.byref(td)))
+        lib_layout = {
+            "beta0": int(b0.value), "gamma0": int(g0.value),
+            "beta": [int(boff[i]) for i in range(T)], "delta_z": int(dz.value),
+            "tau": [int(toff[i]) for i in range(T)], "tau_delta": int(td.value),
+        }
+        self.layout, P = self.param_layout()
+        if lib_layout != self.layout or P != self.num_params:
+            raise RuntimeError(f"parameter layout mismatch: {lib_layout} vs {self.layout}")
+        self._sfx = "f64" if self.dtype == torch.float64 else "f32"
+        self.is_built = True
+        return self
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                self._lib.ptm_problem_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # -- position <-> flat parameter rows ------------------------------------------------
+    def all_terms(self) -> list[tuple[term, int]]:
+        out = [(t, _lib.PTM_LOC) for t in self._loc.terms.values()]
+        return out + [(t, _lib.PTM_SCALE) for t in self._scale.terms.values()]
+
+    def param_layout(self) -> tuple[dict, int]:
+        """Offsets of one chain's parameter row (see include/ptm_b200.h)."""
+        terms = self.all_terms()
+        off, beta = 2, []
+        for t, _ in terms:
+            beta.append(off)
+            off += t.basis.ncoef
+        dz = off
+        tau0 = dz + self.nparam - 1
+        layout = {"beta0": 0, "gamma0": 1, "beta": beta, "delta_z": dz,
+                  "tau": [tau0 + i for i in range(len(terms))], "tau_delta": tau0 + len(terms)}
+        return layout, tau0 + len(terms) + 1
+
+    def pack(self, beta: Sequence[np.ndarray], delta_z, tau=None, tau_delta=None, beta0=None,
+             gamma0=None) -> np.ndarray:
+        """Assemble a [C, P] parameter array from per-variable arrays (ravel_pytree order)."""
+        L, P = self.param_layout()
+        nterms = len(L["beta"])
+        C_ = np.asarray(delta_z).shape[0]
+        out = np.zeros((C_, P), dtype=self.np_dtype)
+        out[:, L["beta0"]] = 0.0 if beta0 is None else beta0
+        out[:, L["gamma0"]] = 0.0 if gamma0 is None else gamma0
+        for t, b in enumerate(beta):
+            out[:, L["beta"][t]: L["beta"][t] + b.shape[1]] = b
+        out[:, L["delta_z"]: L["delta_z"] + self.nparam - 1] = delta_z
+        if nterms:
+            out[:, L["tau"][0]: L["tau"][0] + nterms] = 1.0 if tau is None else tau
+        out[:, L["tau_delta"]] = 1.0 if tau_delta is None else tau_delta
+        return out
+
+    # -- device plumbing -------------------------------------------------------------------
+    def _workspace(self, n_chains: int) -> torch.Tensor:
+        if self._ws is None or self._ws_chains != n_chains:
+            nbytes = int(self._lib.ptm_workspace_bytes(self._handle, n_chains))
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_chains = n_chains
+        return self._ws
+
+    def _check_params(self, params: torch.Tensor) -> torch.Tensor:
+        if not self.is_built:
+            raise RuntimeError("call build() first")
+        if params.dim() == 1:
+            params = params[None, :]
+        if params.dim() != 2 or params.shape[1] != self.num_params:
+            raise ValueError(f"params must have shape (C, {self.num_params}), got {tuple(params.shape)}")
+        if params.dtype != self.dtype or params.device.type != "cuda":
+            raise TypeError(f"params must be a CUDA tensor of dtype {self.dtype}")
+        return params.contiguous()
+
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def set_shard(self, obs_begin: int, obs_end: int, add_priors: bool = True) -> None:
+        """Observation-axis sharding: this handle evaluates [obs_begin, obs_end) only."""
+        _lib.check(self._lib.ptm_problem_set_shard(self._handle, obs_begin, obs_end, int(add_priors)))
+        self._ws = None
+
+    # -- the operators -----------------------------------------------------------------------
+    def log_prob(self, params: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Model log-density for a batch of chain states [C, P] -> [C]."""
+        params = self._check_params(params)
+        Cn = params.shape[0]
+        ws = self._workspace(Cn)
+        logp = out if out is not None else torch.empty(Cn, dtype=self.dtype, device=self.device)
+        f = getattr(self._lib, f"ptm_logp_{self._sfx}")
+        _lib.check(f(self._handle, params.data_ptr(), Cn, logp.data_ptr(), ws.data_ptr(), ws.numel(),
+                     self._stream()))
+        return logp
+
+    def log_prob_and_grad(self, params: torch.Tensor, out_logp: torch.Tensor | None = None,
+                          out_grad: torch.Tensor | None = None):
+        """value_and_grad of the model log-density: [C, P] -> ([C], [C, P])."""
+        params = self._check_params(params)
+        Cn = params.shape[0]
+        ws = self._workspace(Cn)
+        logp = out_logp if out_logp is not None else torch.empty(Cn, dtype=self.dtype, device=self.device)
+        grad = out_grad if out_grad is not None else torch.empty_like(params)
+        f = getattr(self._lib, f"ptm_logp_grad_{self._sfx}")
+        _lib.check(f(self._handle, params.data_ptr(), Cn, logp.data_ptr(), grad.data_ptr(), ws.data_ptr(),
+                     ws.numel(), self._stream()))
+        return logp, grad
+
+    def log_prob_and_grad_host(self, params_host: np.ndarray):
+        """Same call with HOST buffers: H2D of the chain states, kernels, D2H of logp+grad."""
+        if not hasattr(self, "_pin_in") or self._pin_in.shape != params_host.shape:
+            self._pin_in = torch.empty(params_host.shape, dtype=self.dtype).pin_memory()
+            self._pin_lp = torch.empty(params_host.shape[0], dtype=self.dtype).pin_memory()
+            self._pin_g = torch.empty(params_host.shape, dtype=self.dtype).pin_memory()
+            self._dev_in = torch.empty(params_host.shape, dtype=self.dtype, device=self.device)
+            self._dev_lp = torch.empty(params_host.shape[0], dtype=self.dtype, device=self.device)
+            self._dev_g = torch.empty(params_host.shape, dtype=self.dtype, device=self.device)
+        self._pin_in.numpy()[...] = params_host
+        self._dev_in.copy_(self._pin_in, non_blocking=True)
+        self.log_prob_and_grad(self._dev_in, self._dev_lp, self._dev_g)
+        self._pin_lp.copy_(self._dev_lp, non_blocking=True)
+        self._pin_g.copy_(self._dev_g, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pin_lp.numpy(), self._pin_g.numpy()
+
+    def last_launch_count(self) -> int:
+        return int(self._lib.ptm_last_launch_count())
+
+    def basis(self, term_index: int):
+        """Banded design of a term: (interval [n] int32, values [n, 4])."""
+        interval = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        values = torch.empty((self.n, 4), dtype=self.dtype, device=self.device)
+        f = getattr(self._lib, f"ptm_basis_{self._sfx}")
+        _lib.check(f(self._handle, term_index, interval.data_ptr(), values.data_ptr(), self._stream()))
+        return interval, values
+
+    def transform(self, delta: torch.Tensor, r: torch.Tensor):
+        """h(r), h'(r) for raw shape coefficients delta [C, nparam] or [nparam]
+        (TransformationSpline.dot_and_deriv_n_fullbatch, bspline/util.py:91-103)."""
+        squeeze = delta.dim() == 1
+        d2 = (delta[None, :] if squeeze else delta).contiguous()
+        if d2.dim() != 2 or d2.shape[1] != self.nparam:
+            raise ValueError(f"coef must have shape ({self.nparam},) or (C, {self.nparam})")
+        if r.dim() > 1:
+            raise TypeError("dot_and_deriv_n_fullbatch expects x of shape (n,) or ()")
+        was_scalar = r.dim() == 0
+        rv = r.reshape(-1).contiguous()
+        Cn, m = d2.shape[0], rv.shape[0]
+        z = torch.empty((Cn, m), dtype=self.dtype, device=self.device)
+        dz = torch.empty_like(z)
+        cell = torch.empty(m, dtype=torch.int32, device=self.device)
+        f = getattr(self._lib, f"ptm_transform_{self._sfx}")
+        _lib.check(f(self._handle, d2.data_ptr(), Cn, rv.data_ptr(), m, z.data_ptr(), dz.data_ptr(),
+                     cell.data_ptr(), self._stream()))
+        self.last_cell = cell
+        if squeeze:
+            z, dz = z[0], dz[0]
+        if was_scalar:
+            z, dz = z[..., 0], dz[..., 0]
+        return z, dz
+
+    def xtwx(self, term_index: int, params: torch.Tensor) -> torch.Tensor:
+        params = self._check_params(params)
+        Cn = params.shape[0]
+        p = self.terms[term_index][0].basis.ncoef
+        ws = self._workspace(Cn)
+        out = torch.empty((Cn, p, p), dtype=self.dtype, device=self.device)
+        f = getattr(self._lib, f"ptm_xtwx_{self._sfx}")
+        _lib.check(f(self._handle, term_index, params.data_ptr(), Cn, out.data_ptr(), ws.data_ptr(),
+                     ws.numel(), self._stream()))
+        return out
+
+    def precision(self, term_index: int, params: torch.Tensor, with_chol: bool = True):
+        params = self._check_params(params)
+        Cn = params.shape[0]
+        p = self.terms[term_index][0].basis.ncoef
+        ws = self._workspace(Cn)
+        P = torch.empty((Cn, p, p), dtype=self.dtype, device=self.device)
+        L = torch.empty_like(P) if with_chol else None
+        f = getattr(self._lib, f"ptm_loc_precision_{self._sfx}")
+        _lib.check(f(self._handle, term_index, params.data_ptr(), Cn, P.data_ptr(),
+                     L.data_ptr() if with_chol else None, ws.data_ptr(), ws.numel(), self._stream()))
+        return P, L
+
+
+class FlatLogProb:
+    """``FlatLogProb`` of the reference (logprob.py:72-140) over the fused operator:
+    ``log_prob(flat_position)``, ``grad(flat_position)`` with flat positions [C, P]."""
+
+    def __init__(self, model: LocScalePTM) -> None:
+        self.model = model
+
+    def __call__(self, flat_position: torch.Tensor) -> torch.Tensor:
+        return self.log_prob(flat_position)
+
+    def log_prob(self, flat_position: torch.Tensor) -> torch.Tensor:
+        return self.model.log_prob(flat_position)
+
+    def grad(self, flat_position: torch.Tensor) -> torch.Tensor:
+        return self.model.log_prob_and_grad(flat_position)[1]
+
+    def value_and_grad(self, flat_position: torch.Tensor):
+        return self.model.log_prob_and_grad(flat_position)
+
+
+class GaussianLocCholInfo:
+    """iwls_proposals.py:13-89: ``chol_info_fn`` provider for a location term."""
+
+    def __init__(self, model: LocScalePTM, term_index: int) -> None:
+        self.model = model
+        self.term_index = term_index
+
+    @classmethod
+    def from_smooth(cls, smooth: term, model: LocScalePTM):
+        for i, (t, _) in enumerate(model.terms):
+            if t is smooth:
+                return cls(model, i)
+        raise ValueError(f"{smooth.name} is not a term of the model")
+
+    def precision(self, params: torch.Tensor) -> torch.Tensor:
+        return self.model.precision(self.term_index, params, with_chol=False)[0]
+
+    def chol_info(self, params: torch.Tensor) -> torch.Tensor:
+        return self.model.precision(self.term_index, params, with_chol=True)[1]
+
+
+GaussianScaleCholInfo = GaussianLocCholInfo  # W == 2 is selected by the term's predictor

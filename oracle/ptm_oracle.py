@@ -479,6 +479,16 @@ def ps(x, nbases, knots=None, predictor="loc", dtype=np.float64):
     )
 
 
+def term_from_reparam(x, knots, Z, K, rank, predictor="loc"):
+    """PSplineTerm from reparameterisation DATA (Z, K) -- the null-space basis that
+    constraint.py:58-76 picks is LAPACK-dependent, so parity tests hand the oracle the
+    same Z / K the kernels receive and only the dense design B(x) @ Z is rebuilt here."""
+    x = np.asarray(x)
+    B = basis_matrix(x, knots, 3, outer_ok=False)
+    return PSplineTerm(x=x, knots=np.asarray(knots), Z=np.asarray(Z), K=np.asarray(K), rank=int(rank),
+                       design=(B @ Z).astype(x.dtype), predictor=predictor)
+
+
 def trafo_Z(nparam, dtype=np.float64):
     """var.py:164-224 (new_rw1_sumzero) then PTMCoef.__init__ 45-74: Z = Z_rw1 @ Z2.
 
