@@ -254,7 +254,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
     b += (size_t)ptm::kNTW * pr->KK * 5 * 32 * sizeof(R);
     b += (size_t)2 * To * 2 * 32 * sizeof(R);
     b += (size_t)T * 3 * To * 4 * sizeof(R);
-    b += (size_t)T * ptm::kKnotStride * sizeof(R);
+    b += (size_t)T * 4 * ptm::kKnotStride * sizeof(R);
     b += (size_t)ptm::kNTW * ptm::kRegSlots * 32 * sizeof(R);
     b += (size_t)T * 3 * To * sizeof(int);
     return b;
@@ -284,13 +284,20 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   return pl;
 }
 
-template <typename R, int NB, bool GRAD>
-int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
-  auto kern = ptm::k_main<R, NB, GRAD, 512>;
+template <typename R, int NB, bool GRAD, int MAXT>
+int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
+  auto kern = ptm::k_main<R, NB, GRAD, MAXT>;
   PTM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_main));
   kern<<<pl.grid, 32 * (T + ptm::kNTW), pl.smem_main, st>>>(a);
   PTM_CUDA(cudaGetLastError());
   return PTM_OK;
+}
+
+// Up to 10 terms the CTA has <= 448 threads, which leaves 144 registers per thread.
+template <typename R, int NB, bool GRAD>
+int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
+  if (32 * (T + ptm::kNTW) <= 448) return launch_main_t<R, NB, GRAD, 448>(a, pl, T, st);
+  return launch_main_t<R, NB, GRAD, 512>(a, pl, T, st);
 }
 
 template <typename R>

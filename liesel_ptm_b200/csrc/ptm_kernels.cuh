@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "ptm_math.cuh"
+#include "ptm_dispatch.cuh"
 
 namespace ptm {
 
@@ -105,6 +106,37 @@ __device__ __forceinline__ void scatter4(R (&acc)[NB], int jj, R b0, R b1, R b2,
 #undef PTM_BWD_CASE
 }
 
+// Generic (C++ switch) dispatch; ptm_dispatch.cuh specialises the hot shapes with a
+// single PTX jump table.
+template <typename R, int NB>
+struct Dispatch {
+  static constexpr bool kAsm = false;
+  static __device__ __forceinline__ R gather(const R (&g)[NB], int jj, R b0, R b1, R b2, R b3, R v) {
+    return gather4<R, NB>(g, jj, b0, b1, b2, b3, v);
+  }
+  static __device__ __forceinline__ void scatter(R (&acc)[NB], int jj, R b0, R b1, R b2, R b3, R gv) {
+    scatter4<R, NB>(acc, jj, b0, b1, b2, b3, gv);
+  }
+};
+
+// 4 consecutive staged basis values (16-byte aligned): LDS.128 broadcasts
+__device__ __forceinline__ void load4(const double* p, double& b0, double& b1, double& b2, double& b3) {
+  const double2 lo = *reinterpret_cast<const double2*>(p);
+  const double2 hi = *reinterpret_cast<const double2*>(p + 2);
+  b0 = lo.x; b1 = lo.y; b2 = hi.x; b3 = hi.y;
+}
+__device__ __forceinline__ void load4(const float* p, float& b0, float& b1, float& b2, float& b3) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
+}
+__device__ __forceinline__ void store4(double* p, const double (&b)[4]) {
+  *reinterpret_cast<double2*>(p) = make_double2(b[0], b[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(b[2], b[3]);
+}
+__device__ __forceinline__ void store4(float* p, const float (&b)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(b[0], b[1], b[2], b[3]);
+}
+
 // ------------------------------------------------------------------------------
 // K_main: fused logp (+ gradient) sweep.  blockDim = 32 * (T + kNTW).
 // ------------------------------------------------------------------------------
@@ -122,8 +154,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   R* s_gc = s_cc + NCC * 32;                                // [kNTW][KK*5][32]
   R* s_h = s_gc + (GRAD ? kNTW * KK * 5 * 32 : 0);          // [2][To][2][32]
   R* s_b = s_h + 2 * To * 2 * 32;                           // [T][3][To][4]
-  R* s_kn = s_b + T * 3 * To * 4;                           // [T][kKnotStride]
-  R* s_red = s_kn + T * kKnotStride;                        // [kNTW][kRegSlots][32]
+  R* s_kn = s_b + T * 3 * To * 4;                           // [T][4][kKnotStride] knots + reciprocals
+  R* s_red = s_kn + T * 4 * kKnotStride;                    // [kNTW][kRegSlots][32]
   int* s_j = reinterpret_cast<int*>(s_red + kNTW * kRegSlots * 32);  // [T][3][To]
 
   const bool is_term = warp < T;
@@ -141,7 +173,14 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
     t_Tg = t_pred == 0 ? a.T_loc : a.T_scale;
     t_invdk = a.inv_dk[warp];
     t_x = a.X + (long long)warp * a.n;
-    for (int i = lane; i < t_nb + 4; i += 32) s_kn[warp * kKnotStride + i] = a.knots[warp * kKnotStride + i];
+    R* kn = s_kn + warp * 4 * kKnotStride;
+    const R* gk = a.knots + warp * kKnotStride;
+    for (int i = lane; i < t_nb + 4; i += 32) {
+      kn[i] = gk[i];
+      kn[kKnotStride + i] = i + 1 < t_nb + 4 ? R(1) / (gk[i + 1] - gk[i]) : R(0);
+      kn[2 * kKnotStride + i] = i + 2 < t_nb + 4 ? R(1) / (gk[i + 2] - gk[i]) : R(0);
+      kn[3 * kKnotStride + i] = i + 3 < t_nb + 4 ? R(1) / (gk[i + 3] - gk[i]) : R(0);
+    }
   }
   const TrafoScal<R> ts = a.ts;
   const bool has_loc = a.T_loc > 0, has_scale = a.T_scale > 0;
@@ -180,11 +219,10 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
           const R* hp = s_h + (((s & 1) * To) * 2 + t_pred) * 32 + lane;
           const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
 #pragma unroll 2
-          for (int o = 0; o < cnt; ++o) {
-            const R b0 = bp[o * 4 + 0], b1 = bp[o * 4 + 1], b2 = bp[o * 4 + 2], b3 = bp[o * 4 + 3];
-            const int jj = jp[o];
-            const R gv = hp[o * 64];
-            scatter4<R, NB>(acc, jj, b0, b1, b2, b3, gv);
+          for (int o = 0; o < cnt; ++o, bp += 4, ++jp, hp += 64) {
+            R b0, b1, b2, b3;
+            load4(bp, b0, b1, b2, b3);
+            Dispatch<R, NB>::scatter(acc, *jp, b0, b1, b2, b3, *hp);
           }
         }
         // (2) stage tile s: knot interval + four basis values per observation
@@ -197,11 +235,10 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             const long long gi = base + o;
             if (gi < o_end) {
               R bb[4];
-              const int jj = basis_window(t_x[gi], s_kn + warp * kKnotStride, t_nb, t_invdk, bb);
-              bp[o * 4 + 0] = bb[0];
-              bp[o * 4 + 1] = bb[1];
-              bp[o * 4 + 2] = bb[2];
-              bp[o * 4 + 3] = bb[3];
+              const R* kn = s_kn + warp * 4 * kKnotStride;
+              const int jj = basis_window_fast(t_x[gi], kn, kn + kKnotStride, kn + 2 * kKnotStride,
+                                               kn + 3 * kKnotStride, t_nb, t_invdk, bb);
+              store4(bp + o * 4, bb);
               jp[o] = jj;
             }
           }
@@ -225,13 +262,23 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             int o1 = o0 + a.Rsub;
             const long long rem = o_end - base;
             if (o1 > rem) o1 = (int)rem;
+            bp += o0 * 4;
+            jp += o0;
+            hp += o0 * 64;
+            if (first) {
 #pragma unroll 2
-            for (int o = o0; o < o1; ++o) {
-              const R b0 = bp[o * 4 + 0], b1 = bp[o * 4 + 1], b2 = bp[o * 4 + 2], b3 = bp[o * 4 + 3];
-              const int jj = jp[o];
-              R v = first ? R(0) : hp[o * 64];
-              v = gather4<R, NB>(g, jj, b0, b1, b2, b3, v);
-              hp[o * 64] = v;
+              for (int o = o0; o < o1; ++o, bp += 4, ++jp, hp += 64) {
+                R b0, b1, b2, b3;
+                load4(bp, b0, b1, b2, b3);
+                *hp = Dispatch<R, NB>::gather(g, *jp, b0, b1, b2, b3, R(0));
+              }
+            } else {
+#pragma unroll 2
+              for (int o = o0; o < o1; ++o, bp += 4, ++jp, hp += 64) {
+                R b0, b1, b2, b3;
+                load4(bp, b0, b1, b2, b3);
+                *hp = Dispatch<R, NB>::gather(g, *jp, b0, b1, b2, b3, *hp);
+              }
             }
           }
         }

@@ -64,6 +64,8 @@ class LocScalePTM:
         self._loc = _Predictor(_lib.PTM_LOC, "$\\mu$")
         self._scale = _Predictor(_lib.PTM_SCALE, "$\\sigma$")
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self._handle = None
         self._ws = None
         self._ws_chains = 0
