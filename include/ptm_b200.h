@@ -167,6 +167,13 @@ int ptm_loc_precision_f32(const PtmProblem* prob, int32_t term, const float* par
 /* Number of kernels the last logp / logp_grad call on this thread launched. */
 int ptm_last_launch_count(void);
 
+/* Measurement hook (bench.py): when enabled, logp / logp_grad calls on this thread
+ * record CUDA events around the prologue, the fused sweep and the epilogue on the
+ * caller's stream.  ptm_last_kernel_ms() synchronises on the last event and returns
+ * the three durations in milliseconds.  Off by default (no events, no sync). */
+int ptm_profile_enable(int on);
+int ptm_last_kernel_ms(float* pre_ms, float* main_ms, float* post_ms);
+
 const char* ptm_last_error(void);
 const char* ptm_version(void);
 

@@ -29,7 +29,8 @@ SYMBOLS = [
     "ptm_logp_f64", "ptm_logp_f32", "ptm_logp_grad_f64", "ptm_logp_grad_f32",
     "ptm_basis_f64", "ptm_basis_f32", "ptm_transform_f64", "ptm_transform_f32",
     "ptm_xtwx_f64", "ptm_xtwx_f32", "ptm_loc_precision_f64", "ptm_loc_precision_f32",
-    "ptm_last_launch_count", "ptm_last_error", "ptm_version",
+    "ptm_last_launch_count", "ptm_profile_enable", "ptm_last_kernel_ms", "ptm_last_error",
+    "ptm_version",
 ]
 
 
@@ -108,6 +109,10 @@ def load() -> C.CDLL:
         f.argtypes = [vp, i32, vp, i64, vp, vp, vp, sz, vp]
         f.restype = C.c_int
     lib.ptm_last_launch_count.restype = C.c_int
+    lib.ptm_profile_enable.argtypes = [C.c_int]
+    lib.ptm_profile_enable.restype = C.c_int
+    lib.ptm_last_kernel_ms.argtypes = [C.POINTER(C.c_float)] * 3
+    lib.ptm_last_kernel_ms.restype = C.c_int
     lib.ptm_last_error.restype = C.c_char_p
     lib.ptm_version.restype = C.c_char_p
     _lib = lib

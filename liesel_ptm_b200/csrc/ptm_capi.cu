@@ -20,6 +20,8 @@ namespace {
 
 thread_local std::string g_err;
 thread_local int g_launches = 0;
+thread_local int g_profile = 0;
+thread_local cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -328,9 +330,11 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   for (int t = 0; t < pr->T; ++t) {
     pa.nb[t] = pr->nb[t]; pa.p[t] = pr->p[t]; pa.zoff[t] = pr->zoff[t]; pa.boff[t] = pr->boff[t];
   }
+  if (g_profile) PTM_CUDA(cudaEventRecord(g_ev[0], st));
   ptm::k_pre<R><<<(unsigned)C, 128, pr->P * sizeof(R), st>>>(pa);
   PTM_CUDA(cudaGetLastError());
   ++g_launches;
+  if (g_profile) PTM_CUDA(cudaEventRecord(g_ev[1], st));
 
   ptm::MainArgs<R> ma;
   memset(&ma, 0, sizeof ma);
@@ -362,6 +366,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
     rc = want_grad ? launch_main<R, 32, true>(ma, pl, pr->T, st) : launch_main<R, 32, false>(ma, pl, pr->T, st);
   if (rc != PTM_OK) return rc;
   ++g_launches;
+  if (g_profile) PTM_CUDA(cudaEventRecord(g_ev[2], st));
 
   ptm::PostArgs<R> po;
   memset(&po, 0, sizeof po);
@@ -389,6 +394,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   }
   PTM_CUDA(cudaGetLastError());
   ++g_launches;
+  if (g_profile) PTM_CUDA(cudaEventRecord(g_ev[3], st));
   return PTM_OK;
 }
 
@@ -595,6 +601,26 @@ int ptm_loc_precision_f32(const PtmProblem* p, int32_t term, const float* params
 }
 
 int ptm_last_launch_count(void) { return g_launches; }
+
+int ptm_profile_enable(int on) {
+  if (on && !g_ev[0])
+    for (int i = 0; i < 4; ++i) PTM_CUDA(cudaEventCreate(&g_ev[i]));
+  g_profile = on ? 1 : 0;
+  return PTM_OK;
+}
+
+int ptm_last_kernel_ms(float* pre_ms, float* main_ms, float* post_ms) {
+  if (!g_ev[0]) return fail(PTM_ERR_SHAPE, "profiling was never enabled");
+  PTM_CUDA(cudaEventSynchronize(g_ev[3]));
+  float a = 0, b = 0, c = 0;
+  PTM_CUDA(cudaEventElapsedTime(&a, g_ev[0], g_ev[1]));
+  PTM_CUDA(cudaEventElapsedTime(&b, g_ev[1], g_ev[2]));
+  PTM_CUDA(cudaEventElapsedTime(&c, g_ev[2], g_ev[3]));
+  if (pre_ms) *pre_ms = a;
+  if (main_ms) *main_ms = b;
+  if (post_ms) *post_ms = c;
+  return PTM_OK;
+}
 const char* ptm_last_error(void) { return g_err.c_str(); }
 const char* ptm_version(void) { return "ptm_b200 0.1 (sm_100a)"; }
 

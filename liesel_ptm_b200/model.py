@@ -290,6 +290,15 @@ class LocScalePTM:
     def last_launch_count(self) -> int:
         return int(self._lib.ptm_last_launch_count())
 
+    def profile(self, on: bool) -> None:
+        """Measurement hook: record CUDA events around the three kernels of each call."""
+        _lib.check(self._lib.ptm_profile_enable(int(on)))
+
+    def last_kernel_ms(self) -> tuple[float, float, float]:
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _lib.check(self._lib.ptm_last_kernel_ms(C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def basis(self, term_index: int):
         """Banded design of a term: (interval [n] int32, values [n, 4])."""
         interval = torch.empty(self.n, dtype=torch.int32, device=self.device)
