@@ -596,7 +596,7 @@ class PTMModel:
         return out
 
     # --- reverse mode (hand-derived; same DECLARED derivatives as approx.py:498-520)
-    def logp_and_grad(self, st: ChainState):
+    def logp_and_grad(self, st: ChainState, add_priors: bool = True):
         """Returns logp (C,) and a dict of gradients with the ChainState layout."""
         C = st.tau.shape[0]
         sp = self.spline
@@ -613,7 +613,7 @@ class PTMModel:
         for c in range(C):
             f = self.loglik_terms(st, c)
             r, z, d, theta = f["r"], f["z"], f["d"], f["theta"]
-            logp[c] = np.sum(f["ll"]) + self.prior(st, c)
+            logp[c] = np.sum(f["ll"]) + (self.prior(st, c) if add_priors else 0.0)
             code = sp.region_code(r)
             core = code == 2
             lz = -z  # dl/dz
@@ -667,13 +667,14 @@ class PTMModel:
             sm = wts * np.exp(delta - np.max(delta))
             sm = sm / np.sum(sm)
             g_delta = e * g_e - sm * np.sum(e * g_e)
-            g_dz[c] = self.Zd.T @ g_delta - st.delta_z[c] / st.tau_delta[c] ** 2
-            g_taud[c] = np.sum(st.delta_z[c] ** 2) / st.tau_delta[c] ** 3 - (self.nparam - 1) / st.tau_delta[c]
+            pr = 1.0 if add_priors else 0.0
+            g_dz[c] = self.Zd.T @ g_delta - pr * st.delta_z[c] / st.tau_delta[c] ** 2
+            g_taud[c] = pr * (np.sum(st.delta_z[c] ** 2) / st.tau_delta[c] ** 3 - (self.nparam - 1) / st.tau_delta[c])
             for t, term in enumerate(self.terms):
                 ge = g_mu if term.predictor == "loc" else g_ls
                 bt, tau = st.beta[t][c], st.tau[c, t]
-                g_beta[t][c] = term.design.T @ ge - (term.K @ bt) / tau**2
-                g_tau[c, t] = -term.rank / tau + (bt @ term.K @ bt) / tau**3
+                g_beta[t][c] = term.design.T @ ge - pr * (term.K @ bt) / tau**2
+                g_tau[c, t] = pr * (-term.rank / tau + (bt @ term.K @ bt) / tau**3)
             g_b0[c] = np.sum(g_mu)
             g_g0[c] = np.sum(g_ls)
         return logp, dict(beta=g_beta, tau=g_tau, delta_z=g_dz, tau_delta=g_taud, beta0=g_b0, gamma0=g_g0)
@@ -841,6 +842,7 @@ def synth_state(terms, nparam, C, seed=1, dtype=np.float64, amp=0.1):
     beta = []
     for t in terms:
         rms = np.sqrt(np.mean(np.asarray(t.design, dtype=np.float64) ** 2, axis=0))
+        rms = np.where(rms > 1e-8, rms, 1.0)
         b = amp * rng.normal(size=(C, t.p)) / (rms * np.sqrt(t.p))
         beta.append(b.astype(dtype))
     T = len(terms)

@@ -1,0 +1,56 @@
+"""Load a golden logp fixture and rebuild the model / oracle objects from it."""
+
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+import liesel_ptm_b200 as lp
+from oracle import ptm_oracle as o
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def model_from_fixture(d, dtype=np.float64, device="cuda:0"):
+    """Product model built from the fixture's reparameterisation DATA (Z, K, knots)."""
+    model = lp.LocScalePTM.new_ptm(d["y"].astype(dtype), nparam=int(d["nparam"]),
+                                   to_float32=(np.dtype(dtype) == np.float32), device=device)
+    for t in range(int(d["n_terms"])):
+        Z = d[f"Z{t}"].astype(dtype)
+        basis = lp.Basis(x=d[f"x{t}"].astype(dtype), xname=f"x{t}", knots=d[f"knots{t}"].astype(dtype),
+                         Z=np.ascontiguousarray(Z), penalty=np.ascontiguousarray(d[f"K{t}"].astype(dtype)),
+                         nbases=Z.shape[0])
+        tm = lp.term.f_ig(basis)
+        tm.penalty_rank = int(d[f"rank{t}"])
+        if int(d[f"pred{t}"]) == 0:
+            model.loc += tm
+        else:
+            model.scale += tm
+    return model
+
+
+def oracle_from_fixture(d):
+    terms = [
+        o.term_from_reparam(d[f"x{t}"], d[f"knots{t}"], d[f"Z{t}"], d[f"K{t}"], int(d[f"rank{t}"]),
+                            "loc" if int(d[f"pred{t}"]) == 0 else "scale")
+        for t in range(int(d["n_terms"]))
+    ]
+    om = o.PTMModel(d["y"], terms, nparam=int(d["nparam"]))
+    om.Zd = d["trafo_Z"]
+    return om
+
+
+def state_from_params(om, params, layout):
+    T = len(om.terms)
+    L = layout
+    return o.ChainState(
+        beta=[params[:, L["beta"][t]: L["beta"][t] + om.terms[t].p] for t in range(T)],
+        tau=params[:, L["tau"][0]: L["tau"][0] + T] if T else np.zeros((params.shape[0], 0)),
+        delta_z=params[:, L["delta_z"]: L["delta_z"] + om.nparam - 1],
+        tau_delta=params[:, L["tau_delta"]], beta0=params[:, L["beta0"]], gamma0=params[:, L["gamma0"]],
+    )

@@ -37,7 +37,7 @@ def rel_err(a, b):
 def build_case(n=500, n_loc=2, n_scale=1, nbases=12, nparam=20, C=3, dtype=np.float64, seed=0,
                build=True, y_override=None, amp=0.1, beta0=0.05, gamma0=-0.03, tau=None,
                nbases_list=None, device="cuda:0") -> Case:
-    y, X = o.synth_data(max(n, 1), n_loc, n_scale, seed=seed, dtype=dtype)
+    y, X = o.synth_data(max(n, 64), n_loc, n_scale, seed=seed, dtype=dtype)
     y, X = y[:n], X[:, :n]
     if y_override is not None:
         y = y_override(y)

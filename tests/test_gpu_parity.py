@@ -79,3 +79,167 @@ def test_xtwx_and_precision():
         P, _ = case.model.precision(t, params)
         _, ref_P = case.omodel.scale_precision(case.state, t)
         assert rel_err(P.cpu().numpy(), ref_P) < 1e-11
+
+
+# ---------------------------------------------------------------------------------------
+# golden fixtures (committed inputs / outputs) through the CUDA path
+# ---------------------------------------------------------------------------------------
+from tests import golden_io  # noqa: E402
+
+GOLDEN_LOGP = ["n1_c1", "n7_c3", "n100_c1", "n4097_c3", "nan_in_y", "far_tails", "xtwx_nb20", "xtwx_nb30"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_LOGP)
+def test_golden_logp_grad_f64(name):
+    d = golden_io.load(f"logp_{name}.npz")
+    model = golden_io.model_from_fixture(d).build()
+    params = torch.from_numpy(d["params"]).cuda()
+    logp, grad = model.log_prob_and_grad(params)
+    lp_only = model.log_prob(params)
+    torch.cuda.synchronize()
+    assert rel_err(logp.cpu().numpy(), d["logp"]) < TOL64
+    assert rel_err(lp_only.cpu().numpy(), d["logp"]) < TOL64
+    assert rel_err(grad.cpu().numpy(), d["grad"]) < TOL64
+    if name == "nan_in_y":  # NaN in y => NaN logp, like dist.py:340-343
+        assert np.isnan(logp.cpu().numpy()).all()
+    if name.startswith("xtwx"):
+        x = model.xtwx(0, params).cpu().numpy()
+        P, L = model.precision(0, params)
+        assert rel_err(x, d["xtwx"]) < 1e-11
+        assert rel_err(P.cpu().numpy(), d["precision"]) < 1e-11
+        assert rel_err(L.cpu().numpy(), d["chol"]) < 1e-9
+
+
+def test_golden_basis_bit_exact():
+    d = golden_io.load("basis_nb20.npz")
+    import liesel_ptm_b200 as lp
+
+    x = d["x"]
+    model = lp.LocScalePTM.new_ptm(np.zeros_like(x), nparam=20, to_float32=False, device="cuda:0")
+    Z = np.eye(20)
+    model.loc += lp.term.f_ig(lp.Basis(x=x, xname="x", knots=d["knots"], Z=Z, penalty=Z, nbases=20))
+    model.build()
+    interval, values = model.basis(0)
+    interval, values = interval.cpu().numpy(), values.cpu().numpy()
+    assert np.array_equal(interval, d["interval"])
+    dense = np.zeros((x.shape[0], 21))
+    for m in range(4):
+        dense[np.arange(x.shape[0]), interval - 3 + m] = values[:, m]
+    assert np.array_equal(dense[:, :20], d["dense"])
+
+
+def test_golden_trafo_cells_bit_exact():
+    """grid-cell indices on / next to every grid point and region boundary: bit-exact;
+    h, h' within 1e-13 absolute."""
+    t = golden_io.load("trafo_nparam20.npz")
+    case = build_case(n=8, n_loc=1, n_scale=0, nbases=8, nparam=20, C=1)
+    z, dz = case.model.transform(torch.from_numpy(t["delta"]).cuda(), torch.from_numpy(t["r"]).cuda())
+    cell = case.model.last_cell.cpu().numpy()
+    assert np.array_equal(cell, t["cell"])
+    assert np.max(np.abs(z.cpu().numpy() - t["z"])) < 2e-13
+    assert np.max(np.abs(dz.cpu().numpy() - t["d"])) < 2e-12
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's own property tests, on the CUDA path
+# ---------------------------------------------------------------------------------------
+class TestReferenceProperties:
+    def setup_method(self):
+        self.case = build_case(n=8, n_loc=1, n_scale=0, nbases=8, nparam=10, C=1)
+        self.coef = torch.from_numpy(np.random.default_rng(1).normal(size=10)).cuda()
+
+    @pytest.mark.parametrize("m", [300, 10_000])
+    def test_monotone_no_nan(self, m):
+        """tests/test_bspline/test_ptm.py:27-57."""
+        x = torch.linspace(-8.0, 8.0, m, dtype=torch.float64).cuda()
+        fx, fxd = self.case.model.transform(self.coef, x)
+        assert fx.shape == x.shape and fxd.shape == x.shape
+        assert not torch.isnan(fx).any() and not torch.isnan(fxd).any()
+        assert torch.all(fxd > 0.0)
+        assert torch.all(torch.diff(fx) > 0.0)
+
+    def test_scalar_x(self):
+        fx, fxd = self.case.model.transform(self.coef, torch.tensor(1.0, dtype=torch.float64).cuda())
+        assert fx.shape == () and fxd.shape == () and fxd > 0
+
+    def test_identity_at_zero(self):
+        """tests/test_predictor.py:14-22."""
+        x = torch.linspace(-8.0, 8.0, 400, dtype=torch.float64).cuda()
+        fx, fxd = self.case.model.transform(torch.zeros(10, dtype=torch.float64).cuda(), x)
+        assert torch.max(torch.abs(fx - x)) < 5e-5
+        assert torch.max(torch.abs(fxd - 1.0)) < 1e-12
+
+    def test_fullbatch_rejects_batched(self):
+        """tests/test_bspline/test_ptm.py:335-350."""
+        with pytest.raises(TypeError):
+            self.case.model.transform(self.coef, torch.zeros((4, 200), dtype=torch.float64).cuda())
+        with pytest.raises(ValueError):
+            self.case.model.transform(torch.zeros((3, 11), dtype=torch.float64).cuda(),
+                                      torch.zeros(5, dtype=torch.float64).cuda())
+
+
+def test_covariate_outside_knots_raises():
+    import liesel_ptm_b200 as lp
+    from liesel_ptm_b200._lib import PtmError
+
+    x = np.linspace(-2, 2, 50)
+    knots = lp.equidistant_knots(x, 10)
+    Z = np.eye(10)
+    bad = x.copy()
+    bad[7] = 5.0
+    model = lp.LocScalePTM.new_ptm(np.zeros(50), nparam=20, to_float32=False, device="cuda:0")
+    model.loc += lp.term.f_ig(lp.Basis(x=bad, xname="x", knots=knots, Z=Z, penalty=Z, nbases=10))
+    with pytest.raises(PtmError, match="not inside the range of interior knots"):
+        model.build()
+
+
+def test_shapes_no_terms_and_mixed_nbases():
+    """intercept-only model; terms with different nbases; nbases 30 (NB=32 kernel)."""
+    for kw in (dict(n_loc=0, n_scale=0), dict(n_loc=1, n_scale=0), dict(n_loc=0, n_scale=2),
+               dict(n_loc=3, n_scale=1, nbases_list=[8, 20, 13, 6]), dict(n_loc=2, n_scale=1, nbases=30)):
+        case = build_case(n=333, C=2, **kw)
+        lp, g, lp_only = _eval(case)
+        lp_ref, g_ref = oracle_eval(case)
+        assert rel_err(lp, lp_ref) < TOL64, kw
+        assert rel_err(lp_only, lp_ref) < TOL64, kw
+        assert rel_err(g, g_ref) < TOL64, kw
+
+
+def test_obs_shards_add_up():
+    """set_shard: likelihood partials over disjoint observation ranges add up to the full
+    evaluation (priors on one shard only) -- the N>1 observation-sharded path."""
+    case = build_case(n=5000, n_loc=2, n_scale=1, nbases=12, C=3)
+    params = torch.from_numpy(case.params).cuda()
+    full_lp, full_g = case.model.log_prob_and_grad(params)
+    full_lp, full_g = full_lp.clone(), full_g.clone()
+    acc_lp, acc_g = torch.zeros_like(full_lp), torch.zeros_like(full_g)
+    for r, (lo, hi) in enumerate([(0, 1234), (1234, 1235), (1235, 5000)]):
+        case.model.set_shard(lo, hi, add_priors=(r == 0))
+        lp_, g_ = case.model.log_prob_and_grad(params)
+        acc_lp += lp_
+        acc_g += g_
+    assert rel_err(acc_lp.cpu().numpy(), full_lp.cpu().numpy()) < 1e-13
+    assert rel_err(acc_g.cpu().numpy(), full_g.cpu().numpy()) < 1e-12
+
+
+@pytest.mark.parametrize("n,C", [(100, 2), (4097, 3)])
+def test_logp_grad_f32(n, C):
+    """float32 path: rel 1e-5 against the f64 oracle evaluated on the f32-rounded inputs."""
+    case = build_case(n=n, n_loc=2, n_scale=1, nbases=12, nparam=20, C=C, dtype=np.float32)
+    lp, g, lp_only = _eval(case)
+    # oracle in f64 on the same (f32-rounded) numbers
+    om32 = case.omodel
+    terms = [o.term_from_reparam(t.x.astype(np.float64), t.knots.astype(np.float64), t.Z.astype(np.float64),
+                                 t.K.astype(np.float64), t.rank, t.predictor) for t in om32.terms]
+    om = o.PTMModel(om32.y.astype(np.float64), terms, nparam=20)
+    om.spline = o.PTMSpline(om32.knots.knots.astype(np.float64))
+    om.Zd = om32.Zd.astype(np.float64)
+    st = golden_io.state_from_params(om, case.params.astype(np.float64), case.layout)
+    lp_ref, gd = om.logp_and_grad(st)
+    from tests.helpers import pack_grad
+
+    g_ref = pack_grad(case, gd)
+    assert rel_err(lp, lp_ref) < 1e-5
+    assert rel_err(lp_only, lp_ref) < 1e-5
+    for c in range(C):
+        assert rel_err(g[c], g_ref[c]) < 1e-5
