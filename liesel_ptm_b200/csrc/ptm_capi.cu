@@ -38,7 +38,7 @@ int fail(int code, const std::string& msg) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Plan {
-  int CG, M, n_items, grid, NSLOT, To, S, Rsub;
+  int CG, M, n_items, grid, NSLOT, To, NU;
   long long chunk_len;
   size_t smem_main;
   size_t off_gamma, off_cc, off_partial, off_xt, total;
@@ -246,29 +246,30 @@ template <typename R>
 Plan make_plan(const PtmProblem* pr, long long C) {
   Plan pl;
   const int T = pr->T;
-  pl.S = std::max(1, std::max(pr->T_loc, pr->T_scale));
   pl.CG = (int)((C + 31) / 32);
-  pl.NSLOT = ptm::kRegSlots + pr->KK * 5 + pr->sum_nb;
+  const int NGV = pr->KK + 4;
+  pl.NSLOT = ptm::kRegSlots + NGV + pr->sum_nb;
   const int NCC = pr->KK * 5 + 6;
+  pl.NU = T <= 12 ? 8 : 4;  // eval warps (T + NU <= 32 warps)
   auto smem_for = [&](int To) {
     size_t b = 0;
-    b += (size_t)NCC * 32 * sizeof(R);
-    b += (size_t)ptm::kNTW * pr->KK * 5 * 32 * sizeof(R);
-    b += (size_t)2 * To * 2 * 32 * sizeof(R);
-    b += (size_t)T * 3 * To * 4 * sizeof(R);
-    b += (size_t)T * 4 * ptm::kKnotStride * sizeof(R);
-    b += (size_t)ptm::kNTW * ptm::kRegSlots * 32 * sizeof(R);
-    b += (size_t)T * 3 * To * sizeof(int);
+    b += (size_t)pr->sum_nb * 32 * sizeof(R);                 // gamma [coef][lane]
+    b += (size_t)NCC * 32 * sizeof(R);                        // cubic pieces of h
+    b += (size_t)pl.NU * NGV * 32 * sizeof(R);                // private grad tables
+    b += (size_t)2 * To * 2 * 32 * sizeof(R);                 // dl/deta hand-off
+    b += (size_t)T * 3 * To * 4 * sizeof(R);                  // staged basis values
+    b += (size_t)T * 4 * ptm::kKnotStride * sizeof(R);        // knots + reciprocals
+    b += (size_t)pl.NU * ptm::kRegSlots * 32 * sizeof(R);     // scalar partials
+    b += (size_t)(T * 3 * To + 8) * sizeof(int);              // staged intervals
     return b;
   };
-  pl.Rsub = std::max(1, 40 / pl.S);
-  while (pl.Rsub > 1 && smem_for(pl.S * pl.Rsub) > 220 * 1024) --pl.Rsub;
-  pl.To = pl.S * pl.Rsub;
+  pl.To = 32;
+  while (pl.To > 8 && smem_for(pl.To) > 224 * 1024) pl.To -= 8;
   pl.smem_main = smem_for(pl.To);
   const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
   const long long target_items = 8LL * pr->num_sms;
   long long M = std::max<long long>(1, target_items / pl.CG);
-  const long long max_m = std::max<long long>(1, len / ((long long)pl.To * 16));
+  const long long max_m = std::max<long long>(1, len / ((long long)pl.To * 16));  // >= 16 tiles per item
   M = std::min(M, max_m);
   long long chunk = (len + M - 1) / M;
   chunk = std::max<long long>(pl.To, (chunk + pl.To - 1) / pl.To * pl.To);
@@ -290,16 +291,19 @@ template <typename R, int NB, bool GRAD, int MAXT>
 int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
   auto kern = ptm::k_main<R, NB, GRAD, MAXT>;
   PTM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_main));
-  kern<<<pl.grid, 32 * (T + ptm::kNTW), pl.smem_main, st>>>(a);
+  kern<<<pl.grid, 32 * (T + pl.NU), pl.smem_main, st>>>(a);
   PTM_CUDA(cudaGetLastError());
   return PTM_OK;
 }
 
-// Up to 10 terms the CTA has <= 448 threads, which leaves 144 registers per thread.
+// CTA = T term warps + NU eval warps.  Up to 10 terms that is <= 576 threads (112
+// registers per thread); the 1024-thread variant covers up to 24 terms.
 template <typename R, int NB, bool GRAD>
 int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
-  if (32 * (T + ptm::kNTW) <= 448) return launch_main_t<R, NB, GRAD, 448>(a, pl, T, st);
-  return launch_main_t<R, NB, GRAD, 512>(a, pl, T, st);
+  const int threads = 32 * (T + pl.NU);
+  if (threads <= 576) return launch_main_t<R, NB, GRAD, 576>(a, pl, T, st);
+  if (threads <= 768) return launch_main_t<R, NB, GRAD, 768>(a, pl, T, st);
+  return launch_main_t<R, NB, GRAD, 1024>(a, pl, T, st);
 }
 
 template <typename R>
@@ -308,10 +312,10 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   if (!pr || !params || !logp || !ws) return fail(PTM_ERR_NULL, "null argument");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
   if (C < 1) return fail(PTM_ERR_SHAPE, "n_chains must be >= 1");
-  if (pr->T > 12) return fail(PTM_ERR_SHAPE, "fused kernel supports at most 12 smooth terms");
   const Plan pl = make_plan<R>(pr, C);
   if (ws_bytes < pl.total) return fail(PTM_ERR_WORKSPACE, "workspace too small");
   if (pl.smem_main > 227 * 1024) return fail(PTM_ERR_SHAPE, "shared-memory budget exceeded");
+  if (pr->T + pl.NU > 32) return fail(PTM_ERR_SHAPE, "too many smooth terms for one CTA");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   char* wsb = reinterpret_cast<char*>(ws);
   R* Gamma = reinterpret_cast<R*>(wsb + pl.off_gamma);
@@ -349,9 +353,14 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   ma.NSLOT = want_grad ? pl.NSLOT : 3;
   ma.KK = pr->KK;
   ma.T = pr->T; ma.T_loc = pr->T_loc; ma.T_scale = pr->T_scale;
-  ma.S = pl.S; ma.Rsub = pl.Rsub; ma.To = pl.To;
+  ma.To = pl.To; ma.NU = pl.NU; ma.sum_nb = pr->sum_nb;
+  {
+    int q = 0;
+    for (int t = 0; t < pr->T; ++t) if (pr->pred[t] == PTM_LOC) ma.order[q++] = t;
+    for (int t = 0; t < pr->T; ++t) if (pr->pred[t] == PTM_SCALE) ma.order[q++] = t;
+  }
   for (int t = 0; t < pr->T; ++t) {
-    ma.nb[t] = pr->nb[t]; ma.pred[t] = pr->pred[t]; ma.qidx[t] = pr->qidx[t];
+    ma.nb[t] = pr->nb[t]; ma.pred[t] = pr->pred[t];
     ma.goff[t] = pr->goff[t]; ma.inv_dk[t] = (R)pr->inv_dk[t];
   }
   {

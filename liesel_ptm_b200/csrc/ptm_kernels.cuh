@@ -2,17 +2,21 @@
 //
 // Layout and roles (DESIGN.md has the full story):
 //   * lane = chain.  A CTA owns one group of 32 chains and streams a chunk of
-//     observations through a 3-stage software pipeline.
-//   * "term warps" (one per smooth term) keep that term's nb spline coefficients
-//     gamma_t = Z_t beta_t and the nb gradient accumulators of their 32 chains IN
-//     REGISTERS.  The knot interval of an observation is warp-uniform, so a
-//     switch() on it turns the banded gather/scatter into register-indexed FMAs:
-//     no shared-memory traffic for coefficients, no atomics.
-//   * "trafo warps" do the point-wise part: sigma = exp(eta_sigma), r, the
-//     transformation h (grid-lerp semantics of the reference, evaluated from the
-//     cubic pieces), log-Jacobian, Normal logpdf, and the backward weights.
-//   * eta / dl/deta travel between the two kinds of warps through a double
-//     buffered shared-memory tile [obs][predictor][lane] (conflict-free).
+//     observations through a software pipeline of tiles (To observations each).
+//   * "term warps" (one per smooth term) stage the banded design of the next tile
+//     (knot interval + four cubic B-spline values per observation, K1 logic) and run
+//     the BACKWARD pass of the previous tile with that term's nb gradient
+//     accumulators IN REGISTERS: the knot interval is warp-uniform, so one PTX jump
+//     table (brx.idx.uni) turns the banded scatter into register-indexed FMAs -- no
+//     shared-memory traffic for the accumulators, no atomics.
+//   * "eval warps" own the forward pass of the current tile: eta_mu / eta_sigma from
+//     the spline coefficients gamma_t = Z_t beta_t kept in shared memory as
+//     [coef][lane] (conflict-free: every lane reads its own column), then
+//     sigma = exp(eta_sigma), r, the transformation h (grid-lerp semantics of the
+//     reference, evaluated from the cubic pieces), log-Jacobian, Normal logpdf and the
+//     backward weights.  dl/deta goes to the term warps through a double-buffered
+//     shared tile [obs][predictor][lane]; the gradient w.r.t. the transformation's
+//     B-spline coefficients accumulates in a per-warp private [coef][lane] table.
 //   * every (chain group, chunk) work item writes its partial sums to HBM; a small
 //     epilogue kernel reduces them in a fixed order (deterministic) and applies
 //     Z_t', the coefficient-map chain rule and the priors.
@@ -26,7 +30,6 @@ namespace ptm {
 
 constexpr int kMaxTerms = 24;
 constexpr int kKnotStride = kMaxNbases + 4;  // knots per term in the packed table
-constexpr int kNTW = 4;                      // trafo warps per CTA
 constexpr int kRegSlots = 9;                 // per-lane scalar accumulators
 enum Slot { SL_Z2 = 0, SL_LS, SL_LOGD, SL_GB0, SL_GG0, SL_GVL, SL_GDL, SL_GVR, SL_GDR };
 
@@ -43,20 +46,17 @@ struct MainArgs {
   long long obs_begin, obs_end;
   long long chunk_len;
   int C, CG, M, n_items, NSLOT, KK;
-  int T, T_loc, T_scale, S, Rsub, To;
+  int T, T_loc, T_scale, To, NU, sum_nb;
   int nb[kMaxTerms];
   int pred[kMaxTerms];
-  int qidx[kMaxTerms];   // index of the term inside its predictor group
-  int goff[kMaxTerms];   // offset of the term's gamma-gradient block in the slots
+  int goff[kMaxTerms];   // offset of the term's block in the packed coefficient tables
+  int order[kMaxTerms];  // term indices, location terms first
   R inv_dk[kMaxTerms];
   TrafoScal<R> ts;
 };
 
 // CTA-wide barrier issued from role-specific code (whole warps take one role).
 __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
-__device__ __forceinline__ void term_bar(int nthreads) {
-  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-}
 
 // mantissa / exponent split of a positive normal number: x = mant * 2^ex
 __device__ __forceinline__ void split_mant(double x, double& mant, int& ex) {
@@ -138,7 +138,9 @@ __device__ __forceinline__ void store4(float* p, const float (&b)[4]) {
 }
 
 // ------------------------------------------------------------------------------
-// K_main: fused logp (+ gradient) sweep.  blockDim = 32 * (T + kNTW).
+// K_main: fused logp (+ gradient) sweep.  blockDim = 32 * (T + NU).
+//   warps [0, T)      term warps: stage tile s+1, backward of tile s-1
+//   warps [T, T+NU)   eval warps: forward + point-wise part of tile s
 // ------------------------------------------------------------------------------
 template <typename R, int NB, bool GRAD, int MAXTHREADS>
 __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
@@ -146,31 +148,30 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int T = a.T, To = a.To, KK = a.KK;
+  const int T = a.T, To = a.To, KK = a.KK, NU = a.NU;
   const int NCC = KK * 5 + 6;
+  const int NGV = KK + 4;  // J + 1 slots: gradient w.r.t. the B-spline coefficients of h
 
   // ---- shared memory carve-up --------------------------------------------------
-  R* s_cc = reinterpret_cast<R*>(smem_raw);                 // [NCC][32]
-  R* s_gc = s_cc + NCC * 32;                                // [kNTW][KK*5][32]
-  R* s_h = s_gc + (GRAD ? kNTW * KK * 5 * 32 : 0);          // [2][To][2][32]
-  R* s_b = s_h + 2 * To * 2 * 32;                           // [T][3][To][4]
-  R* s_kn = s_b + T * 3 * To * 4;                           // [T][4][kKnotStride] knots + reciprocals
-  R* s_red = s_kn + T * 4 * kKnotStride;                    // [kNTW][kRegSlots][32]
-  int* s_j = reinterpret_cast<int*>(s_red + kNTW * kRegSlots * 32);  // [T][3][To]
+  R* s_gam = reinterpret_cast<R*>(smem_raw);                // [sum_nb][32]
+  R* s_cc = s_gam + a.sum_nb * 32;                          // [NCC][32]
+  R* s_gv = s_cc + NCC * 32;                                // [NU][NGV][32]
+  R* s_g = s_gv + (GRAD ? NU * NGV * 32 : 0);               // [2][To][2][32]
+  R* s_b = s_g + (GRAD ? 2 * To * 2 * 32 : 0);              // [T][3][To][4]
+  R* s_kn = s_b + T * 3 * To * 4;                           // [T][4][kKnotStride]
+  R* s_red = s_kn + T * 4 * kKnotStride;                    // [NU][kRegSlots][32]
+  int* s_j = reinterpret_cast<int*>(s_red + NU * kRegSlots * 32);  // [T][3][To] (+ pad)
 
   const bool is_term = warp < T;
-  const int tw = warp - T;  // trafo warp index when !is_term
-  const int term_threads = T * 32;
+  const int uw = warp - T;  // eval warp index when !is_term
 
   // term-warp constants
-  int t_nb = 0, t_pred = 0, t_q = 0, t_Tg = 1;
+  int t_nb = 0, t_pred = 0;
   R t_invdk = R(0);
   const R* t_x = nullptr;
   if (is_term) {
     t_nb = a.nb[warp];
     t_pred = a.pred[warp];
-    t_q = a.qidx[warp];
-    t_Tg = t_pred == 0 ? a.T_loc : a.T_scale;
     t_invdk = a.inv_dk[warp];
     t_x = a.X + (long long)warp * a.n;
     R* kn = s_kn + warp * 4 * kKnotStride;
@@ -183,7 +184,6 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
     }
   }
   const TrafoScal<R> ts = a.ts;
-  const bool has_loc = a.T_loc > 0, has_scale = a.T_scale > 0;
   __syncthreads();
 
   for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -196,104 +196,71 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
     const int ntiles = (int)((len + To - 1) / To);
     int chain = cg * 32 + lane;
     if (chain >= a.C) chain = a.C - 1;
-
     R* pout = a.partial + (long long)item * a.NSLOT * 32;
+
     if (is_term) {
       // =========================== term warp ========================================
-      R g[NB];
-      R acc[NB];
+      const int term = warp;
+      // this term's spline coefficients of the 32 chains -> shared [coef][lane]
+      for (int j = 0; j < t_nb; ++j)
+        s_gam[(a.goff[term] + j) * 32 + lane] = a.Gamma[((long long)term * kMaxNbases + j) * a.C + chain];
+      R acc[GRAD ? NB : 1];
+      if constexpr (GRAD) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        g[j] = (j < t_nb) ? a.Gamma[((long long)warp * kMaxNbases + j) * a.C + chain] : R(0);
-        acc[j] = R(0);
+        for (int j = 0; j < NB; ++j) acc[j] = R(0);
       }
+      const R* kn = s_kn + term * 4 * kKnotStride;
+      auto stage = [&](int tile) {
+        const long long base = o_begin + (long long)tile * To;
+        const int slot = tile % 3;
+        R* bst = s_b + ((term * 3 + slot) * To) * 4;
+        int* jst = s_j + (term * 3 + slot) * To;
+        for (int o = lane; o < To; o += 32) {
+          const long long gi = base + o;
+          if (gi < o_end) {
+            R bb[4];
+            const int jj = basis_window_fast(t_x[gi], kn, kn + kKnotStride, kn + 2 * kKnotStride,
+                                             kn + 3 * kKnotStride, t_nb, t_invdk, bb);
+            store4(bst + o * 4, bb);
+            jst[o] = jj;
+          }
+        }
+      };
+      if (ntiles > 0) stage(0);
       cta_bar();
-      for (int s = 0; s < ntiles + 2; ++s) {
-        // (1) backward of tile s-2: acc += b * dl/deta
-        if (GRAD && s >= 2) {
-          const int tile = s - 2;
-          const long long base = o_begin + (long long)tile * To;
-          const int slot = tile % 3;
-          const R* bp = s_b + ((warp * 3 + slot) * To) * 4;
-          const int* jp = s_j + (warp * 3 + slot) * To;
-          const R* hp = s_h + (((s & 1) * To) * 2 + t_pred) * 32 + lane;
-          const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
+      for (int s = 0; s <= ntiles; ++s) {
+        if (s + 1 < ntiles) stage(s + 1);
+        if constexpr (GRAD) {
+          if (s >= 1) {
+            // backward of tile s-1: acc[jj..jj+3] += b * dl/deta (register-indexed)
+            const int tile = s - 1;
+            const long long base = o_begin + (long long)tile * To;
+            const int slot = tile % 3;
+            const R* bp = s_b + ((term * 3 + slot) * To) * 4;
+            const int* jp = s_j + (term * 3 + slot) * To;
+            const R* hp = s_g + (((tile & 1) * To) * 2 + t_pred) * 32 + lane;
+            const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
 #pragma unroll 2
-          for (int o = 0; o < cnt; ++o, bp += 4, ++jp, hp += 64) {
-            R b0, b1, b2, b3;
-            load4(bp, b0, b1, b2, b3);
-            Dispatch<R, NB>::scatter(acc, *jp, b0, b1, b2, b3, *hp);
-          }
-        }
-        // (2) stage tile s: knot interval + four basis values per observation
-        if (s < ntiles) {
-          const long long base = o_begin + (long long)s * To;
-          const int slot = s % 3;
-          R* bp = s_b + ((warp * 3 + slot) * To) * 4;
-          int* jp = s_j + (warp * 3 + slot) * To;
-          for (int o = lane; o < To; o += 32) {
-            const long long gi = base + o;
-            if (gi < o_end) {
-              R bb[4];
-              const R* kn = s_kn + warp * 4 * kKnotStride;
-              const int jj = basis_window_fast(t_x[gi], kn, kn + kKnotStride, kn + 2 * kKnotStride,
-                                               kn + 3 * kKnotStride, t_nb, t_invdk, bb);
-              store4(bp + o * 4, bb);
-              jp[o] = jj;
-            }
-          }
-          __syncwarp();
-        }
-        term_bar(term_threads);  // all reads of buffer (s&1) done before it is rewritten
-        // (3) forward of tile s: rotate over the S sub-tiles so that the warps of one
-        //     predictor never touch the same sub-tile in the same sub-step
-        for (int sp = 0; sp < a.S; ++sp) {
-          if (sp > 0) term_bar(term_threads);
-          if (s < ntiles) {
-            int bsub = t_q + sp;
-            if (bsub >= a.S) bsub -= a.S;
-            const bool first = (sp == 0) || (t_q == t_Tg - 1 && sp <= a.S - t_Tg);
-            const long long base = o_begin + (long long)s * To;
-            const int slot = s % 3;
-            const R* bp = s_b + ((warp * 3 + slot) * To) * 4;
-            const int* jp = s_j + (warp * 3 + slot) * To;
-            R* hp = s_h + (((s & 1) * To) * 2 + t_pred) * 32 + lane;
-            const int o0 = bsub * a.Rsub;
-            int o1 = o0 + a.Rsub;
-            const long long rem = o_end - base;
-            if (o1 > rem) o1 = (int)rem;
-            bp += o0 * 4;
-            jp += o0;
-            hp += o0 * 64;
-            if (first) {
-#pragma unroll 2
-              for (int o = o0; o < o1; ++o, bp += 4, ++jp, hp += 64) {
-                R b0, b1, b2, b3;
-                load4(bp, b0, b1, b2, b3);
-                *hp = Dispatch<R, NB>::gather(g, *jp, b0, b1, b2, b3, R(0));
-              }
-            } else {
-#pragma unroll 2
-              for (int o = o0; o < o1; ++o, bp += 4, ++jp, hp += 64) {
-                R b0, b1, b2, b3;
-                load4(bp, b0, b1, b2, b3);
-                *hp = Dispatch<R, NB>::gather(g, *jp, b0, b1, b2, b3, *hp);
-              }
+            for (int o = 0; o < cnt; ++o, bp += 4, ++jp, hp += 64) {
+              R b0, b1, b2, b3;
+              load4(bp, b0, b1, b2, b3);
+              Dispatch<R, NB>::scatter(acc, *jp, b0, b1, b2, b3, *hp);
             }
           }
         }
         cta_bar();
       }
-      if (GRAD) {
+      if constexpr (GRAD) {
 #pragma unroll
         for (int j = 0; j < NB; ++j)
-          if (j < t_nb) pout[(kRegSlots + KK * 5 + a.goff[warp] + j) * 32 + lane] = acc[j];
+          if (j < t_nb) pout[(kRegSlots + NGV + a.goff[term] + j) * 32 + lane] = acc[j];
       }
     } else {
-      // =========================== trafo warp =======================================
-      for (int s = tw; s < NCC; s += kNTW) s_cc[s * 32 + lane] = a.cc[(long long)s * a.C + chain];
+      // =========================== eval warp ========================================
+      for (int s = uw; s < NCC; s += NU) s_cc[s * 32 + lane] = a.cc[(long long)s * a.C + chain];
+      R* gvp = s_gv + (uw * NGV) * 32 + lane;
       if (GRAD)
-        for (int s = 0; s < KK * 5; ++s) s_gc[(tw * KK * 5 + s) * 32 + lane] = R(0);
+        for (int s = 0; s < NGV; ++s) gvp[s * 32] = R(0);
       ChainBoundary<R> cb;
       make_boundary(ts, a.cc[(long long)(KK * 5 + 0) * a.C + chain],
                     a.cc[(long long)(KK * 5 + 1) * a.C + chain],
@@ -306,49 +273,67 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
       R a_z2 = R(0), a_ls = R(0), a_pm = R(1), a_gb0 = R(0), a_gg0 = R(0);
       R a_gvl = R(0), a_gdl = R(0), a_gvr = R(0), a_gdr = R(0);
       int a_pe = 0;
+      const R sixth = R(1) / R(6);
       cta_bar();
-      for (int s = 0; s < ntiles + 2; ++s) {
-        const int tile = s - 1;
-        if (tile >= 0 && tile < ntiles) {
+      for (int s = 0; s <= ntiles; ++s) {
+        if (s < ntiles) {
+          const int tile = s;
           const long long base = o_begin + (long long)tile * To;
-          R* hb = s_h + (((tile & 1) * To) * 2) * 32 + lane;
+          const int slot = tile % 3;
+          R* gb = s_g + (((tile & 1) * To) * 2) * 32 + lane;
           const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
-          for (int o = tw; o < cnt; o += kNTW) {
+#pragma unroll 2
+          for (int o = uw; o < cnt; o += NU) {
             const R yv = a.y[base + o];
+            // ---- additive predictors: banded gather from the shared coefficient table
             R em = beta0, es = gamma0;
-            if (has_loc) em += hb[o * 64];
-            if (has_scale) es += hb[o * 64 + 32];
+            for (int q = 0; q < T; ++q) {
+              const int t = a.order[q];
+              const int so = ((t * 3 + slot) * To + o);
+              R b0, b1, b2, b3;
+              load4(s_b + so * 4, b0, b1, b2, b3);
+              const R* gp = s_gam + (a.goff[t] + s_j[so]) * 32 + lane;
+              R f = b0 * gp[0];
+              f = fma(b1, gp[32], f);
+              f = fma(b2, gp[64], f);
+              f = fma(b3, gp[96], f);
+              if (q < a.T_loc) em += f; else es += f;
+            }
             const R einv = exp(-es);
             const R r = (yv - em) * einv;
             const int code = region_code(ts, r);
-            R z, d, dzdr, dddr;
+            const bool core = code == 2;
+            // ---- core evaluation, unconditionally on the clamped argument (branch-free);
+            //      the rare non-core lanes override the result below
+            const R rc = r < ts.a ? ts.a : (r > ts.b ? ts.b : (r == r ? r : ts.a));
+            int m;
+            R frac;
+            grid_cell(ts, a.grid, rc, m, frac);
             CoreEval<R> ev;
-            if (code == 2) {
-              int m;
-              R frac;
-              grid_cell(ts, a.grid, r, m, frac);
-              core_locate(ts, m, frac, ev);
-              const R* cp = s_cc + (ev.kk * 5) * 32 + lane;
-              core_eval(ts, cp[0], cp[32], cp[64], cp[96], cp[128], ev);
-              z = ev.z; d = ev.d; dzdr = ev.d; dddr = ev.d2;
-            } else if (code == 1) {
-              const R poly = r * ts.a - R(0.5) * r * r;
-              z = (ts.inv_w * poly + cb.dL * (r - poly * ts.inv_w)) + cb.constL;
-              const R q = (ts.a - r) * ts.inv_w;
-              d = (R(1) - q) * cb.dL + q;
-              dzdr = d; dddr = (cb.dL - R(1)) * ts.inv_w;
-            } else if (code == 3) {
-              const R poly = R(0.5) * r * r - r * ts.b;
-              z = (ts.inv_w * poly + cb.dR * (r - poly * ts.inv_w)) + cb.constR;
-              const R q = (r - ts.b) * ts.inv_w;
-              d = (R(1) - q) * cb.dR + q;
-              dzdr = d; dddr = (R(1) - cb.dR) * ts.inv_w;
-            } else if (code == 0) {
-              z = cb.ztailL - (ts.min_eps - r);
-              d = R(1); dzdr = R(1); dddr = R(0);
-            } else {
-              z = cb.ztailR + (r - ts.max_eps);
-              d = R(1); dzdr = R(1); dddr = R(0);
+            core_locate(ts, m, frac, ev);
+            const R* cp = s_cc + (ev.kk * 5) * 32 + lane;
+            core_eval(ts, cp[0], cp[32], cp[64], cp[96], cp[128], ev);
+            R z = ev.z, d = ev.d, dzdr = ev.d, dddr = ev.d2;
+            if (!core) {
+              if (code == 1) {
+                const R poly = r * ts.a - R(0.5) * r * r;
+                z = (ts.inv_w * poly + cb.dL * (r - poly * ts.inv_w)) + cb.constL;
+                const R q = (ts.a - r) * ts.inv_w;
+                d = (R(1) - q) * cb.dL + q;
+                dzdr = d; dddr = (cb.dL - R(1)) * ts.inv_w;
+              } else if (code == 3) {
+                const R poly = R(0.5) * r * r - r * ts.b;
+                z = (ts.inv_w * poly + cb.dR * (r - poly * ts.inv_w)) + cb.constR;
+                const R q = (r - ts.b) * ts.inv_w;
+                d = (R(1) - q) * cb.dR + q;
+                dzdr = d; dddr = (R(1) - cb.dR) * ts.inv_w;
+              } else if (code == 0) {
+                z = cb.ztailL - (ts.min_eps - r);
+                d = R(1); dzdr = R(1); dddr = R(0);
+              } else {
+                z = cb.ztailR + (r - ts.max_eps);
+                d = R(1); dzdr = R(1); dddr = R(0);
+              }
             }
             const R tiny = tiny_of<R>();
             const bool above = d > tiny;
@@ -367,33 +352,39 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               const R gr = fma(lz, dzdr, ld * dddr);
               const R gmu = -gr * einv;
               const R gls = fma(-gr, r, R(-1));
-              if (has_loc) hb[o * 64] = gmu;
-              if (has_scale) hb[o * 64 + 32] = gls;
+              gb[o * 64] = gmu;
+              gb[o * 64 + 32] = gls;
               a_gb0 += gmu;
               a_gg0 += gls;
-              if (code == 2) {
-                R w[5];
-                core_backward(ts, ev, lz, ld, w);
-                R* gp = s_gc + ((tw * KK + ev.kk) * 5) * 32 + lane;
-                gp[0] += w[0];
-                gp[32] += w[1];
-                gp[64] += w[2];
-                gp[96] += w[3];
-                gp[128] += w[4];
-              } else if (code == 1) {
-                const R q = (ts.a - r) * ts.inv_w;
-                a_gvl += lz;
-                a_gdl += fma(lz, cL_of(ts, r), ld * (R(1) - q));
-              } else if (code == 3) {
-                const R q = (r - ts.b) * ts.inv_w;
-                a_gvr += lz;
-                a_gdr += fma(lz, cR_of(ts, r), ld * (R(1) - q));
-              } else if (code == 0) {
-                a_gvl += lz;
-                a_gdl = fma(lz, cLe, a_gdl);
-              } else {
-                a_gvr += lz;
-                a_gdr = fma(lz, cRe, a_gdr);
+              // gradient w.r.t. the five piece coefficients -> B-spline coefficients
+              // vt[kk .. kk+4] (transpose of piece_coefs); zero weights off the core
+              R w[5];
+              core_backward(ts, ev, core ? lz : R(0), core ? ld : R(0), w);
+              const bool lastp = ev.kk + 1 >= KK;
+              const R w4 = lastp ? R(0) : w[4];
+              const R g3 = w[3] - w4;
+              R* gp = gvp + ev.kk * 32;
+              gp[0] += (w[0] - g3) * sixth + (w[2] - w[1]) * R(0.5);
+              gp[32] += (R(4) * w[0] - w4) * sixth - w[2] + g3 * R(0.5);
+              gp[64] += w[0] * sixth + (w[1] + w[2] - g3 + w4) * R(0.5);
+              gp[96] += g3 * sixth - w4 * R(0.5);
+              gp[128] += w4 * sixth;
+              if (!core) {
+                if (code == 1) {
+                  const R q = (ts.a - r) * ts.inv_w;
+                  a_gvl += lz;
+                  a_gdl += fma(lz, cL_of(ts, r), ld * (R(1) - q));
+                } else if (code == 3) {
+                  const R q = (r - ts.b) * ts.inv_w;
+                  a_gvr += lz;
+                  a_gdr += fma(lz, cR_of(ts, r), ld * (R(1) - q));
+                } else if (code == 0) {
+                  a_gvl += lz;
+                  a_gdl = fma(lz, cLe, a_gdl);
+                } else {
+                  a_gvr += lz;
+                  a_gdr = fma(lz, cRe, a_gdr);
+                }
               }
             }
           }
@@ -407,7 +398,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
         }
         cta_bar();
       }
-      R* rp = s_red + (tw * kRegSlots) * 32 + lane;
+      R* rp = s_red + (uw * kRegSlots) * 32 + lane;
       rp[SL_Z2 * 32] = a_z2;
       rp[SL_LS * 32] = a_ls;
       rp[SL_LOGD * 32] = log(a_pm) + R(a_pe) * R(0.69314718055994530942);
@@ -418,19 +409,19 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
       rp[SL_GVR * 32] = a_gvr;
       rp[SL_GDR * 32] = a_gdr;
     }
-    // ---- item epilogue: cross-warp sums of the trafo partials to HBM ------------
+    // ---- item epilogue: cross-warp sums of the eval-warp partials to HBM ------------
     __syncthreads();
     {
       const int nreg = GRAD ? kRegSlots : 3;
       for (int idx = tid; idx < nreg * 32; idx += blockDim.x) {
         R v = R(0);
-        for (int w = 0; w < kNTW; ++w) v += s_red[w * kRegSlots * 32 + idx];
+        for (int w = 0; w < NU; ++w) v += s_red[w * kRegSlots * 32 + idx];
         pout[idx] = v;
       }
       if (GRAD) {
-        for (int idx = tid; idx < KK * 5 * 32; idx += blockDim.x) {
+        for (int idx = tid; idx < NGV * 32; idx += blockDim.x) {
           R v = R(0);
-          for (int w = 0; w < kNTW; ++w) v += s_gc[w * KK * 5 * 32 + idx];
+          for (int w = 0; w < NU; ++w) v += s_gv[w * NGV * 32 + idx];
           pout[kRegSlots * 32 + idx] = v;
         }
       }
@@ -579,7 +570,7 @@ __global__ void k_post(const PostArgs<R> a) {
         const int c = cg * 32 + lane;
         if (c >= a.C) continue;
         const R* par = a.params + (long long)c * a.P;
-        const R* gg = red + (kRegSlots + KK * 5 + a.goff[t]) * 32 + lane;
+        const R* gg = red + (kRegSlots + KK + 4 + a.goff[t]) * 32 + lane;
         R v = R(0);
         for (int j = 0; j < nb; ++j) v = fma(Zt[j * p + k], gg[j * 32], v);
         if (a.add_priors) {
@@ -626,23 +617,16 @@ __global__ void k_post(const PostArgs<R> a) {
           delta[j] = v;
         }
         coef_map_forward(tc, delta, e, sm, vt);
-        for (int j = 0; j <= np_; ++j) gvt[j] = R(0);
+        for (int j = 0; j <= np_; ++j) gvt[j] = red[(kRegSlots + j) * 32 + lane];
+        // boundary gradients fold into the first / last piece (ptm.py:417-419)
         const R gvl = red[SL_GVL * 32 + lane], gdl = red[SL_GDL * 32 + lane];
         const R gvr = red[SL_GVR * 32 + lane], gdr = red[SL_GDR * 32 + lane];
-        for (int kk = 0; kk < KK; ++kk) {
-          R gc[5];
-          for (int q = 0; q < 5; ++q) gc[q] = red[(kRegSlots + kk * 5 + q) * 32 + lane];
-          if (kk == 0) {
-            gc[0] += gvl;
-            gc[1] += gdl * tc.inv_dk;
-          }
-          if (kk == KK - 1) {
-            gc[0] += gvr;
-            gc[1] += gvr + gdr * tc.inv_dk;
-            gc[2] += gvr + R(2) * gdr * tc.inv_dk;
-            gc[3] += gvr + R(3) * gdr * tc.inv_dk;
-          }
-          piece_coefs_backward(gc, kk, KK, gvt);
+        {
+          R gc[5] = {gvl, gdl * tc.inv_dk, R(0), R(0), R(0)};
+          piece_coefs_backward(gc, 0, KK, gvt);
+          R gl[5] = {gvr, gvr + gdr * tc.inv_dk, gvr + R(2) * gdr * tc.inv_dk,
+                     gvr + R(3) * gdr * tc.inv_dk, R(0)};
+          piece_coefs_backward(gl, KK - 1, KK, gvt);
         }
         coef_map_backward(tc, gvt, e, sm, gdelta);
         for (int k = 0; k < np_ - 1; ++k) {
