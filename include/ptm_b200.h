@@ -26,8 +26,6 @@
  *   ptm_xtwx_* / ptm_loc_precision_*  GaussianLocCholInfo.working_weights /
  *                                  precision / chol_info: iwls_proposals.py:55-89
  *                                  (scale terms, W == 2: 118-144).
- *   ptm_quadform_*                 beta' K beta of the Gibbs scale updates:
- *                                  gam/kernel.py:29-39, kernel.py:99-111.
  *
  * Parameter vector of ONE chain (row of the [C, P] row-major `params` array, the
  * layout JAX hands over after ravel_pytree):
