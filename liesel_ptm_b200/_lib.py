@@ -12,7 +12,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptm_b200.so")
+LIB_PATH = os.environ.get("PTM_B200_LIB", os.path.join(_HERE, "libptm_b200.so"))
 
 PTM_F32, PTM_F64 = 0, 1
 PTM_LOC, PTM_SCALE = 0, 1

@@ -296,12 +296,14 @@ int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t
   return PTM_OK;
 }
 
-// CTA = T term warps + NU eval warps.  Up to 10 terms that is <= 576 threads (112
-// registers per thread); the 1024-thread variant covers up to 24 terms.
+// CTA = T term warps + NU eval warps (c3: 18 warps, 96 registers per thread); the
+// 1024-thread variant covers up to 24 terms.
 template <typename R, int NB, bool GRAD>
 int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
+  // registers are granted per 4 warps: <= 16 warps -> 128/thread, 20 -> 96, 24 -> 80, 32 -> 64
   const int threads = 32 * (T + pl.NU);
-  if (threads <= 576) return launch_main_t<R, NB, GRAD, 576>(a, pl, T, st);
+  if (threads <= 512) return launch_main_t<R, NB, GRAD, 512>(a, pl, T, st);
+  if (threads <= 640) return launch_main_t<R, NB, GRAD, 640>(a, pl, T, st);
   if (threads <= 768) return launch_main_t<R, NB, GRAD, 768>(a, pl, T, st);
   return launch_main_t<R, NB, GRAD, 1024>(a, pl, T, st);
 }

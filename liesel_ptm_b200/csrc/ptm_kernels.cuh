@@ -282,7 +282,9 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
           const int slot = tile % 3;
           R* gb = s_g + (((tile & 1) * To) * 2) * 32 + lane;
           const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
-#pragma unroll 2
+          // (interleaving two observations per warp by unrolling was measured slower: the
+          //  extra live values push the eval warps over their 96-register budget)
+#pragma unroll 1
           for (int o = uw; o < cnt; o += NU) {
             const R yv = a.y[base + o];
             // ---- additive predictors: banded gather from the shared coefficient table
