@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -250,21 +251,24 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   const int NGV = pr->KK + 4;
   pl.NSLOT = ptm::kRegSlots + NGV + pr->sum_nb;
   const int NCC = pr->KK * 5 + 6;
-  pl.NU = T <= 12 ? 8 : 4;  // eval warps (T + NU <= 32 warps)
+  // eval warps: fill the CTA up to 20 warps (96 registers per thread; registers are
+  // granted per 4 warps), measured best at c3 (T = 10 -> NU = 10); 4 beyond 12 terms
+  pl.NU = T <= 12 ? std::min(12, std::max(8, 20 - T)) : 4;
+  if (const char* e = getenv("PTM_NU")) pl.NU = std::max(1, std::min(32 - T, atoi(e)));  // tuning knob
   auto smem_for = [&](int To) {
     size_t b = 0;
     b += (size_t)pr->sum_nb * 32 * sizeof(R);                 // gamma [coef][lane]
     b += (size_t)NCC * 32 * sizeof(R);                        // cubic pieces of h
     b += (size_t)pl.NU * NGV * 32 * sizeof(R);                // private grad tables
-    b += (size_t)2 * To * 2 * 32 * sizeof(R);                 // dl/deta hand-off
+    b += (size_t)2 * To * 2 * 32 * sizeof(R);                 // dl/deta hand-off (+ scalar partials at item end)
     b += (size_t)T * 3 * To * 4 * sizeof(R);                  // staged basis values
     b += (size_t)T * 4 * ptm::kKnotStride * sizeof(R);        // knots + reciprocals
-    b += (size_t)pl.NU * ptm::kRegSlots * 32 * sizeof(R);     // scalar partials
     b += (size_t)(T * 3 * To + 8) * sizeof(int);              // staged intervals
     return b;
   };
-  pl.To = 32;
-  while (pl.To > 8 && smem_for(pl.To) > 224 * 1024) pl.To -= 8;
+  pl.To = 4 * pl.NU;  // four observations per eval warp and tile
+  if (const char* e = getenv("PTM_TO")) pl.To = std::max(8, atoi(e));  // tuning knob
+  while (pl.To > 8 && (smem_for(pl.To) > 227 * 1024 || 4 * pl.To < 9 * pl.NU)) pl.To -= 4;
   pl.smem_main = smem_for(pl.To);
   const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
   const long long target_items = 8LL * pr->num_sms;

@@ -157,10 +157,11 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   R* s_cc = s_gam + a.sum_nb * 32;                          // [NCC][32]
   R* s_gv = s_cc + NCC * 32;                                // [NU][NGV][32]
   R* s_g = s_gv + (GRAD ? NU * NGV * 32 : 0);               // [2][To][2][32]
-  R* s_b = s_g + (GRAD ? 2 * To * 2 * 32 : 0);              // [T][3][To][4]
+  R* s_b = s_g + 2 * To * 2 * 32;                           // [T][3][To][4]
   R* s_kn = s_b + T * 3 * To * 4;                           // [T][4][kKnotStride]
-  R* s_red = s_kn + T * 4 * kKnotStride;                    // [NU][kRegSlots][32]
-  int* s_j = reinterpret_cast<int*>(s_red + NU * kRegSlots * 32);  // [T][3][To] (+ pad)
+  R* s_red = s_g;  // [NU][kRegSlots][32] scalar partials: written after the last tile only,
+                   // so they reuse the dl/deta tiles (2*To*64 >= NU*9*32 for To >= 2.25 NU)
+  int* s_j = reinterpret_cast<int*>(s_kn + T * 4 * kKnotStride);  // [T][3][To] (+ pad)
 
   const bool is_term = warp < T;
   const int uw = warp - T;  // eval warp index when !is_term
