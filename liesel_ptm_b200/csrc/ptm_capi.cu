@@ -72,6 +72,7 @@ struct PtmProblem {
   void* d_Kall = nullptr;
   void* d_Zd = nullptr;
   void* d_tc = nullptr;
+  void* d_tc64 = nullptr;  // TrafoConst<double> for the epilogue
   ptm::TrafoConst<double> tc64;  // host copy (double); cast for f32
 };
 
@@ -239,6 +240,11 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
     fill_tc<R>(tc, tcr);
     PTM_CUDA(cudaMalloc(&pr->d_tc, sizeof tcr));
     PTM_CUDA(cudaMemcpy(pr->d_tc, &tcr, sizeof tcr, cudaMemcpyHostToDevice));
+    ptm::TrafoConst<double> tcd;
+    memset(&tcd, 0, sizeof tcd);
+    fill_tc<double>(tc, tcd);
+    PTM_CUDA(cudaMalloc(&pr->d_tc64, sizeof tcd));
+    PTM_CUDA(cudaMemcpy(pr->d_tc64, &tcd, sizeof tcd, cudaMemcpyHostToDevice));
   }
   return PTM_OK;
 }
@@ -260,7 +266,8 @@ Plan make_plan(const PtmProblem* pr, long long C) {
     b += (size_t)pr->sum_nb * 32 * sizeof(R);                 // gamma [coef][lane]
     b += (size_t)NCC * 32 * sizeof(R);                        // cubic pieces of h
     b += (size_t)pl.NU * NGV * 32 * sizeof(R);                // private grad tables
-    b += (size_t)2 * To * 2 * 32 * sizeof(R);                 // dl/deta hand-off (+ scalar partials at item end)
+    b += std::max((size_t)2 * To * 2 * 32 * sizeof(R),        // dl/deta hand-off, reused for the
+                  (size_t)pl.NU * ptm::kRegSlots * 32 * sizeof(double));  // scalar partials at item end
     b += (size_t)T * 3 * To * 4 * sizeof(R);                  // staged basis values
     b += (size_t)T * 4 * ptm::kKnotStride * sizeof(R);        // knots + reciprocals
     b += (size_t)(T * 3 * To + 8) * sizeof(int);              // staged intervals
@@ -268,7 +275,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   };
   pl.To = 4 * pl.NU;  // four observations per eval warp and tile
   if (const char* e = getenv("PTM_TO")) pl.To = std::max(8, atoi(e));  // tuning knob
-  while (pl.To > 8 && (smem_for(pl.To) > 227 * 1024 || 4 * pl.To < 9 * pl.NU)) pl.To -= 4;
+  while (pl.To > 8 && smem_for(pl.To) > 227 * 1024) pl.To -= 4;
   pl.smem_main = smem_for(pl.To);
   const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
   const long long target_items = 8LL * pr->num_sms;
@@ -285,7 +292,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   size_t off = 0;
   pl.off_gamma = off; off = align_up(off + (size_t)std::max(T, 1) * ptm::kMaxNbases * C * sizeof(R), 256);
   pl.off_cc = off;    off = align_up(off + (size_t)NCC * C * sizeof(R), 256);
-  pl.off_partial = off; off = align_up(off + (size_t)pl.n_items * pl.NSLOT * 32 * sizeof(R), 256);
+  pl.off_partial = off; off = align_up(off + (size_t)pl.n_items * pl.NSLOT * 32 * sizeof(double), 256);
   pl.off_xt = off;    off = align_up(off + ptm::xtwx_workspace_bytes<R>(pr->max_nb, C), 256);
   pl.total = off;
   return pl;
@@ -326,7 +333,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   char* wsb = reinterpret_cast<char*>(ws);
   R* Gamma = reinterpret_cast<R*>(wsb + pl.off_gamma);
   R* cc = reinterpret_cast<R*>(wsb + pl.off_cc);
-  R* partial = reinterpret_cast<R*>(wsb + pl.off_partial);
+  double* partial = reinterpret_cast<double*>(wsb + pl.off_partial);
   const bool want_grad = grad != nullptr;
   g_launches = 0;
 
@@ -335,7 +342,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   pa.params = params; pa.Gamma = Gamma; pa.cc = cc;
   pa.Zall = reinterpret_cast<const R*>(pr->d_Zall);
   pa.Zd = reinterpret_cast<const R*>(pr->d_Zd);
-  pa.tc = reinterpret_cast<const ptm::TrafoConst<R>*>(pr->d_tc);
+  pa.tc = reinterpret_cast<const ptm::TrafoConst<double>*>(pr->d_tc64);
   pa.C = (int)C; pa.P = pr->P; pa.T = pr->T; pa.dz_off = pr->dz_off;
   for (int t = 0; t < pr->T; ++t) {
     pa.nb[t] = pr->nb[t]; pa.p[t] = pr->p[t]; pa.zoff[t] = pr->zoff[t]; pa.boff[t] = pr->boff[t];
@@ -389,7 +396,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   po.Zall = reinterpret_cast<const R*>(pr->d_Zall);
   po.Kall = reinterpret_cast<const R*>(pr->d_Kall);
   po.Zd = reinterpret_cast<const R*>(pr->d_Zd);
-  po.tc = reinterpret_cast<const ptm::TrafoConst<R>*>(pr->d_tc);
+  po.tc = reinterpret_cast<const ptm::TrafoConst<double>*>(pr->d_tc64);
   po.C = (int)C; po.P = pr->P; po.T = pr->T; po.M = pl.M; po.NSLOT = ma.NSLOT; po.KK = pr->KK;
   for (int t = 0; t < pr->T; ++t) {
     po.nb[t] = pr->nb[t]; po.p[t] = pr->p[t]; po.zoff[t] = pr->zoff[t]; po.koff[t] = pr->koff[t];
@@ -398,7 +405,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   po.dz_off = pr->dz_off; po.tau_off = pr->tau_off; po.taud_off = pr->taud_off;
   po.n_obs = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
   po.add_priors = pr->add_priors;
-  const size_t smem_post = ((size_t)ma.NSLOT * 32 + 32) * sizeof(R);
+  const size_t smem_post = ((size_t)ma.NSLOT * 32 + 32) * sizeof(double);
   if (want_grad) {
     auto kp = ptm::k_post<R, true>;
     PTM_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_post));
@@ -464,7 +471,7 @@ int xtwx_impl(const PtmProblem* pr, int term, const R* params, long long C, R* x
   pa.params = params; pa.Gamma = Gamma; pa.cc = cc;
   pa.Zall = reinterpret_cast<const R*>(pr->d_Zall);
   pa.Zd = reinterpret_cast<const R*>(pr->d_Zd);
-  pa.tc = reinterpret_cast<const ptm::TrafoConst<R>*>(pr->d_tc);
+  pa.tc = reinterpret_cast<const ptm::TrafoConst<double>*>(pr->d_tc64);
   pa.C = (int)C; pa.P = pr->P; pa.T = pr->T; pa.dz_off = pr->dz_off;
   for (int t = 0; t < pr->T; ++t) {
     pa.nb[t] = pr->nb[t]; pa.p[t] = pr->p[t]; pa.zoff[t] = pr->zoff[t]; pa.boff[t] = pr->boff[t];
@@ -495,7 +502,7 @@ int xtwx_impl(const PtmProblem* pr, int term, const R* params, long long C, R* x
 
 void free_all(PtmProblem* p) {
   cudaFree(p->d_y); cudaFree(p->d_X); cudaFree(p->d_knots); cudaFree(p->d_grid);
-  cudaFree(p->d_Zall); cudaFree(p->d_Kall); cudaFree(p->d_Zd); cudaFree(p->d_tc);
+  cudaFree(p->d_Zall); cudaFree(p->d_Kall); cudaFree(p->d_Zd); cudaFree(p->d_tc); cudaFree(p->d_tc64);
 }
 
 }  // namespace

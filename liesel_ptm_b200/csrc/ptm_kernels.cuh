@@ -41,7 +41,7 @@ struct MainArgs {
   const R* grid;     // [1002]
   const R* Gamma;    // [T][kMaxNbases][C]  gamma_t = Z_t beta_t, chain fastest
   const R* cc;       // [KK*5 + 6][C]       cubic pieces, boundary values, intercepts
-  R* partial;        // [n_items][NSLOT][32]
+  double* partial;   // [n_items][NSLOT][32] partial sums, double for both kernels
   long long n;
   long long obs_begin, obs_end;
   long long chunk_len;
@@ -157,10 +157,11 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   R* s_cc = s_gam + a.sum_nb * 32;                          // [NCC][32]
   R* s_gv = s_cc + NCC * 32;                                // [NU][NGV][32]
   R* s_g = s_gv + (GRAD ? NU * NGV * 32 : 0);               // [2][To][2][32]
-  R* s_b = s_g + 2 * To * 2 * 32;                           // [T][3][To][4]
+  const int g_elems = max(2 * To * 2 * 32, NU * kRegSlots * 32 * (int)(sizeof(double) / sizeof(R)));
+  R* s_b = s_g + g_elems;                                   // [T][3][To][4]
   R* s_kn = s_b + T * 3 * To * 4;                           // [T][4][kKnotStride]
-  R* s_red = s_g;  // [NU][kRegSlots][32] scalar partials: written after the last tile only,
-                   // so they reuse the dl/deta tiles (2*To*64 >= NU*9*32 for To >= 2.25 NU)
+  double* s_red = reinterpret_cast<double*>(s_g);  // [NU][kRegSlots][32] scalar partials (double),
+                   // written after the last tile only: they reuse the dl/deta tiles
   int* s_j = reinterpret_cast<int*>(s_kn + T * 4 * kKnotStride);  // [T][3][To] (+ pad)
 
   const bool is_term = warp < T;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
     const int ntiles = (int)((len + To - 1) / To);
     int chain = cg * 32 + lane;
     if (chain >= a.C) chain = a.C - 1;
-    R* pout = a.partial + (long long)item * a.NSLOT * 32;
+    double* pout = a.partial + (long long)item * a.NSLOT * 32;
 
     if (is_term) {
       // =========================== term warp ========================================
@@ -206,9 +207,17 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
       for (int j = 0; j < t_nb; ++j)
         s_gam[(a.goff[term] + j) * 32 + lane] = a.Gamma[((long long)term * kMaxNbases + j) * a.C + chain];
       R acc[GRAD ? NB : 1];
+      // float kernel: the register accumulators are flushed into doubles every 8 tiles so
+      // that a chunk of ~10^4..10^5 observations does not accumulate float round-off
+      constexpr bool kFlush = GRAD && sizeof(R) == 4;
+      double dacc[kFlush ? NB : 1];
       if constexpr (GRAD) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) acc[j] = R(0);
+      }
+      if constexpr (kFlush) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) dacc[j] = 0.0;
       }
       const R* kn = s_kn + term * 4 * kKnotStride;
       auto stage = [&](int tile) {
@@ -249,12 +258,22 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             }
           }
         }
+        if constexpr (kFlush) {
+          if ((s & 7) == 7) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) { dacc[j] += (double)acc[j]; acc[j] = R(0); }
+          }
+        }
         cta_bar();
       }
       if constexpr (GRAD) {
 #pragma unroll
         for (int j = 0; j < NB; ++j)
-          if (j < t_nb) pout[(kRegSlots + NGV + a.goff[term] + j) * 32 + lane] = acc[j];
+          if (j < t_nb) {
+            double v = (double)acc[j];
+            if constexpr (kFlush) v += dacc[j];
+            pout[(kRegSlots + NGV + a.goff[term] + j) * 32 + lane] = v;
+          }
       }
     } else {
       // =========================== eval warp ========================================
@@ -271,8 +290,10 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
       const R gamma0 = a.cc[(long long)(KK * 5 + 5) * a.C + chain];
       const R cLe = cL_of(ts, ts.min_eps);
       const R cRe = cR_of(ts, ts.max_eps);
-      R a_z2 = R(0), a_ls = R(0), a_pm = R(1), a_gb0 = R(0), a_gg0 = R(0);
-      R a_gvl = R(0), a_gdl = R(0), a_gvr = R(0), a_gdr = R(0);
+      // scalar sums in double for both kernels (a handful of adds per observation)
+      double a_z2 = 0, a_ls = 0, a_gb0 = 0, a_gg0 = 0;
+      double a_gvl = 0, a_gdl = 0, a_gvr = 0, a_gdr = 0;
+      R a_pm = R(1);
       int a_pe = 0;
       const R sixth = R(1) / R(6);
       cta_bar();
@@ -341,8 +362,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             const R tiny = tiny_of<R>();
             const bool above = d > tiny;
             const R dcl = above ? d : tiny;
-            a_z2 = fma(z, z, a_z2);
-            a_ls += es;
+            a_z2 += (double)(z * z);
+            a_ls += (double)es;
             {
               R mant; int ex;
               split_mant(dcl, mant, ex);
@@ -357,8 +378,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               const R gls = fma(-gr, r, R(-1));
               gb[o * 64] = gmu;
               gb[o * 64 + 32] = gls;
-              a_gb0 += gmu;
-              a_gg0 += gls;
+              a_gb0 += (double)gmu;
+              a_gg0 += (double)gls;
               // gradient w.r.t. the five piece coefficients -> B-spline coefficients
               // vt[kk .. kk+4] (transpose of piece_coefs); zero weights off the core
               R w[5];
@@ -375,18 +396,18 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               if (!core) {
                 if (code == 1) {
                   const R q = (ts.a - r) * ts.inv_w;
-                  a_gvl += lz;
-                  a_gdl += fma(lz, cL_of(ts, r), ld * (R(1) - q));
+                  a_gvl += (double)lz;
+                  a_gdl += (double)fma(lz, cL_of(ts, r), ld * (R(1) - q));
                 } else if (code == 3) {
                   const R q = (r - ts.b) * ts.inv_w;
-                  a_gvr += lz;
-                  a_gdr += fma(lz, cR_of(ts, r), ld * (R(1) - q));
+                  a_gvr += (double)lz;
+                  a_gdr += (double)fma(lz, cR_of(ts, r), ld * (R(1) - q));
                 } else if (code == 0) {
-                  a_gvl += lz;
-                  a_gdl = fma(lz, cLe, a_gdl);
+                  a_gvl += (double)lz;
+                  a_gdl += (double)(lz * cLe);
                 } else {
-                  a_gvr += lz;
-                  a_gdr = fma(lz, cRe, a_gdr);
+                  a_gvr += (double)lz;
+                  a_gdr += (double)(lz * cRe);
                 }
               }
             }
@@ -401,10 +422,10 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
         }
         cta_bar();
       }
-      R* rp = s_red + (uw * kRegSlots) * 32 + lane;
+      double* rp = s_red + (uw * kRegSlots) * 32 + lane;
       rp[SL_Z2 * 32] = a_z2;
       rp[SL_LS * 32] = a_ls;
-      rp[SL_LOGD * 32] = log(a_pm) + R(a_pe) * R(0.69314718055994530942);
+      rp[SL_LOGD * 32] = log((double)a_pm) + (double)a_pe * 0.69314718055994530942;
       rp[SL_GB0 * 32] = a_gb0;
       rp[SL_GG0 * 32] = a_gg0;
       rp[SL_GVL * 32] = a_gvl;
@@ -417,14 +438,14 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
     {
       const int nreg = GRAD ? kRegSlots : 3;
       for (int idx = tid; idx < nreg * 32; idx += blockDim.x) {
-        R v = R(0);
+        double v = 0.0;
         for (int w = 0; w < NU; ++w) v += s_red[w * kRegSlots * 32 + idx];
         pout[idx] = v;
       }
       if (GRAD) {
         for (int idx = tid; idx < NGV * 32; idx += blockDim.x) {
-          R v = R(0);
-          for (int w = 0; w < NU; ++w) v += s_gv[w * NGV * 32 + idx];
+          double v = 0.0;
+          for (int w = 0; w < NU; ++w) v += (double)s_gv[w * NGV * 32 + idx];
           pout[kRegSlots * 32 + idx] = v;
         }
       }
@@ -446,7 +467,7 @@ struct PreArgs {
   R* cc;             // [KK*5+6][C]
   const R* Zall;     // packed Z_t, row-major [nb_t][p_t]
   const R* Zd;       // [nparam][nparam-1]
-  const TrafoConst<R>* tc;
+  const TrafoConst<double>* tc;  // double constants: the prologue runs in double
   int C, P, T;
   int nb[kMaxTerms], p[kMaxTerms], zoff[kMaxTerms], boff[kMaxTerms];
   int dz_off;
@@ -454,6 +475,10 @@ struct PreArgs {
 
 template <typename R>
 __global__ void k_pre(const PreArgs<R> a) {
+  // Per-chain tables are computed in double for both kernels and rounded to R once:
+  // the piece coefficients are first / second differences of the cumulative spline
+  // coefficients, which would carry a systematic ~1e-4 relative error in float.
+  typedef double D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* s_par = reinterpret_cast<R*>(smem_raw);  // [P]
   const int c = blockIdx.x;
@@ -465,34 +490,34 @@ __global__ void k_pre(const PreArgs<R> a) {
     if (j < a.nb[t]) {
       const R* zr = a.Zall + a.zoff[t] + j * a.p[t];
       const R* b = s_par + a.boff[t];
-      R v = R(0);
-      for (int k = 0; k < a.p[t]; ++k) v = fma(zr[k], b[k], v);
-      a.Gamma[((long long)t * kMaxNbases + j) * a.C + c] = v;
+      D v = 0.0;
+      for (int k = 0; k < a.p[t]; ++k) v = fma((D)zr[k], (D)b[k], v);
+      a.Gamma[((long long)t * kMaxNbases + j) * a.C + c] = (R)v;
     }
   }
   if (tid == 0) {
-    const TrafoConst<R>& tc = *a.tc;
+    const TrafoConst<D>& tc = *a.tc;
     const int np_ = tc.nparam, KK = tc.KK;
-    R delta[kMaxNparam], e[kMaxNparam], sm[kMaxNparam], vt[kMaxJ];
+    D delta[kMaxNparam], e[kMaxNparam], sm[kMaxNparam], vt[kMaxJ];
     const R* dz = s_par + a.dz_off;
     for (int j = 0; j < np_; ++j) {
-      R v = R(0);
-      for (int k = 0; k < np_ - 1; ++k) v = fma(a.Zd[j * (np_ - 1) + k], dz[k], v);
+      D v = 0.0;
+      for (int k = 0; k < np_ - 1; ++k) v = fma((D)a.Zd[j * (np_ - 1) + k], (D)dz[k], v);
       delta[j] = v;
     }
     coef_map_forward(tc, delta, e, sm, vt);
-    R cfirst[5], clast[5];
+    D cfirst[5], clast[5];
     for (int kk = 0; kk < KK; ++kk) {
-      R cq[5];
+      D cq[5];
       piece_coefs(vt, kk, KK, cq);
-      for (int q = 0; q < 5; ++q) a.cc[(long long)(kk * 5 + q) * a.C + c] = cq[q];
+      for (int q = 0; q < 5; ++q) a.cc[(long long)(kk * 5 + q) * a.C + c] = (R)cq[q];
       if (kk == 0) for (int q = 0; q < 5; ++q) cfirst[q] = cq[q];
       if (kk == KK - 1) for (int q = 0; q < 5; ++q) clast[q] = cq[q];
     }
-    a.cc[(long long)(KK * 5 + 0) * a.C + c] = cfirst[0];
-    a.cc[(long long)(KK * 5 + 1) * a.C + c] = cfirst[1] * tc.inv_dk;
-    a.cc[(long long)(KK * 5 + 2) * a.C + c] = ((clast[0] + clast[1]) + clast[2]) + clast[3];
-    a.cc[(long long)(KK * 5 + 3) * a.C + c] = (clast[1] + R(2) * clast[2] + R(3) * clast[3]) * tc.inv_dk;
+    a.cc[(long long)(KK * 5 + 0) * a.C + c] = (R)cfirst[0];
+    a.cc[(long long)(KK * 5 + 1) * a.C + c] = (R)(cfirst[1] * tc.inv_dk);
+    a.cc[(long long)(KK * 5 + 2) * a.C + c] = (R)(((clast[0] + clast[1]) + clast[2]) + clast[3]);
+    a.cc[(long long)(KK * 5 + 3) * a.C + c] = (R)((clast[1] + 2.0 * clast[2] + 3.0 * clast[3]) * tc.inv_dk);
     a.cc[(long long)(KK * 5 + 4) * a.C + c] = s_par[0];
     a.cc[(long long)(KK * 5 + 5) * a.C + c] = s_par[1];
   }
@@ -505,13 +530,13 @@ __global__ void k_pre(const PreArgs<R> a) {
 template <typename R>
 struct PostArgs {
   const R* params;   // [C][P]
-  const R* partial;  // [CG*M][NSLOT][32]
+  const double* partial;  // [CG*M][NSLOT][32]
   R* logp;           // [C]
   R* grad;           // [C][P] or null
   const R* Zall;
   const R* Kall;     // packed K_t [p_t][p_t]
   const R* Zd;
-  const TrafoConst<R>* tc;
+  const TrafoConst<double>* tc;  // double constants: the epilogue runs in double
   int C, P, T, M, NSLOT, KK;
   int nb[kMaxTerms], p[kMaxTerms], zoff[kMaxTerms], koff[kMaxTerms], boff[kMaxTerms];
   int goff[kMaxTerms], rank[kMaxTerms];
@@ -522,21 +547,25 @@ struct PostArgs {
 
 template <typename R, bool GRAD>
 __global__ void k_post(const PostArgs<R> a) {
+  // All reductions and the chain rule run in double for both kernels: the partials are
+  // double, Z_t' grad(gamma_t) cancels heavily (sum-to-zero constraint, 1/sqrt(eigenvalue)
+  // columns) and would lose ~2 digits in float.  Results are rounded to R at the end.
+  typedef double D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  R* red = reinterpret_cast<R*>(smem_raw);  // [NSLOT][32]
-  R* s_lp = red + a.NSLOT * 32;             // [32] prior accumulator per chain
+  D* red = reinterpret_cast<D*>(smem_raw);  // [NSLOT][32]
+  D* s_lp = red + a.NSLOT * 32;             // [32] prior accumulator per chain
   const int cg = blockIdx.x;
   const int tid = threadIdx.x;
   const int KK = a.KK;
   for (int idx = tid; idx < a.NSLOT * 32; idx += blockDim.x) {
-    R v = R(0);
-    const R* pp = a.partial + ((long long)cg * a.M * a.NSLOT) * 32 + idx;
+    D v = 0.0;  // fixed order => deterministic
+    const D* pp = a.partial + ((long long)cg * a.M * a.NSLOT) * 32 + idx;
     for (int m = 0; m < a.M; ++m) v += pp[(long long)m * a.NSLOT * 32];
     red[idx] = v;
   }
-  if (tid < 32) s_lp[tid] = R(0);
+  if (tid < 32) s_lp[tid] = 0.0;
   __syncthreads();
-  const R half_log_2pi = R(0.91893853320467274178);
+  const D half_log_2pi = 0.91893853320467274178;
 
   // smooth-term priors and gradients: one thread per (lane, term)
   for (int idx = tid; idx < 32 * a.T; idx += blockDim.x) {
@@ -547,17 +576,17 @@ __global__ void k_post(const PostArgs<R> a) {
     const R* b = par + a.boff[t];
     const R* Kt = a.Kall + a.koff[t];
     const int p = a.p[t];
-    const R tau = par[a.tau_off + t];
-    R quad = R(0);
+    const D tau = (D)par[a.tau_off + t];
+    D quad = 0.0;
     for (int i = 0; i < p; ++i) {
-      R kb = R(0);
-      for (int k = 0; k < p; ++k) kb = fma(Kt[i * p + k], b[k], kb);
-      quad = fma(b[i], kb, quad);
+      D kb = 0.0;
+      for (int k = 0; k < p; ++k) kb = fma((D)Kt[i * p + k], (D)b[k], kb);
+      quad = fma((D)b[i], kb, quad);
     }
-    const R it2 = R(1) / (tau * tau);
+    const D it2 = 1.0 / (tau * tau);
     if (a.add_priors) {
-      atomicAdd(&s_lp[lane], -(log(tau) * R(a.rank[t]) + R(0.5) * quad * it2));
-      if (GRAD) a.grad[(long long)c * a.P + a.tau_off + t] = -R(a.rank[t]) / tau + quad * it2 / tau;
+      atomicAdd(&s_lp[lane], -(log(tau) * (D)a.rank[t] + 0.5 * quad * it2));
+      if (GRAD) a.grad[(long long)c * a.P + a.tau_off + t] = (R)(-(D)a.rank[t] / tau + quad * it2 / tau);
     } else if (GRAD) {
       a.grad[(long long)c * a.P + a.tau_off + t] = R(0);
     }
@@ -573,17 +602,17 @@ __global__ void k_post(const PostArgs<R> a) {
         const int c = cg * 32 + lane;
         if (c >= a.C) continue;
         const R* par = a.params + (long long)c * a.P;
-        const R* gg = red + (kRegSlots + KK + 4 + a.goff[t]) * 32 + lane;
-        R v = R(0);
-        for (int j = 0; j < nb; ++j) v = fma(Zt[j * p + k], gg[j * 32], v);
+        const D* gg = red + (kRegSlots + KK + 4 + a.goff[t]) * 32 + lane;
+        D v = 0.0;
+        for (int j = 0; j < nb; ++j) v = fma((D)Zt[j * p + k], gg[j * 32], v);
         if (a.add_priors) {
-          const R tau = par[a.tau_off + t];
+          const D tau = (D)par[a.tau_off + t];
           const R* b = par + a.boff[t];
-          R kb = R(0);
-          for (int i = 0; i < p; ++i) kb = fma(Kt[k * p + i], b[i], kb);
+          D kb = 0.0;
+          for (int i = 0; i < p; ++i) kb = fma((D)Kt[k * p + i], (D)b[i], kb);
           v -= kb / (tau * tau);
         }
-        a.grad[(long long)c * a.P + a.boff[t] + k] = v;
+        a.grad[(long long)c * a.P + a.boff[t] + k] = (R)v;
       }
     }
   }
@@ -593,50 +622,48 @@ __global__ void k_post(const PostArgs<R> a) {
     const int lane = tid;
     const int c = cg * 32 + lane;
     if (c < a.C) {
-      const TrafoConst<R>& tc = *a.tc;
+      const TrafoConst<D>& tc = *a.tc;
       const int np_ = tc.nparam;
       const R* par = a.params + (long long)c * a.P;
       const R* dz = par + a.dz_off;
-      const R taud = par[a.taud_off];
-      R ss = R(0);
-      for (int k = 0; k < np_ - 1; ++k) ss = fma(dz[k], dz[k], ss);
-      R lp = R(-0.5) * red[SL_Z2 * 32 + lane] + red[SL_LOGD * 32 + lane] - red[SL_LS * 32 + lane] -
-             R(a.n_obs) * half_log_2pi;
+      const D taud = (D)par[a.taud_off];
+      D ss = 0.0;
+      for (int k = 0; k < np_ - 1; ++k) ss = fma((D)dz[k], (D)dz[k], ss);
+      D lp = -0.5 * red[SL_Z2 * 32 + lane] + red[SL_LOGD * 32 + lane] - red[SL_LS * 32 + lane] -
+             (D)a.n_obs * half_log_2pi;
       if (a.add_priors) {
         lp += s_lp[lane];
-        lp += R(-0.5) * ss / (taud * taud) - R(np_ - 1) * (log(taud) + half_log_2pi);
+        lp += -0.5 * ss / (taud * taud) - (D)(np_ - 1) * (log(taud) + half_log_2pi);
       }
-      a.logp[c] = lp;
+      a.logp[c] = (R)lp;
       if (GRAD) {
         R* go = a.grad + (long long)c * a.P;
-        go[0] = red[SL_GB0 * 32 + lane];
-        go[1] = red[SL_GG0 * 32 + lane];
-        go[a.taud_off] = a.add_priors ? ss / (taud * taud * taud) - R(np_ - 1) / taud : R(0);
-        // boundary gradients fold into the first / last piece
-        R delta[kMaxNparam], e[kMaxNparam], sm[kMaxNparam], vt[kMaxJ], gvt[kMaxJ], gdelta[kMaxNparam];
+        go[0] = (R)red[SL_GB0 * 32 + lane];
+        go[1] = (R)red[SL_GG0 * 32 + lane];
+        go[a.taud_off] = a.add_priors ? (R)(ss / (taud * taud * taud) - (D)(np_ - 1) / taud) : R(0);
+        D delta[kMaxNparam], e[kMaxNparam], sm[kMaxNparam], vt[kMaxJ], gvt[kMaxJ], gdelta[kMaxNparam];
         for (int j = 0; j < np_; ++j) {
-          R v = R(0);
-          for (int k = 0; k < np_ - 1; ++k) v = fma(a.Zd[j * (np_ - 1) + k], dz[k], v);
+          D v = 0.0;
+          for (int k = 0; k < np_ - 1; ++k) v = fma((D)a.Zd[j * (np_ - 1) + k], (D)dz[k], v);
           delta[j] = v;
         }
         coef_map_forward(tc, delta, e, sm, vt);
         for (int j = 0; j <= np_; ++j) gvt[j] = red[(kRegSlots + j) * 32 + lane];
         // boundary gradients fold into the first / last piece (ptm.py:417-419)
-        const R gvl = red[SL_GVL * 32 + lane], gdl = red[SL_GDL * 32 + lane];
-        const R gvr = red[SL_GVR * 32 + lane], gdr = red[SL_GDR * 32 + lane];
+        const D gvl = red[SL_GVL * 32 + lane], gdl = red[SL_GDL * 32 + lane];
+        const D gvr = red[SL_GVR * 32 + lane], gdr = red[SL_GDR * 32 + lane];
         {
-          R gc[5] = {gvl, gdl * tc.inv_dk, R(0), R(0), R(0)};
+          D gc[5] = {gvl, gdl * tc.inv_dk, 0.0, 0.0, 0.0};
           piece_coefs_backward(gc, 0, KK, gvt);
-          R gl[5] = {gvr, gvr + gdr * tc.inv_dk, gvr + R(2) * gdr * tc.inv_dk,
-                     gvr + R(3) * gdr * tc.inv_dk, R(0)};
+          D gl[5] = {gvr, gvr + gdr * tc.inv_dk, gvr + 2.0 * gdr * tc.inv_dk, gvr + 3.0 * gdr * tc.inv_dk, 0.0};
           piece_coefs_backward(gl, KK - 1, KK, gvt);
         }
         coef_map_backward(tc, gvt, e, sm, gdelta);
         for (int k = 0; k < np_ - 1; ++k) {
-          R v = R(0);
-          for (int j = 0; j < np_; ++j) v = fma(a.Zd[j * (np_ - 1) + k], gdelta[j], v);
-          if (a.add_priors) v -= dz[k] / (taud * taud);
-          go[a.dz_off + k] = v;
+          D v = 0.0;
+          for (int j = 0; j < np_; ++j) v = fma((D)a.Zd[j * (np_ - 1) + k], gdelta[j], v);
+          if (a.add_priors) v -= (D)dz[k] / (taud * taud);
+          go[a.dz_off + k] = (R)v;
         }
       }
     }
