@@ -23,6 +23,8 @@
  *                                  74-210 (called at gam/var.py:1001-1002).
  *   ptm_transform_*                TransformationSpline.dot_and_deriv_n_fullbatch:
  *                                  bspline/util.py:91-103.
+ *   ptm_quadform_*                 beta' K beta of the Gibbs scale updates:
+ *                                  gam/kernel.py:29-39, kernel.py:99-111.
  *   ptm_xtwx_* / ptm_loc_precision_*  GaussianLocCholInfo.working_weights /
  *                                  precision / chol_info: iwls_proposals.py:55-89
  *                                  (scale terms, W == 2: 118-144).
@@ -161,6 +163,14 @@ int ptm_loc_precision_f64(const PtmProblem* prob, int32_t term, const double* pa
 int ptm_loc_precision_f32(const PtmProblem* prob, int32_t term, const float* params,
                           int64_t n_chains, float* precision, float* chol,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* quad[c, t] = beta_t' K_t beta_t for every chain and smooth term: the quadratic form of
+ * the Gibbs updates of the smoothing variances (gam/kernel.py:29-39, kernel.py:99-111:
+ * b + 0.5 * beta' K beta) and of the prior (gam/dist.py:64-70).  quad is [C, T]. */
+int ptm_quadform_f64(const PtmProblem* prob, const double* params, int64_t n_chains,
+                     double* quad, void* stream);
+int ptm_quadform_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
+                     float* quad, void* stream);
 
 /* Number of kernels the last logp / logp_grad call on this thread launched. */
 int ptm_last_launch_count(void);

@@ -73,6 +73,7 @@ struct PtmProblem {
   void* d_Zd = nullptr;
   void* d_tc = nullptr;
   void* d_tc64 = nullptr;  // TrafoConst<double> for the epilogue
+  void* d_meta = nullptr;  // int [T][3]: p, koff, boff
   ptm::TrafoConst<double> tc64;  // host copy (double); cast for f32
 };
 
@@ -240,6 +241,10 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
     fill_tc<R>(tc, tcr);
     PTM_CUDA(cudaMalloc(&pr->d_tc, sizeof tcr));
     PTM_CUDA(cudaMemcpy(pr->d_tc, &tcr, sizeof tcr, cudaMemcpyHostToDevice));
+    std::vector<int> meta(std::max(T, 1) * 3, 0);
+    for (int t = 0; t < T; ++t) { meta[t * 3] = pr->p[t]; meta[t * 3 + 1] = pr->koff[t]; meta[t * 3 + 2] = pr->boff[t]; }
+    PTM_CUDA(cudaMalloc(&pr->d_meta, meta.size() * sizeof(int)));
+    PTM_CUDA(cudaMemcpy(pr->d_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice));
     ptm::TrafoConst<double> tcd;
     memset(&tcd, 0, sizeof tcd);
     fill_tc<double>(tc, tcd);
@@ -500,9 +505,24 @@ int xtwx_impl(const PtmProblem* pr, int term, const R* params, long long C, R* x
   return PTM_OK;
 }
 
+template <typename R>
+int quadform_impl(const PtmProblem* pr, const R* params, long long C, R* quad, void* stream) {
+  if (!pr || !params || !quad) return fail(PTM_ERR_NULL, "null argument");
+  if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  if (C < 1) return fail(PTM_ERR_SHAPE, "n_chains must be >= 1");
+  if (pr->T == 0) return PTM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = C * pr->T;
+  ptm::k_quadform<R><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+      params, (int)C, pr->P, pr->T, reinterpret_cast<const R*>(pr->d_Kall),
+      reinterpret_cast<const int*>(pr->d_meta), quad);
+  PTM_CUDA(cudaGetLastError());
+  return PTM_OK;
+}
+
 void free_all(PtmProblem* p) {
   cudaFree(p->d_y); cudaFree(p->d_X); cudaFree(p->d_knots); cudaFree(p->d_grid);
-  cudaFree(p->d_Zall); cudaFree(p->d_Kall); cudaFree(p->d_Zd); cudaFree(p->d_tc); cudaFree(p->d_tc64);
+  cudaFree(p->d_Zall); cudaFree(p->d_Kall); cudaFree(p->d_Zd); cudaFree(p->d_tc); cudaFree(p->d_tc64); cudaFree(p->d_meta);
 }
 
 }  // namespace
@@ -620,6 +640,13 @@ int ptm_loc_precision_f32(const PtmProblem* p, int32_t term, const float* params
                           float* chol, void* ws, size_t wsb, void* st) {
   if (!precision) return fail(PTM_ERR_NULL, "precision is null");
   return xtwx_impl<float>(p, term, params, C, nullptr, precision, chol, ws, wsb, st);
+}
+
+int ptm_quadform_f64(const PtmProblem* p, const double* params, int64_t C, double* quad, void* st) {
+  return quadform_impl<double>(p, params, C, quad, st);
+}
+int ptm_quadform_f32(const PtmProblem* p, const float* params, int64_t C, float* quad, void* st) {
+  return quadform_impl<float>(p, params, C, quad, st);
 }
 
 int ptm_last_launch_count(void) { return g_launches; }

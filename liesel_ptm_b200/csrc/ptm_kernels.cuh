@@ -671,6 +671,27 @@ __global__ void k_post(const PostArgs<R> a) {
 }
 
 // ------------------------------------------------------------------------------
+// beta_t' K_t beta_t per (chain, term): one thread each, double accumulation.
+// ------------------------------------------------------------------------------
+template <typename R>
+__global__ void k_quadform(const R* __restrict__ params, int C, int P, int T, const R* __restrict__ Kall,
+                           const int* __restrict__ meta /* [T][3]: p, koff, boff */, R* __restrict__ quad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * T) return;
+  const int c = idx / T, t = idx - c * T;
+  const int p = meta[t * 3], koff = meta[t * 3 + 1], boff = meta[t * 3 + 2];
+  const R* b = params + (long long)c * P + boff;
+  const R* Kt = Kall + koff;
+  double q = 0.0;
+  for (int i = 0; i < p; ++i) {
+    double kb = 0.0;
+    for (int k = 0; k < p; ++k) kb = fma((double)Kt[i * p + k], (double)b[k], kb);
+    q = fma((double)b[i], kb, q);
+  }
+  quad[idx] = (R)q;
+}
+
+// ------------------------------------------------------------------------------
 // K1: banded design of one term (test / inspection entry; the fused kernel calls
 // the same device function inline).
 // ------------------------------------------------------------------------------

@@ -332,6 +332,16 @@ class LocScalePTM:
             z, dz = z[..., 0], dz[..., 0]
         return z, dz
 
+    def quadform(self, params: torch.Tensor) -> torch.Tensor:
+        """beta_t' K_t beta_t for every chain and term, [C, T]: the quadratic form of the
+        Gibbs updates of the smoothing variances (gam/kernel.py:29-39, kernel.py:99-111)."""
+        params = self._check_params(params)
+        Cn = params.shape[0]
+        out = torch.empty((Cn, len(self.terms)), dtype=self.dtype, device=self.device)
+        f = getattr(self._lib, f"ptm_quadform_{self._sfx}")
+        _lib.check(f(self._handle, params.data_ptr(), Cn, out.data_ptr(), self._stream()))
+        return out
+
     def xtwx(self, term_index: int, params: torch.Tensor) -> torch.Tensor:
         params = self._check_params(params)
         Cn = params.shape[0]

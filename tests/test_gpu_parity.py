@@ -65,6 +65,15 @@ def test_transform_matches_oracle():
     assert np.all(cell[~core] == -1)
 
 
+def test_quadform():
+    """beta' K beta of the Gibbs scale updates (gam/kernel.py:29-39)."""
+    case = build_case(n=50, n_loc=2, n_scale=1, nbases=12, C=5)
+    q = case.model.quadform(torch.from_numpy(case.params).cuda()).cpu().numpy()
+    for t, term in enumerate(case.omodel.terms):
+        ref = np.einsum("ci,ij,cj->c", case.state.beta[t], term.K, case.state.beta[t])
+        assert rel_err(q[:, t], ref) < 1e-13
+
+
 def test_xtwx_and_precision():
     case = build_case(n=2000, n_loc=2, n_scale=2, nbases=12, C=4)
     params = torch.from_numpy(case.params).cuda()
