@@ -1,0 +1,190 @@
+"""Batched MCMC transitions over the fused operator (host glue, torch on the GPU).
+
+This is the *caller* side of the hot path, restated so that the reference's headline
+"ESS/s" can be measured without liesel.goose: every transition below touches the model
+only through ``log_prob_and_grad`` / ``precision`` (the C ABI), for all chains at once.
+
+* ``iwls_transition`` follows ``IWLSKernelFixed._standard_transition``
+  (iwls_fixed.py:145-188) and ``gs.IWLSKernel`` (same algorithm with
+  ``chol_info_fn(state)`` evaluated at the current and the proposed state,
+  iwls_proposals.py:82-89): proposal mean ``pos + s^2/2 * P^-1 score``, a Gaussian
+  draw with precision-Cholesky ``chol / s``, the reverse density, Metropolis-Hastings.
+  ``solve`` / ``mvn_sample`` / ``mvn_log_prob`` restate liesel.goose.iwls_utils (not in
+  tree): precision-Cholesky parameterisation, log-density without the 2*pi constant
+  cancelling in the ratio.
+* ``mala_transition`` is a plain preconditioned Langevin step for blocks without an
+  information matrix (the transformation coefficients delta_z; the reference samples
+  them with NUTS from blackjax, which is out of scope).
+
+Smoothing scales tau are held fixed (their Gibbs / NUTS updates are O(1) per chain and
+stay with the host sampler).
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import time
+
+import numpy as np
+import torch
+
+from .model import LocScalePTM
+
+
+def _solve(chol: torch.Tensor, rhs: torch.Tensor) -> torch.Tensor:
+    """P^-1 rhs from the lower Cholesky factor of P (iwls_utils.solve)."""
+    return torch.cholesky_solve(rhs.unsqueeze(-1), chol).squeeze(-1)
+
+
+def _mvn_sample(gen, mean: torch.Tensor, chol_prec: torch.Tensor) -> torch.Tensor:
+    """mean + L^-T z for precision P = L L' (iwls_utils.mvn_sample)."""
+    z = torch.randn(mean.shape, dtype=mean.dtype, device=mean.device, generator=gen)
+    return mean + torch.linalg.solve_triangular(chol_prec.transpose(-1, -2), z.unsqueeze(-1), upper=True).squeeze(-1)
+
+
+def _mvn_log_prob(x: torch.Tensor, mean: torch.Tensor, chol_prec: torch.Tensor) -> torch.Tensor:
+    """log N(x; mean, (L L')^-1) up to the 2*pi constant (iwls_utils.mvn_log_prob)."""
+    zq = ((x - mean).unsqueeze(-2) @ chol_prec).squeeze(-2)
+    return -0.5 * (zq * zq).sum(-1) + torch.log(torch.diagonal(chol_prec, dim1=-2, dim2=-1)).sum(-1)
+
+
+@dataclasses.dataclass
+class TransitionInfo:
+    accepted: torch.Tensor  # [C] bool
+    log_alpha: torch.Tensor  # [C]
+
+
+def _mh(gen, params, prop, logp, logp_prop, correction):
+    log_alpha = logp_prop - logp + correction
+    log_alpha = torch.where(torch.isnan(log_alpha), torch.full_like(log_alpha, -float("inf")), log_alpha)
+    u = torch.rand(logp.shape, dtype=logp.dtype, device=logp.device, generator=gen)
+    acc = torch.log(u) < log_alpha
+    return torch.where(acc[:, None], prop, params), acc, log_alpha
+
+
+def iwls_transition(model: LocScalePTM, params: torch.Tensor, term_index: int, step_size: float, gen,
+                    cache=None):
+    """One IWLS-MH transition of the coefficient block of ``term_index`` for all chains.
+    Cost per call: 2 logp+grad sweeps and 2 information sweeps (iwls_fixed.py:159-186)."""
+    lo = model.layout["beta"][term_index]
+    p = model.terms[term_index][0].basis.ncoef
+    s = step_size
+    if torch.is_tensor(s):  # per-chain step sizes
+        s = s[:, None]
+    if cache is None:
+        logp, grad = model.log_prob_and_grad(params)
+        logp, grad = logp.clone(), grad.clone()
+    else:
+        logp, grad = cache
+    _, chol = model.precision(term_index, params)
+    pos = params[:, lo: lo + p]
+    mu = pos + 0.5 * s * s * _solve(chol, grad[:, lo: lo + p])
+    s3 = s[:, :, None] if torch.is_tensor(s) else s
+    prop_block = _mvn_sample(gen, mu, chol / s3)
+    fwd = _mvn_log_prob(prop_block, mu, chol / s3)
+    prop = params.clone()
+    prop[:, lo: lo + p] = prop_block
+    logp_p, grad_p = model.log_prob_and_grad(prop)
+    logp_p, grad_p = logp_p.clone(), grad_p.clone()
+    _, chol_p = model.precision(term_index, prop)
+    mu_p = prop_block + 0.5 * s * s * _solve(chol_p, grad_p[:, lo: lo + p])
+    bwd = _mvn_log_prob(pos, mu_p, chol_p / s3)
+    new, acc, la = _mh(gen, params, prop, logp, logp_p, bwd - fwd)
+    new_logp = torch.where(acc, logp_p, logp)
+    new_grad = torch.where(acc[:, None], grad_p, grad)
+    return new, (new_logp, new_grad), TransitionInfo(acc, la)
+
+
+def mala_transition(model: LocScalePTM, params: torch.Tensor, lo: int, width: int, step_size, gen,
+                    cache=None):
+    """Metropolis-adjusted Langevin step on params[:, lo:lo+width] (identity metric)."""
+    if cache is None:
+        logp, grad = model.log_prob_and_grad(params)
+        logp, grad = logp.clone(), grad.clone()
+    else:
+        logp, grad = cache
+    s = step_size if torch.is_tensor(step_size) else torch.full((params.shape[0],), float(step_size),
+                                                                 dtype=params.dtype, device=params.device)
+    s = s[:, None]
+    pos = params[:, lo: lo + width]
+    mu = pos + 0.5 * s * s * grad[:, lo: lo + width]
+    z = torch.randn(pos.shape, dtype=pos.dtype, device=pos.device, generator=gen)
+    prop_block = mu + s * z
+    prop = params.clone()
+    prop[:, lo: lo + width] = prop_block
+    logp_p, grad_p = model.log_prob_and_grad(prop)
+    logp_p, grad_p = logp_p.clone(), grad_p.clone()
+    mu_p = prop_block + 0.5 * s * s * grad_p[:, lo: lo + width]
+    fwd = -0.5 * (((prop_block - mu) / s) ** 2).sum(-1)
+    bwd = -0.5 * (((pos - mu_p) / s) ** 2).sum(-1)
+    new, acc, la = _mh(gen, params, prop, logp, logp_p, bwd - fwd)
+    return new, (torch.where(acc, logp_p, logp), torch.where(acc[:, None], grad_p, grad)), TransitionInfo(acc, la)
+
+
+def effective_sample_size(x: np.ndarray) -> float:
+    """Bulk ESS of draws x [chains, samples] (Geyer's initial positive sequence on the
+    chain-averaged autocovariance, as arviz / Stan do; rank normalisation omitted)."""
+    x = np.asarray(x, dtype=np.float64)
+    m, n = x.shape
+    xc = x - x.mean(axis=1, keepdims=True)
+    nfft = 1 << int(np.ceil(np.log2(2 * n)))
+    f = np.fft.rfft(xc, nfft, axis=1)
+    acov = np.fft.irfft(f * np.conj(f), nfft, axis=1)[:, :n] / n
+    w = acov[:, 0].mean() * n / (n - 1)
+    b = x.mean(axis=1).var(ddof=1) if m > 1 else 0.0
+    var_plus = w * (n - 1) / n + b
+    if var_plus <= 0:
+        return float(m * n)
+    rho = 1.0 - (w - acov.mean(axis=0)) / var_plus
+    rho[0] = 1.0
+    tau, t = -1.0, 0
+    while t + 1 < n:
+        pair = rho[t] + rho[t + 1]
+        if pair < 0:
+            break
+        tau += 2.0 * pair
+        t += 2
+    return float(m * n / max(tau, 1.0 / np.log10(max(m * n, 10))))
+
+
+def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: int, seed: int = 0,
+               iwls_step: float = 1.0, mala_step: float = 0.02, target_accept: float = 0.6):
+    """Sweep per iteration: an IWLS-MH transition per smooth term, a MALA transition on
+    delta_z (per-chain step size adapted towards ``target_accept`` during warm-up).
+    Returns (draws [draws, C, P] on the host, info dict with timings and acceptance)."""
+    gen = torch.Generator(device=params0.device)
+    gen.manual_seed(seed)
+    params = params0.clone()
+    C = params.shape[0]
+    L = model.layout
+    dz_lo, dz_w = L["delta_z"], model.nparam - 1
+    step = torch.full((C,), float(mala_step), dtype=params.dtype, device=params.device)
+    T = len(model.terms)
+    istep = torch.full((max(T, 1), C), float(iwls_step), dtype=params.dtype, device=params.device)
+    cache = None
+    out = torch.empty((draws, C, params.shape[1]), dtype=params.dtype, device=params.device)
+    acc_iwls, acc_mala, n_it = 0.0, 0.0, 0
+    t_post = 0.0
+    for it in range(warmup + draws):
+        if it == warmup:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        for t in range(T):
+            params, cache, info = iwls_transition(model, params, t, istep[t], gen, cache)
+            if it < warmup:  # dual-averaging stand-in: Robbins-Monro on the log step size
+                a = torch.exp(torch.clamp(info.log_alpha, max=0.0))
+                istep[t] = torch.clamp(istep[t] * torch.exp((a - 0.8) * (10.0 / (it + 10.0))), 1e-3, 2.0)
+            else:
+                acc_iwls += info.accepted.double().mean().item() / T
+        params, cache, info = mala_transition(model, params, dz_lo, dz_w, step, gen, cache)
+        if it < warmup:  # Robbins-Monro adaptation of the per-chain step size
+            a = torch.exp(torch.clamp(info.log_alpha, max=0.0))
+            step = step * torch.exp((a - target_accept) * (10.0 / (it + 10.0)))
+        else:
+            acc_mala += info.accepted.double().mean().item()
+            out[it - warmup] = params
+            n_it += 1
+    torch.cuda.synchronize()
+    t_post = time.perf_counter() - t0
+    return out.cpu().numpy(), {"posterior_seconds": t_post, "accept_iwls": acc_iwls / max(n_it, 1),
+                               "accept_mala": acc_mala / max(n_it, 1), "mala_step_median": float(step.median())}
