@@ -50,7 +50,7 @@ struct MainArgs {
   int nb[kMaxTerms];
   int pred[kMaxTerms];
   int goff[kMaxTerms];   // offset of the term's block in the packed coefficient tables
-  int order[kMaxTerms];  // term indices, location terms first
+  int order[kMaxTerms];  // term indices, location terms first: term warp q owns term order[q]
   R inv_dk[kMaxTerms];
   TrafoScal<R> ts;
 };
@@ -69,6 +69,51 @@ __device__ __forceinline__ void split_mant(float x, float& mant, int& ex) {
   ex = ((bits >> 23) & 0xff) - 127;
   mant = __int_as_float((bits & 0x007fffff) | 0x3f800000);
 }
+
+// exp(x) for the scale predictor: magic-number range reduction (no conversion-pipe
+// instructions), degree-13 Taylor polynomial in Estrin form (dependency depth 5 instead
+// of 13), exponent patched in with integer arithmetic.  |x| is clamped to 700 (such
+// sigma are far outside any model).  Max relative error 4.4e-16; NaN propagates.
+__device__ __forceinline__ double fast_exp(double x) {
+  const double xc = fmin(fmax(x, -700.0), 700.0);
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52
+  const double tm = fma(xc, 1.4426950408889634074, magic);
+  const int k = __double2loint(tm);
+  const double t = tm - magic;
+  double r = fma(t, -6.93147180369123816490e-01, xc);
+  r = fma(t, -1.90821492927058770002e-10, r);
+  const double a0 = r + 1.0;
+  const double a1 = fma(r, 1.0 / 6.0, 0.5);
+  const double a2 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  const double a3 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+  const double a4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+  const double a5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+  const double a6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+  const double r2 = r * r;
+  const double b0 = fma(r2, a1, a0);
+  const double b1 = fma(r2, a3, a2);
+  const double b2 = fma(r2, a5, a4);
+  const double r4 = r2 * r2;
+  const double d0 = fma(r4, b1, b0);
+  const double d1 = fma(r4, a6, b2);
+  const double r8 = r4 * r4;
+  const double p = fma(r8, d1, d0);
+  const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  return x == x ? res : x;
+}
+__device__ __forceinline__ float fast_exp(float x) { return expf(x); }
+
+// 1/x for x >= tiny (normal, positive): hardware seed + two Newton steps (<= 1 ulp).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) { return 1.0f / x; }
 
 #define PTM_REP29(X)                                                              \
   X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) \
@@ -171,13 +216,14 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   int t_nb = 0, t_pred = 0;
   R t_invdk = R(0);
   const R* t_x = nullptr;
+  const int term = is_term ? a.order[warp] : 0;  // staging / hand-off are indexed by warp (= q)
   if (is_term) {
-    t_nb = a.nb[warp];
-    t_pred = a.pred[warp];
-    t_invdk = a.inv_dk[warp];
-    t_x = a.X + (long long)warp * a.n;
+    t_nb = a.nb[term];
+    t_pred = a.pred[term];
+    t_invdk = a.inv_dk[term];
+    t_x = a.X + (long long)term * a.n;
     R* kn = s_kn + warp * 4 * kKnotStride;
-    const R* gk = a.knots + warp * kKnotStride;
+    const R* gk = a.knots + term * kKnotStride;
     for (int i = lane; i < t_nb + 4; i += 32) {
       kn[i] = gk[i];
       kn[kKnotStride + i] = i + 1 < t_nb + 4 ? R(1) / (gk[i + 1] - gk[i]) : R(0);
@@ -202,7 +248,6 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
 
     if (is_term) {
       // =========================== term warp ========================================
-      const int term = warp;
       // this term's spline coefficients of the 32 chains -> shared [coef][lane]
       for (int j = 0; j < t_nb; ++j)
         s_gam[(a.goff[term] + j) * 32 + lane] = a.Gamma[((long long)term * kMaxNbases + j) * a.C + chain];
@@ -219,12 +264,13 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) dacc[j] = 0.0;
       }
-      const R* kn = s_kn + term * 4 * kKnotStride;
+      const R* kn = s_kn + warp * 4 * kKnotStride;
+      const int goff32 = a.goff[term] * 32;
       auto stage = [&](int tile) {
         const long long base = o_begin + (long long)tile * To;
         const int slot = tile % 3;
-        R* bst = s_b + ((term * 3 + slot) * To) * 4;
-        int* jst = s_j + (term * 3 + slot) * To;
+        R* bst = s_b + ((warp * 3 + slot) * To) * 4;
+        int* jst = s_j + (warp * 3 + slot) * To;
         for (int o = lane; o < To; o += 32) {
           const long long gi = base + o;
           if (gi < o_end) {
@@ -232,7 +278,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             const int jj = basis_window_fast(t_x[gi], kn, kn + kKnotStride, kn + 2 * kKnotStride,
                                              kn + 3 * kKnotStride, t_nb, t_invdk, bb);
             store4(bst + o * 4, bb);
-            jst[o] = jj;
+            jst[o] = goff32 + jj * 32;  // row offset into the shared gamma table
           }
         }
       };
@@ -246,15 +292,15 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             const int tile = s - 1;
             const long long base = o_begin + (long long)tile * To;
             const int slot = tile % 3;
-            const R* bp = s_b + ((term * 3 + slot) * To) * 4;
-            const int* jp = s_j + (term * 3 + slot) * To;
+            const R* bp = s_b + ((warp * 3 + slot) * To) * 4;
+            const int* jp = s_j + (warp * 3 + slot) * To;
             const R* hp = s_g + (((tile & 1) * To) * 2 + t_pred) * 32 + lane;
             const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
 #pragma unroll 2
             for (int o = 0; o < cnt; ++o, bp += 4, ++jp, hp += 64) {
               R b0, b1, b2, b3;
               load4(bp, b0, b1, b2, b3);
-              Dispatch<R, NB>::scatter(acc, *jp, b0, b1, b2, b3, *hp);
+              Dispatch<R, NB>::scatter(acc, (*jp - goff32) >> 5, b0, b1, b2, b3, *hp);
             }
           }
         }
@@ -310,31 +356,46 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
           for (int o = uw; o < cnt; o += NU) {
             const R yv = a.y[base + o];
             // ---- additive predictors: banded gather from the shared coefficient table
+            //      gamma[row + m][lane]; staging is indexed by the location-first order
             R em = beta0, es = gamma0;
-            for (int q = 0; q < T; ++q) {
-              const int t = a.order[q];
-              const int so = ((t * 3 + slot) * To + o);
-              R b0, b1, b2, b3;
-              load4(s_b + so * 4, b0, b1, b2, b3);
-              const R* gp = s_gam + (a.goff[t] + s_j[so]) * 32 + lane;
-              R f = b0 * gp[0];
-              f = fma(b1, gp[32], f);
-              f = fma(b2, gp[64], f);
-              f = fma(b3, gp[96], f);
-              if (q < a.T_loc) em += f; else es += f;
+            {
+              const R* bq = s_b + (slot * To + o) * 4;
+              const int* jq = s_j + slot * To + o;
+              const R* gl = s_gam + lane;
+              const int qstep = 3 * To;
+              int q = 0;
+#pragma unroll 2
+              for (; q < a.T_loc; ++q, bq += qstep * 4, jq += qstep) {
+                R b0, b1, b2, b3;
+                load4(bq, b0, b1, b2, b3);
+                const R* gp = gl + *jq;
+                R f = b0 * gp[0];
+                f = fma(b1, gp[32], f);
+                f = fma(b2, gp[64], f);
+                f = fma(b3, gp[96], f);
+                em += f;
+              }
+#pragma unroll 2
+              for (; q < T; ++q, bq += qstep * 4, jq += qstep) {
+                R b0, b1, b2, b3;
+                load4(bq, b0, b1, b2, b3);
+                const R* gp = gl + *jq;
+                R f = b0 * gp[0];
+                f = fma(b1, gp[32], f);
+                f = fma(b2, gp[64], f);
+                f = fma(b3, gp[96], f);
+                es += f;
+              }
             }
-            const R einv = exp(-es);
+            const R einv = fast_exp(-es);
             const R r = (yv - em) * einv;
             const int code = region_code(ts, r);
             const bool core = code == 2;
             // ---- core evaluation, unconditionally on the clamped argument (branch-free);
             //      the rare non-core lanes override the result below
             const R rc = r < ts.a ? ts.a : (r > ts.b ? ts.b : (r == r ? r : ts.a));
-            int m;
-            R frac;
-            grid_cell(ts, a.grid, rc, m, frac);
             CoreEval<R> ev;
-            core_locate(ts, m, frac, ev);
+            core_locate_fast(ts, a.grid, rc, ev);
             const R* cp = s_cc + (ev.kk * 5) * 32 + lane;
             core_eval(ts, cp[0], cp[32], cp[64], cp[96], cp[128], ev);
             R z = ev.z, d = ev.d, dzdr = ev.d, dddr = ev.d2;
@@ -372,7 +433,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             }
             if (GRAD) {
               const R lz = -z;
-              const R ld = above ? R(1) / dcl : R(0);
+              const R ld = above ? fast_rcp(dcl) : R(0);
               const R gr = fma(lz, dzdr, ld * dddr);
               const R gmu = -gr * einv;
               const R gls = fma(-gr, r, R(-1));

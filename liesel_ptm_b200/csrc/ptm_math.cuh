@@ -385,6 +385,14 @@ PTM_HD void grid_cell(const TrafoScal<R>& tc, const R* grid, R r, int& m, R& fra
 // grid spacing in knot units and jmp the jump of the cubic coefficient at the next
 // knot, the right sample is P(u+s) + jmp*max(u+s-1,0)^3 (C2 continuity), which is
 // expanded around u so that only one set of five coefficients is touched.
+// Branch-light variant for the fused sweep: the argument is already clamped to [a, b],
+// so floor(t) is in [0, 999] without clamping; everything stays in floating point
+// except the piece index.  The exact table is consulted only within frac_eps of a grid
+// point (a rare branch), which keeps the cell bit-exact with the reference.
+template <typename R> struct CoreEval;
+template <typename R>
+PTM_HD void core_locate_fast(const TrafoScal<R>& tc, const R* grid, R rc, CoreEval<R>& ev);
+
 template <typename R>
 struct CoreEval {
   R z, d, d2;        // lerped G theta, G' theta, G'' theta rows (approx.py:429-452)
@@ -395,6 +403,31 @@ struct CoreEval {
 template <typename R>
 PTM_HD void core_locate(const TrafoScal<R>& tc, int m, R frac, CoreEval<R>& ev) {
   const R p = R(m) * tc.ratio;
+  R fk = floor(p);
+  fk = fk > R(tc.KK - 1) ? R(tc.KK - 1) : fk;
+  ev.kk = (int)fk;
+  ev.u = p - fk;
+  ev.kappa = frac * tc.kap_scale;
+  const R over = ev.u + tc.ratio - R(1);
+  ev.mm = over > R(0) ? over : R(0);
+}
+
+template <typename R>
+PTM_HD void core_locate_fast(const TrafoScal<R>& tc, const R* grid, R rc, CoreEval<R>& ev) {
+  const R t = (rc - tc.a) * tc.inv_h;
+  R fm = floor(t);
+  R frac = t - fm;
+  if (frac < tc.frac_eps || frac > R(1) - tc.frac_eps) {
+    int m = (int)fm;
+    m = m < 0 ? 0 : (m > kGridN - 1 ? kGridN - 1 : m);
+    int i = m + 1;
+    if (rc < grid[i]) --i;
+    else if (i < kGridN && rc >= grid[i + 1]) ++i;
+    if (i < 1) i = 1;
+    fm = R(i - 1);
+    frac = (rc - grid[i]) * tc.inv_h;
+  }
+  const R p = fm * tc.ratio;
   R fk = floor(p);
   fk = fk > R(tc.KK - 1) ? R(tc.KK - 1) : fk;
   ev.kk = (int)fk;
