@@ -172,6 +172,20 @@ int ptm_quadform_f64(const PtmProblem* prob, const double* params, int64_t n_cha
 int ptm_quadform_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
                      float* quad, void* stream);
 
+/* Sufficient statistics of the intercept pseudo-Gibbs updates (predictor.py:80-100,
+ * 126-130, 133-175, 239-281), one fused sweep over the handle's observation range:
+ *   stats[c, 0] = sum_i exp(-eta_sigma_i)
+ *   stats[c, 1] = sum_i r_i            r_i = (y_i - eta_mu_i) exp(-eta_sigma_i)
+ *   stats[c, 2] = sum_i r_i^2
+ * with both intercepts at their current values.  Then, with n observations,
+ *   beta0_new  = beta0  + (stats1 / n) / (stats0 / n)        (LocationIntercept)
+ *   gamma0_new = gamma0 + log sqrt(stats2/n - (stats1/n)^2)  (LogScaleIntercept)
+ * The sums are additive over observation shards (all-reduce before the formulas). */
+int ptm_intercept_stats_f64(const PtmProblem* prob, const double* params, int64_t n_chains,
+                            double* stats, void* workspace, size_t workspace_bytes, void* stream);
+int ptm_intercept_stats_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
+                            float* stats, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernels the last logp / logp_grad call on this thread launched. */
 int ptm_last_launch_count(void);
 

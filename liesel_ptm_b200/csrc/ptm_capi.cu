@@ -42,7 +42,7 @@ struct Plan {
   int CG, M, n_items, grid, NSLOT, To, NU;
   long long chunk_len;
   size_t smem_main;
-  size_t off_gamma, off_cc, off_partial, off_xt, total;
+  size_t off_gamma, off_cc, off_partial, off_xt, off_scratch, total;
 };
 
 }  // namespace
@@ -299,6 +299,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   pl.off_cc = off;    off = align_up(off + (size_t)NCC * C * sizeof(R), 256);
   pl.off_partial = off; off = align_up(off + (size_t)pl.n_items * pl.NSLOT * 32 * sizeof(double), 256);
   pl.off_xt = off;    off = align_up(off + ptm::xtwx_workspace_bytes<R>(pr->max_nb, C), 256);
+  pl.off_scratch = off; off = align_up(off + (size_t)C * sizeof(R), 256);
   pl.total = off;
   return pl;
 }
@@ -326,7 +327,7 @@ int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t s
 
 template <typename R>
 int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* grad, void* ws,
-              size_t ws_bytes, void* stream) {
+              size_t ws_bytes, void* stream, R* stats = nullptr) {
   if (!pr || !params || !logp || !ws) return fail(PTM_ERR_NULL, "null argument");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
   if (C < 1) return fail(PTM_ERR_SHAPE, "n_chains must be >= 1");
@@ -368,7 +369,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   ma.n = pr->n; ma.obs_begin = pr->obs_begin; ma.obs_end = pr->obs_end;
   ma.chunk_len = pl.chunk_len;
   ma.C = (int)C; ma.CG = pl.CG; ma.M = pl.M; ma.n_items = pl.n_items;
-  ma.NSLOT = want_grad ? pl.NSLOT : 3;
+  ma.NSLOT = want_grad ? pl.NSLOT : ptm::kLogpSlots;
   ma.KK = pr->KK;
   ma.T = pr->T; ma.T_loc = pr->T_loc; ma.T_scale = pr->T_scale;
   ma.To = pl.To; ma.NU = pl.NU; ma.sum_nb = pr->sum_nb;
@@ -397,7 +398,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
 
   ptm::PostArgs<R> po;
   memset(&po, 0, sizeof po);
-  po.params = params; po.partial = partial; po.logp = logp; po.grad = grad;
+  po.params = params; po.partial = partial; po.logp = logp; po.grad = grad; po.stats = stats;
   po.Zall = reinterpret_cast<const R*>(pr->d_Zall);
   po.Kall = reinterpret_cast<const R*>(pr->d_Kall);
   po.Zd = reinterpret_cast<const R*>(pr->d_Zd);
@@ -640,6 +641,25 @@ int ptm_loc_precision_f32(const PtmProblem* p, int32_t term, const float* params
                           float* chol, void* ws, size_t wsb, void* st) {
   if (!precision) return fail(PTM_ERR_NULL, "precision is null");
   return xtwx_impl<float>(p, term, params, C, nullptr, precision, chol, ws, wsb, st);
+}
+
+int ptm_intercept_stats_f64(const PtmProblem* p, const double* params, int64_t C, double* stats, void* ws,
+                            size_t wsb, void* st) {
+  if (!p || !stats || !ws || C < 1) return fail(PTM_ERR_NULL, "null argument");
+  if (p->dtype != PTM_F64) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  const Plan pl = make_plan<double>(p, C);
+  if (wsb < pl.total) return fail(PTM_ERR_WORKSPACE, "workspace too small");
+  double* scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + pl.off_scratch);
+  return eval_impl<double>(p, params, C, scratch, nullptr, ws, wsb, st, stats);
+}
+int ptm_intercept_stats_f32(const PtmProblem* p, const float* params, int64_t C, float* stats, void* ws,
+                            size_t wsb, void* st) {
+  if (!p || !stats || !ws || C < 1) return fail(PTM_ERR_NULL, "null argument");
+  if (p->dtype != PTM_F32) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  const Plan pl = make_plan<float>(p, C);
+  if (wsb < pl.total) return fail(PTM_ERR_WORKSPACE, "workspace too small");
+  float* scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.off_scratch);
+  return eval_impl<float>(p, params, C, scratch, nullptr, ws, wsb, st, stats);
 }
 
 int ptm_quadform_f64(const PtmProblem* p, const double* params, int64_t C, double* quad, void* st) {

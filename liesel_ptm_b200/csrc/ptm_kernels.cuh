@@ -32,6 +32,11 @@ constexpr int kMaxTerms = 24;
 constexpr int kKnotStride = kMaxNbases + 4;  // knots per term in the packed table
 constexpr int kRegSlots = 9;                 // per-lane scalar accumulators
 enum Slot { SL_Z2 = 0, SL_LS, SL_LOGD, SL_GB0, SL_GG0, SL_GVL, SL_GDL, SL_GVR, SL_GDR };
+// The logp-only sweep has no gradient slots; it reuses three of them for the sums the
+// intercept pseudo-Gibbs updates need (predictor.py:80-100,126-130):
+//   sum_i exp(-eta_sigma_i),  sum_i r_i,  sum_i r_i^2   with r = (y - eta_mu) exp(-eta_sigma)
+enum StatSlot { SL_SEINV = 3, SL_SR = 4, SL_SR2 = 5 };
+constexpr int kLogpSlots = 6;
 
 template <typename R>
 struct MainArgs {
@@ -425,6 +430,11 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             const R dcl = above ? d : tiny;
             a_z2 += (double)(z * z);
             a_ls += (double)es;
+            if (!GRAD) {  // intercept statistics ride along with the logp-only sweep
+              a_gb0 += (double)einv;
+              a_gg0 += (double)r;
+              a_gvl += (double)(r * r);
+            }
             {
               R mant; int ex;
               split_mant(dcl, mant, ex);
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
     // ---- item epilogue: cross-warp sums of the eval-warp partials to HBM ------------
     __syncthreads();
     {
-      const int nreg = GRAD ? kRegSlots : 3;
+      const int nreg = GRAD ? kRegSlots : kLogpSlots;
       for (int idx = tid; idx < nreg * 32; idx += blockDim.x) {
         double v = 0.0;
         for (int w = 0; w < NU; ++w) v += s_red[w * kRegSlots * 32 + idx];
@@ -594,6 +604,7 @@ struct PostArgs {
   const double* partial;  // [CG*M][NSLOT][32]
   R* logp;           // [C]
   R* grad;           // [C][P] or null
+  R* stats;          // [C][3] or null (logp-only sweep): sum exp(-eta_sigma), sum r, sum r^2
   const R* Zall;
   const R* Kall;     // packed K_t [p_t][p_t]
   const R* Zd;
@@ -697,6 +708,11 @@ __global__ void k_post(const PostArgs<R> a) {
         lp += -0.5 * ss / (taud * taud) - (D)(np_ - 1) * (log(taud) + half_log_2pi);
       }
       a.logp[c] = (R)lp;
+      if (!GRAD && a.stats != nullptr) {
+        a.stats[c * 3 + 0] = (R)red[SL_SEINV * 32 + lane];
+        a.stats[c * 3 + 1] = (R)red[SL_SR * 32 + lane];
+        a.stats[c * 3 + 2] = (R)red[SL_SR2 * 32 + lane];
+      }
       if (GRAD) {
         R* go = a.grad + (long long)c * a.P;
         go[0] = (R)red[SL_GB0 * 32 + lane];

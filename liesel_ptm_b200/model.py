@@ -332,6 +332,31 @@ class LocScalePTM:
             z, dz = z[..., 0], dz[..., 0]
         return z, dz
 
+    def intercept_stats(self, params: torch.Tensor) -> torch.Tensor:
+        """[C, 3] sufficient statistics of the intercept pseudo-Gibbs updates: sum exp(-eta_sigma),
+        sum r, sum r^2 over this handle's observation range (additive over shards)."""
+        params = self._check_params(params)
+        Cn = params.shape[0]
+        ws = self._workspace(Cn)
+        out = torch.empty((Cn, 3), dtype=self.dtype, device=self.device)
+        f = getattr(self._lib, f"ptm_intercept_stats_{self._sfx}")
+        _lib.check(f(self._handle, params.data_ptr(), Cn, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                     self._stream()))
+        return out
+
+    def compute_intercepts(self, params: torch.Tensor, n_obs: int | None = None):
+        """LocationIntercept.compute_intercept / LogScaleIntercept.compute_intercept
+        (predictor.py:80-100, 126-130) for every chain, from one fused sweep: returns
+        (beta0_new, gamma0_new) where gamma0_new is evaluated at the CURRENT beta0, as the
+        reference's two kernels each see the current state."""
+        st = self.intercept_stats(params)
+        n = float(self.n if n_obs is None else n_obs)
+        L = self.layout
+        m_e, m_r, m_r2 = st[:, 0] / n, st[:, 1] / n, st[:, 2] / n
+        beta0 = params[:, L["beta0"]] + m_r / m_e
+        gamma0 = params[:, L["gamma0"]] + 0.5 * torch.log(m_r2 - m_r * m_r)
+        return beta0, gamma0
+
     def quadform(self, params: torch.Tensor) -> torch.Tensor:
         """beta_t' K_t beta_t for every chain and term, [C, T]: the quadratic form of the
         Gibbs updates of the smoothing variances (gam/kernel.py:29-39, kernel.py:99-111)."""

@@ -757,6 +757,22 @@ class PTMModel:
         out += (np.sum(st.delta_z[c] ** 2) / td**3 - (self.nparam - 1) / td) * dst.tau_delta[c]
         return out
 
+    # --- intercept pseudo-Gibbs values (predictor.py:80-100, 126-130) ------
+    def compute_intercepts(self, st: ChainState, c: int):
+        """LocationIntercept.compute_intercept and LogScaleIntercept.compute_intercept for
+        chain c, literally: loc_model / log_scale_model are the predictors WITHOUT their
+        intercepts; the scale intercept sees loc = beta0 + loc_model at the current beta0."""
+        mu, ls = self.predictors(st, c)
+        loc_model = mu - st.beta0[c]
+        log_scale_model = ls - st.gamma0[c]
+        nobs = self.n
+        log_mean_exp = logsumexp(-log_scale_model) - np.log(nobs)
+        inv_scale_model_mean = np.exp(-log_mean_exp)
+        residual_model_mean = np.mean((self.y - loc_model) * np.exp(-log_scale_model))
+        beta0 = inv_scale_model_mean * residual_model_mean
+        gamma0 = np.log(np.std((self.y - mu) / np.exp(log_scale_model)))
+        return beta0, gamma0
+
     # --- IWLS information (iwls_proposals.py:55-89, 118-144) --------------
     def loc_precision(self, st: ChainState, t: int):
         """GaussianLocCholInfo.precision for term t over all chains -> (C,p,p), plus

@@ -65,6 +65,23 @@ def test_transform_matches_oracle():
     assert np.all(cell[~core] == -1)
 
 
+def test_intercept_pseudo_gibbs_values():
+    """predictor.py:80-100,126-130: the fused sufficient statistics reproduce the reference's
+    compute_intercept formulas (restated literally in the oracle)."""
+    case = build_case(n=3000, n_loc=2, n_scale=1, nbases=12, C=5, beta0=0.3, gamma0=-0.2)
+    params = torch.from_numpy(case.params).cuda()
+    b0, g0 = case.model.compute_intercepts(params)
+    st = case.model.intercept_stats(params).cpu().numpy()
+    assert st.shape == (5, 3) and np.isfinite(st).all()
+    for c in range(5):
+        rb, rg = case.omodel.compute_intercepts(case.state, c)
+        assert abs(b0[c].item() - rb) < 1e-11 * max(1.0, abs(rb))
+        assert abs(g0[c].item() - rg) < 1e-11 * max(1.0, abs(rg))
+    # the logp output of the same sweep is untouched
+    lp_ref, _ = oracle_eval(case)
+    assert rel_err(case.model.log_prob(params).cpu().numpy(), lp_ref) < TOL64
+
+
 def test_quadform():
     """beta' K beta of the Gibbs scale updates (gam/kernel.py:29-39)."""
     case = build_case(n=50, n_loc=2, n_scale=1, nbases=12, C=5)
