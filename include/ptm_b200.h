@@ -164,6 +164,17 @@ int ptm_loc_precision_f32(const PtmProblem* prob, int32_t term, const float* par
                           int64_t n_chains, float* precision, float* chol,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Precision and Cholesky factor of ALL location terms from ONE sweep over the
+ * observations (the working weights depend only on the scale predictor, so the loc
+ * terms share them).  Term blocks follow each other in model order: block t is
+ * [C, p_t, p_t] row-major.  chol may be NULL. */
+int ptm_loc_precision_all_f64(const PtmProblem* prob, const double* params, int64_t n_chains,
+                              double* precision, double* chol, void* workspace,
+                              size_t workspace_bytes, void* stream);
+int ptm_loc_precision_all_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
+                              float* precision, float* chol, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* quad[c, t] = beta_t' K_t beta_t for every chain and smooth term: the quadratic form of
  * the Gibbs updates of the smoothing variances (gam/kernel.py:29-39, kernel.py:99-111:
  * b + 0.5 * beta' K beta) and of the prior (gam/dist.py:64-70).  quad is [C, T]. */

@@ -30,6 +30,7 @@ SYMBOLS = [
     "ptm_basis_f64", "ptm_basis_f32", "ptm_transform_f64", "ptm_transform_f32",
     "ptm_xtwx_f64", "ptm_xtwx_f32", "ptm_loc_precision_f64", "ptm_loc_precision_f32",
     "ptm_quadform_f64", "ptm_quadform_f32", "ptm_intercept_stats_f64", "ptm_intercept_stats_f32",
+    "ptm_loc_precision_all_f64", "ptm_loc_precision_all_f32",
     "ptm_last_launch_count", "ptm_profile_enable", "ptm_last_kernel_ms", "ptm_last_error",
     "ptm_version",
 ]
@@ -105,6 +106,9 @@ def load() -> C.CDLL:
         f.restype = C.c_int
         f = getattr(lib, f"ptm_xtwx_{sfx}")
         f.argtypes = [vp, i32, vp, i64, vp, vp, sz, vp]
+        f.restype = C.c_int
+        f = getattr(lib, f"ptm_loc_precision_all_{sfx}")
+        f.argtypes = [vp, vp, i64, vp, vp, vp, sz, vp]
         f.restype = C.c_int
         f = getattr(lib, f"ptm_intercept_stats_{sfx}")
         f.argtypes = [vp, vp, i64, vp, vp, sz, vp]

@@ -298,7 +298,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   pl.off_gamma = off; off = align_up(off + (size_t)std::max(T, 1) * ptm::kMaxNbases * C * sizeof(R), 256);
   pl.off_cc = off;    off = align_up(off + (size_t)NCC * C * sizeof(R), 256);
   pl.off_partial = off; off = align_up(off + (size_t)pl.n_items * pl.NSLOT * 32 * sizeof(double), 256);
-  pl.off_xt = off;    off = align_up(off + ptm::xtwx_workspace_bytes<R>(pr->max_nb, C), 256);
+  pl.off_xt = off;    off = align_up(off + ptm::xtwx_workspace_bytes<R>(std::max(pr->sum_nb, 1), C), 256);
   pl.off_scratch = off; off = align_up(off + (size_t)C * sizeof(R), 256);
   pl.total = off;
   return pl;
@@ -457,21 +457,29 @@ int transform_impl(const PtmProblem* pr, const R* delta, long long C, const R* r
   return PTM_OK;
 }
 
+// Information sweep for the terms in `terms` (all LOC, or one SCALE term): shared
+// prologue (gamma of the scale terms), one banded sweep, one epilogue per term.
+// Outputs are per term: out_x / out_p / out_l[i] may be null.
 template <typename R>
-int xtwx_impl(const PtmProblem* pr, int term, const R* params, long long C, R* xtwx, R* precision,
-              R* chol, void* ws, size_t ws_bytes, void* stream) {
+int xtwx_terms(const PtmProblem* pr, const int* terms, int nterms, const R* params, long long C,
+               R* const* out_x, R* const* out_p, R* const* out_l, void* ws, size_t ws_bytes, void* stream) {
   if (!pr || !params || !ws) return fail(PTM_ERR_NULL, "null argument");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
-  if (term < 0 || term >= pr->T) return fail(PTM_ERR_SHAPE, "term index out of range");
   if (C < 1) return fail(PTM_ERR_SHAPE, "n_chains must be >= 1");
+  if (nterms < 1) return PTM_OK;
+  for (int i = 0; i < nterms; ++i)
+    if (terms[i] < 0 || terms[i] >= pr->T) return fail(PTM_ERR_SHAPE, "term index out of range");
+  const bool loc = pr->pred[terms[0]] == PTM_LOC;
+  for (int i = 1; i < nterms; ++i)
+    if ((pr->pred[terms[i]] == PTM_LOC) != loc) return fail(PTM_ERR_SHAPE, "terms must share a predictor");
+  if (!loc && nterms != 1) return fail(PTM_ERR_SHAPE, "one scale term per call");
   const Plan pl = make_plan<R>(pr, C);
   if (ws_bytes < pl.total) return fail(PTM_ERR_WORKSPACE, "workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   char* wsb = reinterpret_cast<char*>(ws);
   R* Gamma = reinterpret_cast<R*>(wsb + pl.off_gamma);
   R* cc = reinterpret_cast<R*>(wsb + pl.off_cc);
-  R* xt = reinterpret_cast<R*>(wsb + pl.off_xt);
-  // gamma of the SCALE terms (sigma depends on them) via the shared prologue
+  double* xt = reinterpret_cast<double*>(wsb + pl.off_xt);
   ptm::PreArgs<R> pa;
   memset(&pa, 0, sizeof pa);
   pa.params = params; pa.Gamma = Gamma; pa.cc = cc;
@@ -494,16 +502,66 @@ int xtwx_impl(const PtmProblem* pr, int term, const R* params, long long C, R* x
   xa.Zall = reinterpret_cast<const R*>(pr->d_Zall);
   xa.Kall = reinterpret_cast<const R*>(pr->d_Kall);
   xa.n = pr->n; xa.obs_begin = pr->obs_begin; xa.obs_end = pr->obs_end;
-  xa.C = (int)C; xa.P = pr->P; xa.T = pr->T; xa.term = term; xa.KK = pr->KK;
+  xa.C = (int)C; xa.P = pr->P; xa.T = pr->T; xa.KK = pr->KK;
   xa.tau_off = pr->tau_off;
+  xa.add_penalty = pr->add_priors;
   for (int t = 0; t < pr->T; ++t) {
-    xa.nb[t] = pr->nb[t]; xa.p[t] = pr->p[t]; xa.pred[t] = pr->pred[t];
+    xa.nb[t] = pr->nb[t]; xa.p[t] = pr->p[t];
     xa.zoff[t] = pr->zoff[t]; xa.koff[t] = pr->koff[t]; xa.inv_dk[t] = (R)pr->inv_dk[t];
   }
-  xa.add_penalty = pr->add_priors;
-  const int rc = ptm::xtwx_launch<R>(xa, xt, xtwx, precision, chol, pr->num_sms, st, &g_launches);
-  if (rc != 0) return fail(PTM_ERR_CUDA, std::string("xtwx launch: ") + cudaGetErrorString((cudaError_t)rc));
+  xa.const_w = loc ? 0 : 1;  // scale terms: W == 2 (iwls_proposals.py:118-119)
+  if (loc)
+    for (int t = 0; t < pr->T; ++t)
+      if (pr->pred[t] == PTM_SCALE) {
+        xa.sc_term[xa.nsc] = t; xa.sc_goff[xa.nsc] = xa.sum_sc_nb; xa.sum_sc_nb += pr->nb[t]; ++xa.nsc;
+      }
+  // as many requested terms per sweep as the 20-warp / shared-memory budget allows
+  int done = 0;
+  while (done < nterms) {
+    int take = std::min(nterms - done, std::max(1, 16 - xa.nsc));
+    int rc = -1;
+    while (take >= 1) {
+      xa.nbt = take; xa.band_slots = 0;
+      for (int i = 0; i < take; ++i) {
+        xa.bt_term[i] = terms[done + i]; xa.bt_boff[i] = xa.band_slots; xa.band_slots += pr->nb[terms[done + i]] * 4;
+      }
+      rc = ptm::xtwx_sweep<R>(xa, xt, pr->num_sms, st, &g_launches);
+      if (rc != -1) break;
+      --take;
+    }
+    if (rc == -1) return fail(PTM_ERR_SHAPE, "information sweep does not fit in shared memory");
+    if (rc != 0) return fail(PTM_ERR_CUDA, std::string("xtwx sweep: ") + cudaGetErrorString((cudaError_t)rc));
+    for (int i = 0; i < take; ++i) {
+      const int k = done + i;
+      rc = ptm::xtwx_post<R>(xa, terms[k], xa.bt_boff[i], out_x ? out_x[k] : nullptr, out_p ? out_p[k] : nullptr,
+                             out_l ? out_l[k] : nullptr, st, &g_launches);
+      if (rc != 0) return fail(PTM_ERR_CUDA, std::string("xtwx post: ") + cudaGetErrorString((cudaError_t)rc));
+    }
+    done += take;
+  }
   return PTM_OK;
+}
+
+template <typename R>
+int xtwx_impl(const PtmProblem* pr, int term, const R* params, long long C, R* xtwx, R* precision,
+              R* chol, void* ws, size_t ws_bytes, void* stream) {
+  R* ox[1] = {xtwx}; R* op[1] = {precision}; R* ol[1] = {chol};
+  return xtwx_terms<R>(pr, &term, 1, params, C, ox, op, ol, ws, ws_bytes, stream);
+}
+
+// Precision + Cholesky of ALL location terms from one sweep (they share the weights).
+template <typename R>
+int precision_all_impl(const PtmProblem* pr, const R* params, long long C, R* precision, R* chol, void* ws,
+                       size_t ws_bytes, void* stream) {
+  if (!pr || !precision) return fail(PTM_ERR_NULL, "null argument");
+  int terms[PTM_MAX_TERMS]; R* op[PTM_MAX_TERMS]; R* ol[PTM_MAX_TERMS];
+  int nt = 0; size_t off = 0;
+  for (int t = 0; t < pr->T; ++t)
+    if (pr->pred[t] == PTM_LOC) {
+      terms[nt] = t; op[nt] = precision + off; ol[nt] = chol ? chol + off : nullptr;
+      off += (size_t)C * pr->p[t] * pr->p[t]; ++nt;
+    }
+  return xtwx_terms<R>(pr, terms, nt, params, C, nullptr, op, ol, ws, ws_bytes, stream);
 }
 
 template <typename R>
@@ -667,6 +725,15 @@ int ptm_quadform_f64(const PtmProblem* p, const double* params, int64_t C, doubl
 }
 int ptm_quadform_f32(const PtmProblem* p, const float* params, int64_t C, float* quad, void* st) {
   return quadform_impl<float>(p, params, C, quad, st);
+}
+
+int ptm_loc_precision_all_f64(const PtmProblem* p, const double* params, int64_t C, double* precision,
+                              double* chol, void* ws, size_t wsb, void* st) {
+  return precision_all_impl<double>(p, params, C, precision, chol, ws, wsb, st);
+}
+int ptm_loc_precision_all_f32(const PtmProblem* p, const float* params, int64_t C, float* precision,
+                              float* chol, void* ws, size_t wsb, void* st) {
+  return precision_all_impl<float>(p, params, C, precision, chol, ws, wsb, st);
 }
 
 int ptm_last_launch_count(void) { return g_launches; }

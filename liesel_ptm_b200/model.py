@@ -391,6 +391,31 @@ class LocScalePTM:
         return P, L
 
 
+def _precision_all(self, params: torch.Tensor, with_chol: bool = True):
+    """Precision (and Cholesky factor) of every LOCATION term from one sweep: lists of
+    [C, p_t, p_t] tensors in model order."""
+    params = self._check_params(params)
+    Cn = params.shape[0]
+    ps_ = [t.basis.ncoef for t, k in self.terms if k == _lib.PTM_LOC]
+    total = sum(Cn * p * p for p in ps_)
+    ws = self._workspace(Cn)
+    P = torch.empty(max(total, 1), dtype=self.dtype, device=self.device)
+    L = torch.empty_like(P) if with_chol else None
+    f = getattr(self._lib, f"ptm_loc_precision_all_{self._sfx}")
+    _lib.check(f(self._handle, params.data_ptr(), Cn, P.data_ptr(), L.data_ptr() if with_chol else None,
+                 ws.data_ptr(), ws.numel(), self._stream()))
+    outP, outL, off = [], [], 0
+    for p in ps_:
+        outP.append(P[off: off + Cn * p * p].view(Cn, p, p))
+        if with_chol:
+            outL.append(L[off: off + Cn * p * p].view(Cn, p, p))
+        off += Cn * p * p
+    return outP, outL
+
+
+LocScalePTM.precision_all = _precision_all
+
+
 class FlatLogProb:
     """``FlatLogProb`` of the reference (logprob.py:72-140) over the fused operator:
     ``log_prob(flat_position)``, ``grad(flat_position)`` with flat positions [C, P]."""

@@ -105,6 +105,13 @@ def test_xtwx_and_precision():
         P, _ = case.model.precision(t, params)
         _, ref_P = case.omodel.scale_precision(case.state, t)
         assert rel_err(P.cpu().numpy(), ref_P) < 1e-11
+    # all location terms from one sweep
+    Ps, Ls = case.model.precision_all(params)
+    assert len(Ps) == 2
+    for t in range(2):
+        _, ref_P, ref_L = case.omodel.loc_precision(case.state, t)
+        assert rel_err(Ps[t].cpu().numpy(), ref_P) < 1e-11
+        assert rel_err(Ls[t].cpu().numpy(), ref_L) < 1e-9
 
 
 # ---------------------------------------------------------------------------------------

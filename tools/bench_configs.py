@@ -31,7 +31,9 @@ for name in ["c1_readme_n100", "c2_n100k_3loc_1scale_64chains", "c3_n1M_5loc_5sc
         ms_x = timeit(lambda: m.xtwx(0, p))
         ms_p = timeit(lambda: m.precision(0, p))
         pdim = wl.model.all_terms()[0][0].basis.ncoef
-        rec.update({"xtwx_term_ms": ms_x, "precision_chol_term_ms": ms_p,
+        ms_all = timeit(lambda: m.precision_all(p))
+        rec.update({"xtwx_term_ms": ms_x, "precision_chol_term_ms": ms_p, "precision_chol_all_loc_terms_ms": ms_all,
+                    "n_loc_terms": wl.n_loc,
                     "xtwx_dense_equiv_tflops": 2.0 * wl.n * pdim * pdim * C / ms_x * 1e3 / 1e12,
                     "xtwx_banded_gflops": 2.0 * wl.n * 10 * C / ms_x * 1e3 / 1e9})
     out[name] = rec
