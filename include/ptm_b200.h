@@ -200,6 +200,12 @@ int ptm_intercept_stats_f32(const PtmProblem* prob, const float* params, int64_t
 /* Number of kernels the last logp / logp_grad call on this thread launched. */
 int ptm_last_launch_count(void);
 
+/* Route the last information sweep (ptm_xtwx / ptm_loc_precision / ptm_loc_precision_all)
+ * on this thread took: 0 = banded CUDA-core sweep, 1 = tcgen05 tensor-core sweep (float
+ * problems, location terms, when the terms fit TMEM / shared memory).  Setting the
+ * environment variable PTM_XTWX_TC=0 forces route 0. */
+int ptm_last_xtwx_route(void);
+
 /* Measurement hook (bench.py): when enabled, logp / logp_grad calls on this thread
  * record CUDA events around the prologue, the fused sweep and the epilogue on the
  * caller's stream.  ptm_last_kernel_ms() synchronises on the last event and returns

@@ -31,7 +31,7 @@ SYMBOLS = [
     "ptm_xtwx_f64", "ptm_xtwx_f32", "ptm_loc_precision_f64", "ptm_loc_precision_f32",
     "ptm_quadform_f64", "ptm_quadform_f32", "ptm_intercept_stats_f64", "ptm_intercept_stats_f32",
     "ptm_loc_precision_all_f64", "ptm_loc_precision_all_f32",
-    "ptm_last_launch_count", "ptm_profile_enable", "ptm_last_kernel_ms", "ptm_last_error",
+    "ptm_last_launch_count", "ptm_last_xtwx_route", "ptm_profile_enable", "ptm_last_kernel_ms", "ptm_last_error",
     "ptm_version",
 ]
 
@@ -120,6 +120,7 @@ def load() -> C.CDLL:
         f.argtypes = [vp, i32, vp, i64, vp, vp, vp, sz, vp]
         f.restype = C.c_int
     lib.ptm_last_launch_count.restype = C.c_int
+    lib.ptm_last_xtwx_route.restype = C.c_int
     lib.ptm_profile_enable.argtypes = [C.c_int]
     lib.ptm_profile_enable.restype = C.c_int
     lib.ptm_last_kernel_ms.argtypes = [C.POINTER(C.c_float)] * 3

@@ -16,6 +16,7 @@
 #include "../../include/ptm_b200.h"
 #include "ptm_kernels.cuh"
 #include "ptm_xtwx.cuh"
+#include "ptm_xtwx_tc.cuh"
 
 namespace {
 
@@ -457,6 +458,16 @@ int transform_impl(const PtmProblem* pr, const R* delta, long long C, const R* r
   return PTM_OK;
 }
 
+static thread_local int g_last_xtwx_route = 0;  // 0 = banded CUDA-core sweep, 1 = tcgen05 sweep
+static bool tc_route_enabled() {
+  const char* e = getenv("PTM_XTWX_TC");
+  return !(e && e[0] == '0');
+}
+static int tc_flush_tiles() {
+  const char* e = getenv("PTM_TC_FLUSH");
+  return e ? atoi(e) : 0;
+}
+
 // Information sweep for the terms in `terms` (all LOC, or one SCALE term): shared
 // prologue (gamma of the scale terms), one banded sweep, one epilogue per term.
 // Outputs are per term: out_x / out_p / out_l[i] may be null.
@@ -525,7 +536,18 @@ int xtwx_terms(const PtmProblem* pr, const int* terms, int nterms, const R* para
       for (int i = 0; i < take; ++i) {
         xa.bt_term[i] = terms[done + i]; xa.bt_boff[i] = xa.band_slots; xa.band_slots += pr->nb[terms[done + i]] * 4;
       }
-      rc = ptm::xtwx_sweep<R>(xa, xt, pr->num_sms, st, &g_launches);
+      rc = -1;
+      if constexpr (sizeof(R) == 4) {
+        // float problems, location terms: tensor-core route (ptm_xtwx_tc.cuh) when it fits
+        if (loc && tc_route_enabled()) {
+          rc = ptm::xtwx_tc_sweep(xa, xt, pr->num_sms, tc_flush_tiles(), st, &g_launches);
+          g_last_xtwx_route = rc == 0 ? 1 : 0;
+        }
+      }
+      if (rc == -1) {
+        rc = ptm::xtwx_sweep<R>(xa, xt, pr->num_sms, st, &g_launches);
+        if (rc == 0) g_last_xtwx_route = 0;
+      }
       if (rc != -1) break;
       --take;
     }
@@ -737,6 +759,7 @@ int ptm_loc_precision_all_f32(const PtmProblem* p, const float* params, int64_t 
 }
 
 int ptm_last_launch_count(void) { return g_launches; }
+int ptm_last_xtwx_route(void) { return g_last_xtwx_route; }
 
 int ptm_profile_enable(int on) {
   if (on && !g_ev[0])

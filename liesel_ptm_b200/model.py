@@ -294,6 +294,10 @@ class LocScalePTM:
         """Measurement hook: record CUDA events around the three kernels of each call."""
         _lib.check(self._lib.ptm_profile_enable(int(on)))
 
+    def last_xtwx_route(self) -> str:
+        """Route of the last information sweep: "banded" (CUDA cores) or "tcgen05"."""
+        return "tcgen05" if self._lib.ptm_last_xtwx_route() == 1 else "banded"
+
     def last_kernel_ms(self) -> tuple[float, float, float]:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         _lib.check(self._lib.ptm_last_kernel_ms(C.byref(a), C.byref(b), C.byref(c)))

@@ -278,6 +278,52 @@ def test_logp_grad_f32(n, C):
         assert rel_err(g[c], g_ref[c]) < 1e-5
 
 
+def _f64_oracle_of(case, nparam=20):
+    """The f64 oracle on the f32-rounded numbers of a float32 case."""
+    om32 = case.omodel
+    terms = [o.term_from_reparam(t.x.astype(np.float64), t.knots.astype(np.float64), t.Z.astype(np.float64),
+                                 t.K.astype(np.float64), t.rank, t.predictor) for t in om32.terms]
+    om = o.PTMModel(om32.y.astype(np.float64), terms, nparam=nparam)
+    om.spline = o.PTMSpline(om32.knots.knots.astype(np.float64))
+    om.Zd = om32.Zd.astype(np.float64)
+    st = golden_io.state_from_params(om, case.params.astype(np.float64), case.layout)
+    return om, st
+
+
+@pytest.mark.parametrize("n,C", [(37, 3), (5000, 130), (20011, 257)])
+def test_xtwx_f32_tensor_core_and_banded_routes(n, C, monkeypatch):
+    """float32 information of the location terms: the tcgen05 route (3xTF32, f32 TMEM
+    accumulators promoted to double) and the banded CUDA-core route against the f64 oracle
+    on the f32-rounded inputs, rel 2e-5 (north star: 1e-5 f32; the weights 1/sigma^2 carry
+    the f32 rounding of eta_sigma, |eta| * 6e-8 * 2)."""
+    case = build_case(n=n, n_loc=2, n_scale=2, nbases=12, nparam=20, C=C, dtype=np.float32)
+    om, st = _f64_oracle_of(case)
+    params = torch.from_numpy(case.params).cuda()
+    refs = [om.loc_precision(st, t) for t in range(2)]
+    for flush in ("3", None):  # promote every 3 tiles / default cadence
+        if flush:
+            monkeypatch.setenv("PTM_TC_FLUSH", flush)
+        else:
+            monkeypatch.delenv("PTM_TC_FLUSH", raising=False)
+        Ps, Ls = case.model.precision_all(params)
+        assert case.model.last_xtwx_route() == "tcgen05"
+        for t in range(2):
+            assert rel_err(Ps[t].cpu().numpy(), refs[t][1]) < 2e-5
+            assert rel_err(Ls[t].cpu().numpy(), refs[t][2]) < 2e-4
+    x_tc = case.model.xtwx(0, params).cpu().numpy()
+    assert case.model.last_xtwx_route() == "tcgen05"
+    assert rel_err(x_tc, refs[0][0]) < 2e-5
+    monkeypatch.setenv("PTM_XTWX_TC", "0")
+    x_b = case.model.xtwx(0, params).cpu().numpy()
+    assert case.model.last_xtwx_route() == "banded"
+    assert rel_err(x_b, refs[0][0]) < 2e-5
+    # scale terms (W == 2) always take the banded route
+    monkeypatch.delenv("PTM_XTWX_TC")
+    P, _ = case.model.precision(2, params)
+    assert case.model.last_xtwx_route() == "banded"
+    assert rel_err(P.cpu().numpy(), om.scale_precision(st, 2)[1]) < 2e-5
+
+
 # ---------------------------------------------------------------------------------------
 # BASELINE.json's full size (c3: n = 1M, 5+5 terms) through size-independent properties
 # ---------------------------------------------------------------------------------------
