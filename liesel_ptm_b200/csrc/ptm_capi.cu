@@ -529,28 +529,29 @@ int xtwx_terms(const PtmProblem* pr, const int* terms, int nterms, const R* para
   // as many requested terms per sweep as the 20-warp / shared-memory budget allows
   int done = 0;
   while (done < nterms) {
-    int take = std::min(nterms - done, std::max(1, 16 - xa.nsc));
-    int rc = -1;
-    while (take >= 1) {
-      xa.nbt = take; xa.band_slots = 0;
-      for (int i = 0; i < take; ++i) {
+    int rc = -1, take = 0;
+    auto select = [&](int cnt) {
+      xa.nbt = cnt; xa.band_slots = 0;
+      for (int i = 0; i < cnt; ++i) {
         xa.bt_term[i] = terms[done + i]; xa.bt_boff[i] = xa.band_slots; xa.band_slots += pr->nb[terms[done + i]] * 4;
       }
-      rc = -1;
-      if constexpr (sizeof(R) == 4) {
-        // float problems, location terms: tensor-core route (ptm_xtwx_tc.cuh) when it fits
-        if (loc && tc_route_enabled()) {
+    };
+    if constexpr (sizeof(R) == 4) {
+      // float problems, location terms: tensor-core route (ptm_xtwx_tc.cuh) with as many
+      // terms per sweep as TMEM / shared memory take
+      if (loc && tc_route_enabled())
+        for (take = std::min(nterms - done, 8); take >= 1 && rc == -1; --take) {
+          select(take);
           rc = ptm::xtwx_tc_sweep(xa, xt, pr->num_sms, tc_flush_tiles(), st, &g_launches);
-          g_last_xtwx_route = rc == 0 ? 1 : 0;
+          if (rc != -1) { g_last_xtwx_route = 1; break; }
         }
-      }
-      if (rc == -1) {
-        rc = ptm::xtwx_sweep<R>(xa, xt, pr->num_sms, st, &g_launches);
-        if (rc == 0) g_last_xtwx_route = 0;
-      }
-      if (rc != -1) break;
-      --take;
     }
+    if (rc == -1)
+      for (take = std::min(nterms - done, std::max(1, 16 - xa.nsc)); take >= 1; --take) {
+        select(take);
+        rc = ptm::xtwx_sweep<R>(xa, xt, pr->num_sms, st, &g_launches);
+        if (rc != -1) { g_last_xtwx_route = 0; break; }
+      }
     if (rc == -1) return fail(PTM_ERR_SHAPE, "information sweep does not fit in shared memory");
     if (rc != 0) return fail(PTM_ERR_CUDA, std::string("xtwx sweep: ") + cudaGetErrorString((cudaError_t)rc));
     for (int i = 0; i < take; ++i) {

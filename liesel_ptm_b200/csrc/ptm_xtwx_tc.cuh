@@ -44,6 +44,8 @@ struct XtwxTcArgs {
   int CB;                // chain blocks of 128
 };
 
+constexpr float kLogSqrtEpsF = -7.9711924f;  // log(sqrt(FLT_EPSILON)) = log(3.4526698e-04)
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ float tf32_round(float x) {
@@ -77,6 +79,8 @@ __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) {
   if (!done) __trap();
 }
 
+// NSC > 0: number of scale terms known at compile time (predictor loop fully unrolled).
+template <int NSC>
 __global__ void __launch_bounds__(1024, 1) k_xtwx_tc(const XtwxTcArgs g) {
   const XtwxArgs<float>& a = g.a;
   extern __shared__ __align__(128) unsigned char smem_tc[];
@@ -127,7 +131,6 @@ __global__ void __launch_bounds__(1024, 1) k_xtwx_tc(const XtwxTcArgs g) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
   const uint32_t bar0 = smem_u32(&s_bar[0]);
-  const float eps = sqrt_eps<float>();
   uint32_t use0 = 0, use1 = 0;  // commits issued so far on each buffer's barrier (tracked by every thread)
 
   const int q4 = warp & 3, og = (warp >> 2) & 3;  // weight warp: chain quarter, observation quad
@@ -147,13 +150,13 @@ __global__ void __launch_bounds__(1024, 1) k_xtwx_tc(const XtwxTcArgs g) {
       const float* kn = s_kn + sidx * 4 * kKnotStride;
       if (lane < kTcKT) {
         const long long gi = o_begin + (long long)tile * kTcKT + lane;
-        if (gi < o_end) {
-          float bb[4];
-          const int jj = basis_window_fast(t_x[gi], kn, kn + kKnotStride, kn + 2 * kKnotStride, kn + 3 * kKnotStride,
-                                           t_nb, t_invdk, bb);
-          store4(s_b + ((sidx * 2 + slot) * kTcKT + lane) * 4, bb);
-          s_j[(sidx * 2 + slot) * kTcKT + lane] = (a.sc_goff[sidx] + jj) * 128;
-        }
+        float bb[4] = {0.f, 0.f, 0.f, 0.f};
+        int jj = 0;  // observations past the chunk end: a harmless in-range gather
+        if (gi < o_end)
+          jj = basis_window_fast(t_x[gi], kn, kn + kKnotStride, kn + 2 * kKnotStride, kn + 3 * kKnotStride, t_nb,
+                                 t_invdk, bb);
+        store4(s_b + ((sidx * 2 + slot) * kTcKT + lane) * 4, bb);
+        s_j[(sidx * 2 + slot) * kTcKT + lane] = (a.sc_goff[sidx] + jj) * 128;
       }
     };
     if (is_stager) {
@@ -186,28 +189,29 @@ __global__ void __launch_bounds__(1024, 1) k_xtwx_tc(const XtwxTcArgs g) {
       if (is_weight) {
         float hi[4], lo[4];
         const float* gl = s_gam + row;
+        const int nq = NSC > 0 ? NSC : nsc;
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const int o = og * 4 + k4;
-          float wgt = 0.f;
-          if (base + o < o_end) {
-            float es = gamma0;
-            const float* bq = s_b + (b * kTcKT + o) * 4;
-            const int* jq = s_j + b * kTcKT + o;
-            for (int q = 0; q < nsc; ++q, bq += 2 * kTcKT * 4, jq += 2 * kTcKT) {
-              float b0, b1, b2, b3;
-              load4(bq, b0, b1, b2, b3);
-              const float* gp = gl + *jq;
-              float f = b0 * gp[0];
-              f = fmaf(b1, gp[128], f);
-              f = fmaf(b2, gp[256], f);
-              f = fmaf(b3, gp[384], f);
-              es += f;
-            }
-            const float sd = fast_exp(es);
-            const float sdc = sd > eps ? sd : eps;
-            wgt = fast_rcp(sdc * sdc);
+          float es = gamma0;
+          const float* bq = s_b + (b * kTcKT + o) * 4;
+          const int* jq = s_j + b * kTcKT + o;
+#pragma unroll
+          for (int q = 0; q < nq; ++q) {
+            float b0, b1, b2, b3;
+            load4(bq + q * (2 * kTcKT * 4), b0, b1, b2, b3);
+            const float* gp = gl + jq[q * (2 * kTcKT)];
+            float f = b0 * gp[0];
+            f = fmaf(b1, gp[128], f);
+            f = fmaf(b2, gp[256], f);
+            f = fmaf(b3, gp[384], f);
+            es += f;
           }
+          // w = 1/max(sigma, sqrt(eps))^2 = exp(-2 max(eta_sigma, log sqrt(eps)))
+          const float ec = es > kLogSqrtEpsF ? es : kLogSqrtEpsF;
+          float wgt;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(wgt) : "f"(ec * -2.8853900817779268f));
+          if (base + o >= o_end) wgt = 0.f;
           hi[k4] = tf32_round(wgt);
           lo[k4] = wgt - hi[k4];
         }
@@ -346,11 +350,22 @@ inline int xtwx_tc_sweep(XtwxArgs<float>& a, double* partial, int num_sms, int f
   a.chunk_len = chunk;
   a.n_items = g.CB * a.M;
   g.a = a;
-  cudaError_t e = cudaFuncSetAttribute(k_xtwx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
   const int warps = (kTcWW + NS + 1 + 3) / 4 * 4;
   const int grid = std::min(a.n_items, num_sms);
-  k_xtwx_tc<<<grid, 32 * warps, smem, st>>>(g);
+  cudaError_t e = cudaSuccess;
+  auto launch = [&](auto kern) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) kern<<<grid, 32 * warps, smem, st>>>(g);
+  };
+  switch (a.nsc) {
+    case 1: launch(k_xtwx_tc<1>); break;
+    case 2: launch(k_xtwx_tc<2>); break;
+    case 3: launch(k_xtwx_tc<3>); break;
+    case 4: launch(k_xtwx_tc<4>); break;
+    case 5: launch(k_xtwx_tc<5>); break;
+    default: launch(k_xtwx_tc<0>); break;
+  }
+  if (e != cudaSuccess) return (int)e;
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   ++*launches;

@@ -290,6 +290,19 @@ def _f64_oracle_of(case, nparam=20):
     return om, st
 
 
+def test_xtwx_f32_tensor_core_several_sweeps():
+    """5 location terms with 30 bases need 5 x 128 TMEM columns: two tensor-core sweeps."""
+    case = build_case(n=3001, n_loc=5, n_scale=1, nbases=30, nparam=20, C=40, dtype=np.float32)
+    om, st = _f64_oracle_of(case)
+    params = torch.from_numpy(case.params).cuda()
+    Ps, Ls = case.model.precision_all(params)
+    assert case.model.last_xtwx_route() == "tcgen05"
+    for t in range(5):
+        _, ref_P, ref_L = om.loc_precision(st, t)
+        assert rel_err(Ps[t].cpu().numpy(), ref_P) < 2e-5
+        assert rel_err(Ls[t].cpu().numpy(), ref_L) < 2e-4
+
+
 @pytest.mark.parametrize("n,C", [(37, 3), (5000, 130), (20011, 257)])
 def test_xtwx_f32_tensor_core_and_banded_routes(n, C, monkeypatch):
     """float32 information of the location terms: the tcgen05 route (3xTF32, f32 TMEM
