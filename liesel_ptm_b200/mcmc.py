@@ -12,9 +12,9 @@ only through ``log_prob_and_grad`` / ``precision`` (the C ABI), for all chains a
   ``solve`` / ``mvn_sample`` / ``mvn_log_prob`` restate liesel.goose.iwls_utils (not in
   tree): precision-Cholesky parameterisation, log-density without the 2*pi constant
   cancelling in the ratio.
-* ``mala_transition`` is a plain preconditioned Langevin step for blocks without an
-  information matrix (the transformation coefficients delta_z; the reference samples
-  them with NUTS from blackjax, which is out of scope).
+* ``hmc_transition`` / ``mala_transition`` are plain HMC / Langevin steps for the block
+  without an information matrix (the transformation coefficients delta_z; the reference
+  samples them with NUTS from blackjax, which is out of scope).
 
 Smoothing scales tau are held fixed (their Gibbs / NUTS updates are O(1) per chain and
 stay with the host sampler).
@@ -28,6 +28,7 @@ import time
 import numpy as np
 import torch
 
+from . import _lib
 from .model import LocScalePTM
 
 
@@ -63,9 +64,15 @@ def _mh(gen, params, prop, logp, logp_prop, correction):
 
 
 def iwls_transition(model: LocScalePTM, params: torch.Tensor, term_index: int, step_size: float, gen,
-                    cache=None):
+                    cache=None, chol=None):
     """One IWLS-MH transition of the coefficient block of ``term_index`` for all chains.
-    Cost per call: 2 logp+grad sweeps and 2 information sweeps (iwls_fixed.py:159-186)."""
+    Cost per call: 2 logp+grad sweeps and 2 information sweeps (iwls_fixed.py:159-186).
+
+    ``chol``: precision Cholesky factor [C, p, p] valid at the current AND the proposed
+    state.  The information of a location term depends on the state only through the scale
+    predictor (w = 1/sigma^2) and tau, that of a scale term (W == 2) only on tau, so a
+    proposal that moves this block alone leaves it unchanged; passing it skips both
+    information sweeps without changing the transition."""
     lo = model.layout["beta"][term_index]
     p = model.terms[term_index][0].basis.ncoef
     s = step_size
@@ -76,7 +83,9 @@ def iwls_transition(model: LocScalePTM, params: torch.Tensor, term_index: int, s
         logp, grad = logp.clone(), grad.clone()
     else:
         logp, grad = cache
-    _, chol = model.precision(term_index, params)
+    fixed_info = chol is not None
+    if not fixed_info:
+        _, chol = model.precision(term_index, params)
     pos = params[:, lo: lo + p]
     mu = pos + 0.5 * s * s * _solve(chol, grad[:, lo: lo + p])
     s3 = s[:, :, None] if torch.is_tensor(s) else s
@@ -86,7 +95,7 @@ def iwls_transition(model: LocScalePTM, params: torch.Tensor, term_index: int, s
     prop[:, lo: lo + p] = prop_block
     logp_p, grad_p = model.log_prob_and_grad(prop)
     logp_p, grad_p = logp_p.clone(), grad_p.clone()
-    _, chol_p = model.precision(term_index, prop)
+    chol_p = chol if fixed_info else model.precision(term_index, prop)[1]
     mu_p = prop_block + 0.5 * s * s * _solve(chol_p, grad_p[:, lo: lo + p])
     bwd = _mvn_log_prob(pos, mu_p, chol_p / s3)
     new, acc, la = _mh(gen, params, prop, logp, logp_p, bwd - fwd)
@@ -147,10 +156,47 @@ def effective_sample_size(x: np.ndarray) -> float:
     return float(m * n / max(tau, 1.0 / np.log10(max(m * n, 10))))
 
 
+def hmc_transition(model: LocScalePTM, params: torch.Tensor, lo: int, width: int, step_size, n_leapfrog: int,
+                   metric_chol: torch.Tensor, gen, cache=None):
+    """Hamiltonian Monte Carlo on params[:, lo:lo+width] with a dense metric: ``metric_chol``
+    is the lower Cholesky factor L of the inverse mass matrix Sigma = L L' (the pooled
+    posterior covariance estimate), per-chain step sizes, ``n_leapfrog`` logp+grad sweeps.
+    Stands in for the reference's NUTS block on delta_z (blackjax, out of scope)."""
+    if cache is None:
+        logp, grad = model.log_prob_and_grad(params)
+        logp, grad = logp.clone(), grad.clone()
+    else:
+        logp, grad = cache
+    eps = (step_size if torch.is_tensor(step_size) else
+           torch.full((params.shape[0],), float(step_size), dtype=params.dtype, device=params.device))[:, None]
+    Lm = metric_chol
+    sigma = Lm @ Lm.T
+    z = torch.randn((params.shape[0], width), dtype=params.dtype, device=params.device, generator=gen)
+    mom0 = torch.linalg.solve_triangular(Lm.T, z.T, upper=True).T  # p = L^-T z ~ N(0, Sigma^-1)
+    mom = mom0 + 0.5 * eps * grad[:, lo: lo + width]
+    q = params.clone()
+    logp_q, grad_q = logp, grad
+    for i in range(n_leapfrog):
+        q[:, lo: lo + width] += eps * (mom @ sigma)
+        logp_q, grad_q = model.log_prob_and_grad(q)
+        logp_q, grad_q = logp_q.clone(), grad_q.clone()
+        mom = mom + (0.5 if i == n_leapfrog - 1 else 1.0) * eps * grad_q[:, lo: lo + width]
+    kin0 = 0.5 * (z * z).sum(-1)
+    kin1 = 0.5 * ((mom @ Lm) ** 2).sum(-1)
+    new, acc, la = _mh(gen, params, q, logp, logp_q, kin0 - kin1)
+    return new, (torch.where(acc, logp_q, logp), torch.where(acc[:, None], grad_q, grad)), TransitionInfo(acc, la)
+
+
 def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: int, seed: int = 0,
-               iwls_step: float = 1.0, mala_step: float = 0.02, target_accept: float = 0.6):
-    """Sweep per iteration: an IWLS-MH transition per smooth term, a MALA transition on
-    delta_z (per-chain step size adapted towards ``target_accept`` during warm-up).
+               iwls_step: float = 1.0, dz_step: float = 0.05, target_accept: float = 0.8, n_leapfrog: int = 8,
+               reuse_information: bool = True):
+    """Sweep per iteration: an IWLS-MH transition per smooth term, an HMC transition on
+    delta_z.  Warm-up adapts the per-chain step sizes (Robbins-Monro on the acceptance
+    probability) and, at 2/8 ... 7/8 of its length, the dense metric of delta_z from the
+    pooled across-chain covariance of the draws since the previous update.  With ``reuse_information`` the information matrices are
+    evaluated once per sweep for all location terms (``precision_all``; they only change
+    when a scale term or an intercept moves) and once per run for the scale terms (W == 2,
+    tau fixed) instead of twice per transition -- same transitions, fewer sweeps.
     Returns (draws [draws, C, P] on the host, info dict with timings and acceptance)."""
     gen = torch.Generator(device=params0.device)
     gen.manual_seed(seed)
@@ -158,33 +204,62 @@ def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: in
     C = params.shape[0]
     L = model.layout
     dz_lo, dz_w = L["delta_z"], model.nparam - 1
-    step = torch.full((C,), float(mala_step), dtype=params.dtype, device=params.device)
+    step = torch.full((C,), float(dz_step), dtype=params.dtype, device=params.device)
+    metric_chol = torch.eye(dz_w, dtype=params.dtype, device=params.device)
+    adapt_t = 0
+    metric_updates = {(warmup * k) // 8 for k in (2, 3, 4, 5, 6, 7)}
     T = len(model.terms)
+    is_loc = [pred == _lib.PTM_LOC for _, pred in model.terms]
     istep = torch.full((max(T, 1), C), float(iwls_step), dtype=params.dtype, device=params.device)
     cache = None
     out = torch.empty((draws, C, params.shape[1]), dtype=params.dtype, device=params.device)
-    acc_iwls, acc_mala, n_it = 0.0, 0.0, 0
-    t_post = 0.0
+    acc_iwls, acc_dz, n_it = 0.0, 0.0, 0
+    scale_chol = {}
+    if reuse_information:
+        for t in range(T):
+            if not is_loc[t]:
+                scale_chol[t] = model.precision(t, params)[1].clone()
+    window = []
+    t0 = time.perf_counter()
     for it in range(warmup + draws):
         if it == warmup:
             torch.cuda.synchronize()
             t0 = time.perf_counter()
+        loc_chol = None
+        if reuse_information and any(is_loc):
+            loc_chol = [c.clone() for c in model.precision_all(params)[1]]
+        k_loc = 0
         for t in range(T):
-            params, cache, info = iwls_transition(model, params, t, istep[t], gen, cache)
-            if it < warmup:  # dual-averaging stand-in: Robbins-Monro on the log step size
+            chol = None
+            if reuse_information:
+                chol = loc_chol[k_loc] if is_loc[t] else scale_chol[t]
+            k_loc += 1 if is_loc[t] else 0
+            params, cache, info = iwls_transition(model, params, t, istep[t], gen, cache, chol=chol)
+            if it < warmup:
                 a = torch.exp(torch.clamp(info.log_alpha, max=0.0))
                 istep[t] = torch.clamp(istep[t] * torch.exp((a - 0.8) * (10.0 / (it + 10.0))), 1e-3, 2.0)
             else:
                 acc_iwls += info.accepted.double().mean().item() / T
-        params, cache, info = mala_transition(model, params, dz_lo, dz_w, step, gen, cache)
-        if it < warmup:  # Robbins-Monro adaptation of the per-chain step size
+        params, cache, info = hmc_transition(model, params, dz_lo, dz_w, step, n_leapfrog, metric_chol, gen, cache)
+        if it < warmup:
             a = torch.exp(torch.clamp(info.log_alpha, max=0.0))
-            step = step * torch.exp((a - target_accept) * (10.0 / (it + 10.0)))
+            step = step * torch.exp((a - target_accept) * (10.0 / (adapt_t + 10.0)))
+            adapt_t += 1
+            if it >= warmup // 8:
+                window.append(params[:, dz_lo: dz_lo + dz_w].clone())
+            if window and (it + 1) in metric_updates and C * len(window) >= 10 * dz_w:
+                cov = torch.cov(torch.cat(window, 0).T)
+                cov = cov + 1e-6 * torch.diagonal(cov).mean() * torch.eye(dz_w, dtype=cov.dtype, device=cov.device)
+                metric_chol = torch.linalg.cholesky(cov)
+                step = torch.full_like(step, 0.5 * dz_w ** -0.25)  # whitened scale; re-adapt from there
+                adapt_t = 0
+                window = []
         else:
-            acc_mala += info.accepted.double().mean().item()
+            acc_dz += info.accepted.double().mean().item()
             out[it - warmup] = params
             n_it += 1
     torch.cuda.synchronize()
     t_post = time.perf_counter() - t0
     return out.cpu().numpy(), {"posterior_seconds": t_post, "accept_iwls": acc_iwls / max(n_it, 1),
-                               "accept_mala": acc_mala / max(n_it, 1), "mala_step_median": float(step.median())}
+                               "accept_dz": acc_dz / max(n_it, 1), "dz_step_median": float(step.median()),
+                               "n_leapfrog": n_leapfrog}

@@ -468,7 +468,11 @@ def test_sampler_runs_and_mixes():
     params = torch.from_numpy(case.params).cuda()
     draws, info = mcmc.run_chains(case.model, params, warmup=60, draws=120, seed=1)
     assert draws.shape == (120, 16, case.P) and np.isfinite(draws).all()
-    assert 0.05 < info["accept_iwls"] <= 1.0 and 0.05 < info["accept_mala"] <= 1.0
+    assert 0.05 < info["accept_iwls"] <= 1.0 and 0.05 < info["accept_dz"] <= 1.0
     lo = case.layout["beta"][0]
     ess = mcmc.effective_sample_size(draws[:, :, lo].T)
     assert ess > 50
+    # reusing the information matrices does not change the chain (same seed, same draws)
+    draws2, _ = mcmc.run_chains(case.model, params, warmup=10, draws=10, seed=3, reuse_information=True)
+    draws3, _ = mcmc.run_chains(case.model, params, warmup=10, draws=10, seed=3, reuse_information=False)
+    assert np.allclose(draws2, draws3, rtol=1e-9, atol=1e-11)

@@ -1,4 +1,4 @@
-"""ESS/s of the repo's minimal sampler (IWLS-MH per smooth term + MALA on delta_z, smoothing
+"""ESS/s of the repo's minimal sampler (IWLS-MH per smooth term + HMC on delta_z, smoothing
 scales fixed) over the fused operator, for BASELINE configs 1 and 2.  min bulk-ESS over the
 sampled parameters / wall seconds of the posterior epoch."""
 import json, sys
@@ -19,11 +19,12 @@ for name, C, warm, draws in [("c1_readme_n100", 64, 300, 500), ("c2_n100k_3loc_1
     L = m.layout
     cols = list(range(L["beta"][0], L["delta_z"] + m.nparam - 1)) if m.terms else list(range(L["delta_z"], L["delta_z"] + m.nparam - 1))
     ess = np.array([mcmc.effective_sample_size(dr[:, :, j].T) for j in cols])
+    print("ess per parameter", np.round(ess).astype(int).tolist())
     rec = {"chains": C, "warmup": warm, "draws": draws, "posterior_seconds": info["posterior_seconds"],
            "min_ess": float(ess.min()), "median_ess": float(np.median(ess)),
            "min_ess_per_s": float(ess.min() / info["posterior_seconds"]),
            "iterations_per_s": draws / info["posterior_seconds"],
-           "accept_iwls": info["accept_iwls"], "accept_mala": info["accept_mala"]}
+           "accept_iwls": info["accept_iwls"], "accept_dz": info["accept_dz"], "n_leapfrog": info["n_leapfrog"]}
     out[name] = rec
     print(name, json.dumps(rec))
 json.dump(out, open("gpurun_out/r1_ess.json", "w"), indent=1)
