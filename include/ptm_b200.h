@@ -201,9 +201,12 @@ int ptm_intercept_stats_f32(const PtmProblem* prob, const float* params, int64_t
 int ptm_last_launch_count(void);
 
 /* Route the last information sweep (ptm_xtwx / ptm_loc_precision / ptm_loc_precision_all)
- * on this thread took: 0 = banded CUDA-core sweep, 1 = tcgen05 tensor-core sweep (float
- * problems, location terms, when the terms fit TMEM / shared memory).  Setting the
- * environment variable PTM_XTWX_TC=0 forces route 0. */
+ * on this thread took: 0 = banded CUDA-core sweep; 2 = tcgen05 tensor-core sweep (float
+ * problems, location terms, when the terms fit TMEM / shared memory) with the scale
+ * predictor evaluated on the tensor cores as well; 1 = tcgen05 contraction with the weights
+ * evaluated on CUDA cores.  By default route 2 is taken when its operand tiles can be
+ * double-buffered in shared memory, else route 1, else route 0.  The environment variable
+ * PTM_XTWX_TC=0/1/2 forces a route (falling back downwards when it does not fit). */
 int ptm_last_xtwx_route(void);
 
 /* Measurement hook (bench.py): when enabled, logp / logp_grad calls on this thread

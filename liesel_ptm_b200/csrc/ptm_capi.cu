@@ -463,6 +463,13 @@ static bool tc_route_enabled() {
   const char* e = getenv("PTM_XTWX_TC");
   return !(e && e[0] == '0');
 }
+// PTM_XTWX_TC: 0 banded sweep, 1 tensor-core contraction with the weights on CUDA cores,
+// 2 scale predictor on the tensor cores too; unset = pick 2 when its Q tiles can be
+// double-buffered, else 1.
+static int tc_version() {
+  const char* e = getenv("PTM_XTWX_TC");
+  return e ? atoi(e) : 3;
+}
 static int tc_flush_tiles() {
   const char* e = getenv("PTM_TC_FLUSH");
   return e ? atoi(e) : 0;
@@ -542,6 +549,10 @@ int xtwx_terms(const PtmProblem* pr, const int* terms, int nterms, const R* para
       if (loc && tc_route_enabled())
         for (take = std::min(nterms - done, 8); take >= 1 && rc == -1; --take) {
           select(take);
+          rc = tc_version() >= 2 ? ptm::xtwx_tc2_sweep(xa, xt, pr->num_sms, tc_flush_tiles(), tc_version() == 2, st,
+                                                       &g_launches)
+                                 : -1;
+          if (rc != -1) { g_last_xtwx_route = 2; break; }
           rc = ptm::xtwx_tc_sweep(xa, xt, pr->num_sms, tc_flush_tiles(), st, &g_launches);
           if (rc != -1) { g_last_xtwx_route = 1; break; }
         }

@@ -60,6 +60,11 @@ struct MainArgs {
   TrafoScal<R> ts;
 };
 
+#ifndef PTM_TERM_UNROLL
+#define PTM_TERM_UNROLL 2  // terms of one predictor evaluated per unrolled eval-loop iteration
+#endif
+constexpr int kTermUnroll = PTM_TERM_UNROLL;
+
 // CTA-wide barrier issued from role-specific code (whole warps take one role).
 __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
 
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               const R* gl = s_gam + lane;
               const int qstep = 3 * To;
               int q = 0;
-#pragma unroll 2
+#pragma unroll kTermUnroll
               for (; q < a.T_loc; ++q, bq += qstep * 4, jq += qstep) {
                 R b0, b1, b2, b3;
                 load4(bq, b0, b1, b2, b3);
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                 f = fma(b3, gp[96], f);
                 em += f;
               }
-#pragma unroll 2
+#pragma unroll kTermUnroll
               for (; q < T; ++q, bq += qstep * 4, jq += qstep) {
                 R b0, b1, b2, b3;
                 load4(bq, b0, b1, b2, b3);

@@ -295,8 +295,9 @@ class LocScalePTM:
         _lib.check(self._lib.ptm_profile_enable(int(on)))
 
     def last_xtwx_route(self) -> str:
-        """Route of the last information sweep: "banded" (CUDA cores) or "tcgen05"."""
-        return "tcgen05" if self._lib.ptm_last_xtwx_route() == 1 else "banded"
+        """Route of the last information sweep: "banded" (CUDA cores), "tcgen05-w" (tensor-core
+        contraction, weights on CUDA cores) or "tcgen05" (scale predictor on the tensor cores too)."""
+        return {0: "banded", 1: "tcgen05-w", 2: "tcgen05"}[self._lib.ptm_last_xtwx_route()]
 
     def last_kernel_ms(self) -> tuple[float, float, float]:
         a, b, c = C.c_float(), C.c_float(), C.c_float()

@@ -296,7 +296,7 @@ def test_xtwx_f32_tensor_core_several_sweeps():
     om, st = _f64_oracle_of(case)
     params = torch.from_numpy(case.params).cuda()
     Ps, Ls = case.model.precision_all(params)
-    assert case.model.last_xtwx_route() == "tcgen05"
+    assert case.model.last_xtwx_route().startswith("tcgen05")
     for t in range(5):
         _, ref_P, ref_L = om.loc_precision(st, t)
         assert rel_err(Ps[t].cpu().numpy(), ref_P) < 2e-5
@@ -313,6 +313,7 @@ def test_xtwx_f32_tensor_core_and_banded_routes(n, C, monkeypatch):
     om, st = _f64_oracle_of(case)
     params = torch.from_numpy(case.params).cuda()
     refs = [om.loc_precision(st, t) for t in range(2)]
+    monkeypatch.setenv("PTM_XTWX_TC", "2")  # scale predictor on the tensor cores as well
     for flush in ("3", None):  # promote every 3 tiles / default cadence
         if flush:
             monkeypatch.setenv("PTM_TC_FLUSH", flush)
@@ -326,6 +327,10 @@ def test_xtwx_f32_tensor_core_and_banded_routes(n, C, monkeypatch):
     x_tc = case.model.xtwx(0, params).cpu().numpy()
     assert case.model.last_xtwx_route() == "tcgen05"
     assert rel_err(x_tc, refs[0][0]) < 2e-5
+    monkeypatch.setenv("PTM_XTWX_TC", "1")  # weights on CUDA cores, contraction on tensor cores
+    x_tw = case.model.xtwx(0, params).cpu().numpy()
+    assert case.model.last_xtwx_route() == "tcgen05-w"
+    assert rel_err(x_tw, refs[0][0]) < 2e-5
     monkeypatch.setenv("PTM_XTWX_TC", "0")
     x_b = case.model.xtwx(0, params).cpu().numpy()
     assert case.model.last_xtwx_route() == "banded"

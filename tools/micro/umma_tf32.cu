@@ -97,6 +97,69 @@ __global__ void __launch_bounds__(128, 1) k_test(const float* A, const float* B,
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
 }
 
+
+// ---- timing: REP back-to-back MMAs (same operands, one accumulator) for several N ----
+template <int NN>
+__global__ void __launch_bounds__(128, 1) k_time(long long* out, int rep) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_t;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 * KT * 4 + 256 * KT * 4) / 4; i += 128) reinterpret_cast<float*>(sm)[i] = 1.0f;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&s_t)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_t;
+  long long t0 = 0, t1 = 0;
+  if (tid == 0) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const uint64_t da = make_desc(smem_u32(sm)), db = make_desc(smem_u32(sm) + 128 * KT * 4);
+    t0 = clock64();
+    for (int r = 0; r < rep; ++r)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
+          "l"(da), "l"(db), "r"(idesc), "r"(1u)
+          : "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar))
+                 : "memory");
+    uint32_t done = 0;
+    while (!done)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+    t1 = clock64();
+    out[0] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+}
+
+template <int NN>
+void time_n() {
+  long long* d; cudaMalloc(&d, 8);
+  const int smem = 128 * KT * 4 + 256 * KT * 4;
+  cudaFuncSetAttribute(k_time<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep : {64, 512}) {
+    k_time<NN><<<1, 128, smem>>>(d, rep);
+    cudaDeviceSynchronize();
+    long long c; cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+    printf("SS tf32 M=128 N=%3d K=8: %4d MMAs in %7lld cycles = %.1f cycles/MMA (math floor %d)\n", NN, rep, c,
+           (double)c / rep, 128 * NN / 256);
+  }
+  cudaFree(d);
+}
+
 int main() {
   float *hA = new float[M * KT], *hB = new float[N * KT], *hD = new float[M * N];
   srand(1);
@@ -120,6 +183,7 @@ int main() {
       if (!(err <= 1e-5)) { if (bad < 5) printf("mismatch m=%d n=%d got %g want %g\n", m, n, hD[m * N + n], ref); ++bad; }
       if (err > maxerr) maxerr = err;
     }
+  time_n<16>(); time_n<32>(); time_n<80>(); time_n<128>(); time_n<256>();
   printf("umma_tf32: max abs err %.3g, mismatches %d of %d\n", maxerr, bad, M * N);
   return bad != 0;
 }

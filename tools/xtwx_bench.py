@@ -33,11 +33,10 @@ for name in names:
         wl = bw.build(name, dtype=dt)
         m = wl.model.build()
         p = torch.from_numpy(wl.params).cuda()
-        for route in (("tcgen05", "banded") if dt == np.float32 else ("banded",)):
-            if route == "banded":
-                os.environ["PTM_XTWX_TC"] = "0"
-            else:
-                os.environ.pop("PTM_XTWX_TC", None)
+        for route in (("auto", "tcgen05", "tcgen05-w", "banded") if dt == np.float32 else ("banded",)):
+            os.environ.pop("PTM_XTWX_TC", None)
+            if route != "auto":
+                os.environ["PTM_XTWX_TC"] = {"banded": "0", "tcgen05-w": "1", "tcgen05": "2"}[route]
             ms_all = timeit(lambda: m.precision_all(p))
             used_all = m.last_xtwx_route()
             ms_one = timeit(lambda: m.precision(0, p))
