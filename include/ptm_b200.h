@@ -197,6 +197,22 @@ int ptm_intercept_stats_f64(const PtmProblem* prob, const double* params, int64_
 int ptm_intercept_stats_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
                             float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Pointwise predictive records over n_samples posterior samples -- the streaming WAIC /
+ * lppd of the reference (EvaluatePTM._lppdi, .lppdi, .waic: model/evaluate.py:106-133,
+ * 177-236) as one sweep.  params is [n_samples, P] like the chain states (draws x chains
+ * flattened).  For every observation i of the shard (device arrays of length n, entries
+ * outside the shard are left untouched):
+ *   lppd[i]  = logsumexp_s log p(y_i | sample s) - log n_samples
+ *   pwaic[i] = Var_s log p(y_i | sample s)                       (ddof = 0)
+ * with log p(y_i | s) = -z^2/2 - log(2 pi)/2 + log h'(r) - eta_sigma (dist.py:339-346).
+ * The aggregates of the WAIC table are sums over i on the caller's side.
+ * Workspace: ptm_pointwise_workspace_bytes(prob, n_samples). */
+size_t ptm_pointwise_workspace_bytes(const PtmProblem* prob, int64_t n_samples);
+int ptm_pointwise_f64(const PtmProblem* prob, const double* params, int64_t n_samples, double* lppd,
+                      double* pwaic, void* workspace, size_t workspace_bytes, void* stream);
+int ptm_pointwise_f32(const PtmProblem* prob, const float* params, int64_t n_samples, float* lppd,
+                      float* pwaic, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernels the last logp / logp_grad call on this thread launched. */
 int ptm_last_launch_count(void);
 

@@ -31,6 +31,7 @@ SYMBOLS = [
     "ptm_xtwx_f64", "ptm_xtwx_f32", "ptm_loc_precision_f64", "ptm_loc_precision_f32",
     "ptm_quadform_f64", "ptm_quadform_f32", "ptm_intercept_stats_f64", "ptm_intercept_stats_f32",
     "ptm_loc_precision_all_f64", "ptm_loc_precision_all_f32",
+    "ptm_pointwise_workspace_bytes", "ptm_pointwise_f64", "ptm_pointwise_f32",
     "ptm_last_launch_count", "ptm_last_xtwx_route", "ptm_profile_enable", "ptm_last_kernel_ms", "ptm_last_error",
     "ptm_version",
 ]
@@ -118,6 +119,12 @@ def load() -> C.CDLL:
         f.restype = C.c_int
         f = getattr(lib, f"ptm_loc_precision_{sfx}")
         f.argtypes = [vp, i32, vp, i64, vp, vp, vp, sz, vp]
+        f.restype = C.c_int
+    lib.ptm_pointwise_workspace_bytes.argtypes = [vp, i64]
+    lib.ptm_pointwise_workspace_bytes.restype = sz
+    for sfx in ("f64", "f32"):
+        f = getattr(lib, f"ptm_pointwise_{sfx}")
+        f.argtypes = [vp, vp, i64, vp, vp, vp, sz, vp]
         f.restype = C.c_int
     lib.ptm_last_launch_count.restype = C.c_int
     lib.ptm_last_xtwx_route.restype = C.c_int

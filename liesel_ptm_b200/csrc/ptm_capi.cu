@@ -305,9 +305,9 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   return pl;
 }
 
-template <typename R, int NB, bool GRAD, int MAXT>
+template <typename R, int NB, int MODE, int MAXT>
 int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
-  auto kern = ptm::k_main<R, NB, GRAD, MAXT>;
+  auto kern = ptm::k_main<R, NB, MODE, MAXT>;
   PTM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_main));
   kern<<<pl.grid, 32 * (T + pl.NU), pl.smem_main, st>>>(a);
   PTM_CUDA(cudaGetLastError());
@@ -316,14 +316,57 @@ int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t
 
 // CTA = T term warps + NU eval warps (c3: 18 warps, 96 registers per thread); the
 // 1024-thread variant covers up to 24 terms.
-template <typename R, int NB, bool GRAD>
+template <typename R, int NB, int MODE>
 int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
   // registers are granted per 4 warps: <= 16 warps -> 128/thread, 20 -> 96, 24 -> 80, 32 -> 64
   const int threads = 32 * (T + pl.NU);
-  if (threads <= 512) return launch_main_t<R, NB, GRAD, 512>(a, pl, T, st);
-  if (threads <= 640) return launch_main_t<R, NB, GRAD, 640>(a, pl, T, st);
-  if (threads <= 768) return launch_main_t<R, NB, GRAD, 768>(a, pl, T, st);
-  return launch_main_t<R, NB, GRAD, 1024>(a, pl, T, st);
+  if (threads <= 512) return launch_main_t<R, NB, MODE, 512>(a, pl, T, st);
+  if (threads <= 640) return launch_main_t<R, NB, MODE, 640>(a, pl, T, st);
+  if (threads <= 768) return launch_main_t<R, NB, MODE, 768>(a, pl, T, st);
+  return launch_main_t<R, NB, MODE, 1024>(a, pl, T, st);
+}
+
+template <typename R>
+void fill_main_args(const PtmProblem* pr, const Plan& pl, long long C, R* Gamma, R* cc, double* partial,
+                    ptm::MainArgs<R>& ma) {
+  memset(&ma, 0, sizeof ma);
+  ma.y = reinterpret_cast<const R*>(pr->d_y);
+  ma.X = reinterpret_cast<const R*>(pr->d_X);
+  ma.knots = reinterpret_cast<const R*>(pr->d_knots);
+  ma.grid = reinterpret_cast<const R*>(pr->d_grid);
+  ma.Gamma = Gamma; ma.cc = cc; ma.partial = partial;
+  ma.n = pr->n; ma.obs_begin = pr->obs_begin; ma.obs_end = pr->obs_end;
+  ma.chunk_len = pl.chunk_len;
+  ma.C = (int)C; ma.CG = pl.CG; ma.M = pl.M; ma.n_items = pl.n_items;
+  ma.NSLOT = pl.NSLOT;
+  ma.KK = pr->KK;
+  ma.T = pr->T; ma.T_loc = pr->T_loc; ma.T_scale = pr->T_scale;
+  ma.To = pl.To; ma.NU = pl.NU; ma.sum_nb = pr->sum_nb;
+  {
+    int q = 0;
+    for (int t = 0; t < pr->T; ++t) if (pr->pred[t] == PTM_LOC) ma.order[q++] = t;
+    for (int t = 0; t < pr->T; ++t) if (pr->pred[t] == PTM_SCALE) ma.order[q++] = t;
+  }
+  for (int t = 0; t < pr->T; ++t) {
+    ma.nb[t] = pr->nb[t]; ma.pred[t] = pr->pred[t];
+    ma.goff[t] = pr->goff[t]; ma.inv_dk[t] = (R)pr->inv_dk[t];
+  }
+  ptm::TrafoConst<R> tcr;
+  fill_tc<R>(pr->tc64, tcr);
+  ma.ts = tcr;
+}
+
+template <typename R>
+void fill_pre_args(const PtmProblem* pr, const R* params, long long C, R* Gamma, R* cc, ptm::PreArgs<R>& pa) {
+  memset(&pa, 0, sizeof pa);
+  pa.params = params; pa.Gamma = Gamma; pa.cc = cc;
+  pa.Zall = reinterpret_cast<const R*>(pr->d_Zall);
+  pa.Zd = reinterpret_cast<const R*>(pr->d_Zd);
+  pa.tc = reinterpret_cast<const ptm::TrafoConst<double>*>(pr->d_tc64);
+  pa.C = (int)C; pa.P = pr->P; pa.T = pr->T; pa.dz_off = pr->dz_off;
+  for (int t = 0; t < pr->T; ++t) {
+    pa.nb[t] = pr->nb[t]; pa.p[t] = pr->p[t]; pa.zoff[t] = pr->zoff[t]; pa.boff[t] = pr->boff[t];
+  }
 }
 
 template <typename R>
@@ -345,15 +388,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   g_launches = 0;
 
   ptm::PreArgs<R> pa;
-  memset(&pa, 0, sizeof pa);
-  pa.params = params; pa.Gamma = Gamma; pa.cc = cc;
-  pa.Zall = reinterpret_cast<const R*>(pr->d_Zall);
-  pa.Zd = reinterpret_cast<const R*>(pr->d_Zd);
-  pa.tc = reinterpret_cast<const ptm::TrafoConst<double>*>(pr->d_tc64);
-  pa.C = (int)C; pa.P = pr->P; pa.T = pr->T; pa.dz_off = pr->dz_off;
-  for (int t = 0; t < pr->T; ++t) {
-    pa.nb[t] = pr->nb[t]; pa.p[t] = pr->p[t]; pa.zoff[t] = pr->zoff[t]; pa.boff[t] = pr->boff[t];
-  }
+  fill_pre_args<R>(pr, params, C, Gamma, cc, pa);
   if (g_profile) PTM_CUDA(cudaEventRecord(g_ev[0], st));
   ptm::k_pre<R><<<(unsigned)C, 128, pr->P * sizeof(R), st>>>(pa);
   PTM_CUDA(cudaGetLastError());
@@ -361,38 +396,15 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   if (g_profile) PTM_CUDA(cudaEventRecord(g_ev[1], st));
 
   ptm::MainArgs<R> ma;
-  memset(&ma, 0, sizeof ma);
-  ma.y = reinterpret_cast<const R*>(pr->d_y);
-  ma.X = reinterpret_cast<const R*>(pr->d_X);
-  ma.knots = reinterpret_cast<const R*>(pr->d_knots);
-  ma.grid = reinterpret_cast<const R*>(pr->d_grid);
-  ma.Gamma = Gamma; ma.cc = cc; ma.partial = partial;
-  ma.n = pr->n; ma.obs_begin = pr->obs_begin; ma.obs_end = pr->obs_end;
-  ma.chunk_len = pl.chunk_len;
-  ma.C = (int)C; ma.CG = pl.CG; ma.M = pl.M; ma.n_items = pl.n_items;
-  ma.NSLOT = want_grad ? pl.NSLOT : ptm::kLogpSlots;
-  ma.KK = pr->KK;
-  ma.T = pr->T; ma.T_loc = pr->T_loc; ma.T_scale = pr->T_scale;
-  ma.To = pl.To; ma.NU = pl.NU; ma.sum_nb = pr->sum_nb;
-  {
-    int q = 0;
-    for (int t = 0; t < pr->T; ++t) if (pr->pred[t] == PTM_LOC) ma.order[q++] = t;
-    for (int t = 0; t < pr->T; ++t) if (pr->pred[t] == PTM_SCALE) ma.order[q++] = t;
-  }
-  for (int t = 0; t < pr->T; ++t) {
-    ma.nb[t] = pr->nb[t]; ma.pred[t] = pr->pred[t];
-    ma.goff[t] = pr->goff[t]; ma.inv_dk[t] = (R)pr->inv_dk[t];
-  }
-  {
-    ptm::TrafoConst<R> tcr;
-    fill_tc<R>(pr->tc64, tcr);
-    ma.ts = tcr;
-  }
+  fill_main_args<R>(pr, pl, C, Gamma, cc, partial, ma);
+  if (!want_grad) ma.NSLOT = ptm::kLogpSlots;
   int rc;
   if (pr->max_nb <= 20)
-    rc = want_grad ? launch_main<R, 20, true>(ma, pl, pr->T, st) : launch_main<R, 20, false>(ma, pl, pr->T, st);
+    rc = want_grad ? launch_main<R, 20, ptm::kModeGrad>(ma, pl, pr->T, st)
+                   : launch_main<R, 20, ptm::kModeLogp>(ma, pl, pr->T, st);
   else
-    rc = want_grad ? launch_main<R, 32, true>(ma, pl, pr->T, st) : launch_main<R, 32, false>(ma, pl, pr->T, st);
+    rc = want_grad ? launch_main<R, 32, ptm::kModeGrad>(ma, pl, pr->T, st)
+                   : launch_main<R, 32, ptm::kModeLogp>(ma, pl, pr->T, st);
   if (rc != PTM_OK) return rc;
   ++g_launches;
   if (g_profile) PTM_CUDA(cudaEventRecord(g_ev[2], st));
@@ -424,6 +436,54 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   PTM_CUDA(cudaGetLastError());
   ++g_launches;
   if (g_profile) PTM_CUDA(cudaEventRecord(g_ev[3], st));
+  return PTM_OK;
+}
+
+// Pointwise predictive records over S posterior samples (evaluate.py:120-133, 177-236):
+// lppd_i and p_waic_i for every observation of the shard.  The sweep is the logp-only
+// kernel in its pointwise mode with one CTA per observation chunk visiting all sample
+// groups in turn; the records [n][4] live behind the ordinary workspace.
+template <typename R>
+int pointwise_impl(const PtmProblem* pr, const R* params, long long S, R* lppd, R* pwaic, void* ws,
+                   size_t ws_bytes, void* stream) {
+  if (!pr || !params || !lppd || !pwaic || !ws) return fail(PTM_ERR_NULL, "null argument");
+  if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  if (S < 1) return fail(PTM_ERR_SHAPE, "n_samples must be >= 1");
+  Plan pl = make_plan<R>(pr, S);
+  const size_t need = pl.total + (size_t)pr->n * 4 * sizeof(double);
+  if (ws_bytes < need) return fail(PTM_ERR_WORKSPACE, "workspace too small (see ptm_pointwise_workspace_bytes)");
+  if (pl.smem_main > 227 * 1024) return fail(PTM_ERR_SHAPE, "shared-memory budget exceeded");
+  if (pr->T + pl.NU > 32) return fail(PTM_ERR_SHAPE, "too many smooth terms for one CTA");
+  const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
+  if (len == 0) return PTM_OK;
+  // one CTA per observation chunk, all sample groups of a chunk on the same CTA:
+  // item = cg * M + mchunk with M == gridDim.x
+  long long M = std::min<long long>(pr->num_sms, std::max<long long>(1, len / pl.To));
+  long long chunk = (len + M - 1) / M;
+  chunk = std::max<long long>(pl.To, (chunk + pl.To - 1) / pl.To * pl.To);
+  M = std::max<long long>(1, (len + chunk - 1) / chunk);
+  pl.M = (int)M; pl.chunk_len = chunk; pl.n_items = pl.CG * pl.M; pl.grid = pl.M;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* wsb = reinterpret_cast<char*>(ws);
+  R* Gamma = reinterpret_cast<R*>(wsb + pl.off_gamma);
+  R* cc = reinterpret_cast<R*>(wsb + pl.off_cc);
+  double* point = reinterpret_cast<double*>(wsb + pl.total);
+  g_launches = 0;
+  ptm::PreArgs<R> pa;
+  fill_pre_args<R>(pr, params, S, Gamma, cc, pa);
+  ptm::k_pre<R><<<(unsigned)S, 128, pr->P * sizeof(R), st>>>(pa);
+  PTM_CUDA(cudaGetLastError());
+  ++g_launches;
+  ptm::MainArgs<R> ma;
+  fill_main_args<R>(pr, pl, S, Gamma, cc, nullptr, ma);
+  ma.point = point;
+  int rc = launch_main<R, 20, ptm::kModePoint>(ma, pl, pr->T, st);
+  if (rc != PTM_OK) return rc;
+  ++g_launches;
+  const int blocks = (int)std::min<long long>((len + 255) / 256, 148LL * 8);
+  ptm::k_point_final<R><<<blocks, 256, 0, st>>>(point, pr->obs_begin, pr->obs_end, S, lppd, pwaic);
+  PTM_CUDA(cudaGetLastError());
+  ++g_launches;
   return PTM_OK;
 }
 
@@ -768,6 +828,20 @@ int ptm_loc_precision_all_f64(const PtmProblem* p, const double* params, int64_t
 int ptm_loc_precision_all_f32(const PtmProblem* p, const float* params, int64_t C, float* precision,
                               float* chol, void* ws, size_t wsb, void* st) {
   return precision_all_impl<float>(p, params, C, precision, chol, ws, wsb, st);
+}
+
+size_t ptm_pointwise_workspace_bytes(const PtmProblem* p, int64_t S) {
+  if (!p || S < 1) return 0;
+  const size_t base = ptm_workspace_bytes(p, S);
+  return base ? base + (size_t)p->n * 4 * sizeof(double) : 0;
+}
+int ptm_pointwise_f64(const PtmProblem* p, const double* params, int64_t S, double* lppd, double* pwaic, void* ws,
+                      size_t wsb, void* st) {
+  return pointwise_impl<double>(p, params, S, lppd, pwaic, ws, wsb, st);
+}
+int ptm_pointwise_f32(const PtmProblem* p, const float* params, int64_t S, float* lppd, float* pwaic, void* ws,
+                      size_t wsb, void* st) {
+  return pointwise_impl<float>(p, params, S, lppd, pwaic, ws, wsb, st);
 }
 
 int ptm_last_launch_count(void) { return g_launches; }

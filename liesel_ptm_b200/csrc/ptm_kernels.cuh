@@ -47,6 +47,7 @@ struct MainArgs {
   const R* Gamma;    // [T][kMaxNbases][C]  gamma_t = Z_t beta_t, chain fastest
   const R* cc;       // [KK*5 + 6][C]       cubic pieces, boundary values, intercepts
   double* partial;   // [n_items][NSLOT][32] partial sums, double for both kernels
+  double* point;     // [n][4] per-observation records of the pointwise mode (max, sum exp, sum, sum sq)
   long long n;
   long long obs_begin, obs_end;
   long long chunk_len;
@@ -197,8 +198,14 @@ __device__ __forceinline__ void store4(float* p, const float (&b)[4]) {
 //   warps [0, T)      term warps: stage tile s+1, backward of tile s-1
 //   warps [T, T+NU)   eval warps: forward + point-wise part of tile s
 // ------------------------------------------------------------------------------
-template <typename R, int NB, bool GRAD, int MAXTHREADS>
+// MODE: kModeLogp (logp + intercept statistics), kModeGrad (logp + gradient), kModePoint
+// (per-observation log-density reduced over the chains of the CTA: lppd / WAIC records).
+constexpr int kModeLogp = 0, kModeGrad = 1, kModePoint = 2;
+
+template <typename R, int NB, int MODE, int MAXTHREADS>
 __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
+  constexpr bool GRAD = MODE == kModeGrad;
+  constexpr bool POINT = MODE == kModePoint;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -433,9 +440,43 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             const R tiny = tiny_of<R>();
             const bool above = d > tiny;
             const R dcl = above ? d : tiny;
+            if constexpr (POINT) {
+              // log-density of this observation under the lane's chain (dist.py:339-346),
+              // then max / sum exp / sum / sum of squares over the chains of this group and a
+              // merge into the observation's record.  The CTA that owns this chunk visits
+              // the chain groups one after the other, so the record needs no atomics.
+              const int nvalid = a.C - cg * 32 < 32 ? a.C - cg * 32 : 32;
+              const bool valid = lane < nvalid;
+              const double ll = (-0.5 * (double)z * (double)z - 0.91893853320467274178) +
+                                (log((double)dcl) - (double)es);
+              const bool bad = __any_sync(0xffffffffu, valid && !(ll == ll));
+              double mx = valid ? ll : -INFINITY;
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+              double se = valid ? fast_exp(ll - mx) : 0.0, sa = valid ? ll : 0.0, sq = valid ? ll * ll : 0.0;
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) {
+                se += __shfl_xor_sync(0xffffffffu, se, off);
+                sa += __shfl_xor_sync(0xffffffffu, sa, off);
+                sq += __shfl_xor_sync(0xffffffffu, sq, off);
+              }
+              if (lane == 0) {
+                double* rec = a.point + (base + o) * 4;
+                if (bad) mx = se = sa = sq = __longlong_as_double(0x7ff8000000000000LL);
+                if (cg > 0) {
+                  const double m0 = rec[0], s0 = rec[1];
+                  const double mn = fmax(m0, mx);
+                  se = (m0 == m0 && mx == mx) ? s0 * fast_exp(m0 - mn) + se * fast_exp(mx - mn) : m0 + mx;
+                  mx = (m0 == m0 && mx == mx) ? mn : m0 + mx;
+                  sa += rec[2];
+                  sq += rec[3];
+                }
+                rec[0] = mx; rec[1] = se; rec[2] = sa; rec[3] = sq;
+              }
+            }
             a_z2 += (double)(z * z);
             a_ls += (double)es;
-            if (!GRAD) {  // intercept statistics ride along with the logp-only sweep
+            if (MODE == kModeLogp) {  // intercept statistics ride along with the logp-only sweep
               a_gb0 += (double)einv;
               a_gg0 += (double)r;
               a_gvl += (double)(r * r);
@@ -511,7 +552,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
     }
     // ---- item epilogue: cross-warp sums of the eval-warp partials to HBM ------------
     __syncthreads();
-    {
+    if constexpr (!POINT) {
       const int nreg = GRAD ? kRegSlots : kLogpSlots;
       for (int idx = tid; idx < nreg * 32; idx += blockDim.x) {
         double v = 0.0;
@@ -527,6 +568,21 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
       }
     }
     __syncthreads();
+  }
+}
+
+// Pointwise records -> lppd_i = log mean_s p(y_i | s), p_waic_i = Var_s log p(y_i | s)
+// (ddof = 0), evaluate.py:120-133 and 177-236.
+template <typename R>
+__global__ void k_point_final(const double* __restrict__ point, long long obs_begin, long long obs_end,
+                              long long S, R* __restrict__ lppd, R* __restrict__ pwaic) {
+  for (long long i = obs_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < obs_end;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double* rec = point + i * 4;
+    const double mean = rec[2] / (double)S;
+    lppd[i] = (R)(rec[0] + log(rec[1]) - log((double)S));
+    const double var = rec[3] / (double)S - mean * mean;
+    pwaic[i] = (R)(var > 0.0 || !(var == var) ? var : 0.0);
   }
 }
 

@@ -349,6 +349,32 @@ class LocScalePTM:
                      self._stream()))
         return out
 
+    def pointwise(self, samples: torch.Tensor):
+        """Pointwise predictive records over posterior samples [S, P] (draws x chains
+        flattened): (lppd_i [n], p_waic_i [n]) -- EvaluatePTM._lppdi / .waic
+        (model/evaluate.py:106-133, 177-236) as one fused sweep."""
+        samples = self._check_params(samples)
+        S = samples.shape[0]
+        nbytes = int(self._lib.ptm_pointwise_workspace_bytes(self._handle, S))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+        lppd = torch.zeros(self.n, dtype=self.dtype, device=self.device)
+        pwaic = torch.zeros(self.n, dtype=self.dtype, device=self.device)
+        f = getattr(self._lib, f"ptm_pointwise_{self._sfx}")
+        _lib.check(f(self._handle, samples.data_ptr(), S, lppd.data_ptr(), pwaic.data_ptr(), ws.data_ptr(),
+                     ws.numel(), self._stream()))
+        return lppd, pwaic
+
+    def waic(self, samples: torch.Tensor) -> dict:
+        """The reference's WAIC table (model/evaluate.py:215-236) from ``pointwise``."""
+        lppd_i, p_i = self.pointwise(samples)
+        lppd_i, p_i = lppd_i.double(), p_i.double()
+        elpd_i = lppd_i - p_i
+        n = float(self.n)
+        lppd, p = float(lppd_i.sum()), float(p_i.sum())
+        return {"waic_lppd": lppd, "waic_elpd": lppd - p,
+                "waic_se": float(elpd_i.std(unbiased=False) * n ** 0.5), "waic_p": p,
+                "waic_deviance": -2.0 * (lppd - p), "n_warning": int((p_i > 4).sum())}
+
     def compute_intercepts(self, params: torch.Tensor, n_obs: int | None = None):
         """LocationIntercept.compute_intercept / LogScaleIntercept.compute_intercept
         (predictor.py:80-100, 126-130) for every chain, from one fused sweep: returns

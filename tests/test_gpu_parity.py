@@ -82,6 +82,45 @@ def test_intercept_pseudo_gibbs_values():
     assert rel_err(case.model.log_prob(params).cpu().numpy(), lp_ref) < TOL64
 
 
+def _oracle_pointwise(om, st, C):
+    ll = np.stack([om.loglik_terms(st, c)["ll"] for c in range(C)])  # [C, n]
+    m = ll.max(axis=0)
+    lppd = m + np.log(np.exp(ll - m).sum(axis=0)) - np.log(C)
+    return ll, lppd, ll.var(axis=0)
+
+
+@pytest.mark.parametrize("n,C", [(1, 1), (53, 7), (3000, 32), (4097, 70)])
+def test_pointwise_lppd_and_waic(n, C):
+    """Streaming WAIC / lppd of the reference (evaluate.py:106-133, 177-236): per-observation
+    logsumexp and variance over the samples, in one sweep; ragged last sample group, several
+    observation chunks."""
+    case = build_case(n=n, n_loc=2, n_scale=1, nbases=12, C=C)
+    ll, lppd_ref, p_ref = _oracle_pointwise(case.omodel, case.state, C)
+    params = torch.from_numpy(case.params).cuda()
+    lppd, pwaic = case.model.pointwise(params)
+    assert rel_err(lppd.cpu().numpy(), lppd_ref) < 1e-12
+    assert np.allclose(pwaic.cpu().numpy(), p_ref, rtol=1e-9, atol=1e-13 * max(1.0, float(np.abs(ll).max()) ** 2))
+    tab = case.model.waic(params)
+    elpd_i = lppd_ref - p_ref
+    assert abs(tab["waic_lppd"] - lppd_ref.sum()) < 1e-10 * max(1.0, abs(lppd_ref.sum()))
+    assert abs(tab["waic_p"] - p_ref.sum()) < 1e-9 * max(1.0, p_ref.sum())
+    assert abs(tab["waic_se"] - elpd_i.std() * np.sqrt(n)) < 1e-9 * max(1.0, elpd_i.std() * np.sqrt(n))
+    # the sum over observations of the per-sample log-densities is the likelihood part of logp
+    case.model.set_shard(0, n, add_priors=False)
+    lp = case.model.log_prob(params).cpu().numpy()
+    case.model.set_shard(0, n, add_priors=True)
+    assert rel_err(lp, ll.sum(axis=1)) < 1e-12
+
+
+def test_pointwise_nan_response_and_f32():
+    case = build_case(n=300, n_loc=1, n_scale=1, nbases=12, C=9, dtype=np.float32)
+    om, st = _f64_oracle_of(case)
+    _, lppd_ref, p_ref = _oracle_pointwise(om, st, 9)
+    lppd, pwaic = case.model.pointwise(torch.from_numpy(case.params).cuda())
+    assert rel_err(lppd.cpu().numpy(), lppd_ref) < 1e-5
+    assert np.allclose(pwaic.cpu().numpy(), p_ref, rtol=1e-3, atol=1e-5)
+
+
 def test_quadform():
     """beta' K beta of the Gibbs scale updates (gam/kernel.py:29-39)."""
     case = build_case(n=50, n_loc=2, n_scale=1, nbases=12, C=5)

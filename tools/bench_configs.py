@@ -36,6 +36,9 @@ for name in ["c1_readme_n100", "c2_n100k_3loc_1scale_64chains", "c3_n1M_5loc_5sc
                     "n_loc_terms": wl.n_loc,
                     "xtwx_dense_equiv_tflops": 2.0 * wl.n * pdim * pdim * C / ms_x * 1e3 / 1e12,
                     "xtwx_banded_gflops": 2.0 * wl.n * 10 * C / ms_x * 1e3 / 1e9})
+    if name.startswith("c3") or name.startswith("c2"):
+        ms_w = timeit(lambda: m.pointwise(p))
+        rec.update({"pointwise_waic_ms": ms_w, "pointwise_evals_per_s": wl.n * C / ms_w * 1e3})
     out[name] = rec
     print(name, json.dumps(rec))
 json.dump(out, open("gpurun_out/r1_configs.json", "w"), indent=1)
