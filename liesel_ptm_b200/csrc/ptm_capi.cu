@@ -309,7 +309,11 @@ template <typename R, int NB, int MODE, int MAXT>
 int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
   auto kern = ptm::k_main<R, NB, MODE, MAXT>;
   PTM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_main));
+#if PTM_RESPLIT
+  kern<<<pl.grid, 32 * ((T + pl.NU + 3) / 4 * 4), pl.smem_main, st>>>(a);
+#else
   kern<<<pl.grid, 32 * (T + pl.NU), pl.smem_main, st>>>(a);
+#endif
   PTM_CUDA(cudaGetLastError());
   return PTM_OK;
 }
@@ -319,7 +323,11 @@ int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t
 template <typename R, int NB, int MODE>
 int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
   // registers are granted per 4 warps: <= 16 warps -> 128/thread, 20 -> 96, 24 -> 80, 32 -> 64
+#if PTM_RESPLIT
+  const int threads = 32 * ((T + pl.NU + 3) / 4 * 4);
+#else
   const int threads = 32 * (T + pl.NU);
+#endif
   if (threads <= 512) return launch_main_t<R, NB, MODE, 512>(a, pl, T, st);
   if (threads <= 640) return launch_main_t<R, NB, MODE, 640>(a, pl, T, st);
   if (threads <= 768) return launch_main_t<R, NB, MODE, 768>(a, pl, T, st);

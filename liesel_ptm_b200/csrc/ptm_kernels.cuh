@@ -65,6 +65,22 @@ struct MainArgs {
 #define PTM_TERM_UNROLL 2  // terms of one predictor evaluated per unrolled eval-loop iteration
 #endif
 constexpr int kTermUnroll = PTM_TERM_UNROLL;
+// Experiment (off by default): eval warps first, registers re-split between the roles with
+// setmaxnreg (eval PTM_RESPLIT_EVAL, others PTM_RESPLIT_TERM) and two observations per
+// eval-loop iteration.  Needs NU % 4 == 0 and a CTA padded to whole warpgroups.
+#ifndef PTM_RESPLIT
+#define PTM_RESPLIT 0
+#endif
+#ifndef PTM_RESPLIT_EVAL
+#define PTM_RESPLIT_EVAL 128
+#endif
+#ifndef PTM_RESPLIT_TERM
+#define PTM_RESPLIT_TERM 72
+#endif
+#ifndef PTM_EVAL_UNROLL
+#define PTM_EVAL_UNROLL 1
+#endif
+constexpr int kEvalUnroll = PTM_EVAL_UNROLL;
 
 // CTA-wide barrier issued from role-specific code (whole warps take one role).
 __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
@@ -226,20 +242,29 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                    // written after the last tile only: they reuse the dl/deta tiles
   int* s_j = reinterpret_cast<int*>(s_kn + T * 4 * kKnotStride);  // [T][3][To] (+ pad)
 
+#if PTM_RESPLIT
+  const bool is_term = warp >= NU && warp < NU + T;
+  const bool is_pad = warp >= NU + T;
+  const int uw = warp;       // eval warp index when warp < NU
+  const int tq = warp - NU;  // term slot
+#else
   const bool is_term = warp < T;
+  constexpr bool is_pad = false;
   const int uw = warp - T;  // eval warp index when !is_term
+  const int tq = warp;      // term slot
+#endif
 
   // term-warp constants
   int t_nb = 0, t_pred = 0;
   R t_invdk = R(0);
   const R* t_x = nullptr;
-  const int term = is_term ? a.order[warp] : 0;  // staging / hand-off are indexed by warp (= q)
+  const int term = is_term ? a.order[tq] : 0;  // staging / hand-off are indexed by warp (= q)
   if (is_term) {
     t_nb = a.nb[term];
     t_pred = a.pred[term];
     t_invdk = a.inv_dk[term];
     t_x = a.X + (long long)term * a.n;
-    R* kn = s_kn + warp * 4 * kKnotStride;
+    R* kn = s_kn + tq * 4 * kKnotStride;
     const R* gk = a.knots + term * kKnotStride;
     for (int i = lane; i < t_nb + 4; i += 32) {
       kn[i] = gk[i];
@@ -251,6 +276,12 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   const TrafoScal<R> ts = a.ts;
   __syncthreads();
 
+  // The roles run their own work-item loops (no code is shared after the role split, so a
+  // register re-split between the roles stays possible); they meet at the CTA barriers.
+  if (is_term) {
+#if PTM_RESPLIT
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PTM_RESPLIT_TERM));
+#endif
   for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int cg = item / a.M;
     const int mchunk = item - cg * a.M;
@@ -263,7 +294,6 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
     if (chain >= a.C) chain = a.C - 1;
     double* pout = a.partial + (long long)item * a.NSLOT * 32;
 
-    if (is_term) {
       // =========================== term warp ========================================
       // this term's spline coefficients of the 32 chains -> shared [coef][lane]
       for (int j = 0; j < t_nb; ++j)
@@ -281,13 +311,13 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) dacc[j] = 0.0;
       }
-      const R* kn = s_kn + warp * 4 * kKnotStride;
+      const R* kn = s_kn + tq * 4 * kKnotStride;
       const int goff32 = a.goff[term] * 32;
       auto stage = [&](int tile) {
         const long long base = o_begin + (long long)tile * To;
         const int slot = tile % 3;
-        R* bst = s_b + ((warp * 3 + slot) * To) * 4;
-        int* jst = s_j + (warp * 3 + slot) * To;
+        R* bst = s_b + ((tq * 3 + slot) * To) * 4;
+        int* jst = s_j + (tq * 3 + slot) * To;
         for (int o = lane; o < To; o += 32) {
           const long long gi = base + o;
           if (gi < o_end) {
@@ -309,8 +339,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             const int tile = s - 1;
             const long long base = o_begin + (long long)tile * To;
             const int slot = tile % 3;
-            const R* bp = s_b + ((warp * 3 + slot) * To) * 4;
-            const int* jp = s_j + (warp * 3 + slot) * To;
+            const R* bp = s_b + ((tq * 3 + slot) * To) * 4;
+            const int* jp = s_j + (tq * 3 + slot) * To;
             const R* hp = s_g + (((tile & 1) * To) * 2 + t_pred) * 32 + lane;
             const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
 #pragma unroll 2
@@ -338,7 +368,47 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             pout[(kRegSlots + NGV + a.goff[term] + j) * 32 + lane] = v;
           }
       }
-    } else {
+    cta_bar();
+    cta_bar();
+  }
+  } else if (is_pad) {
+#if PTM_RESPLIT
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PTM_RESPLIT_TERM));
+#endif
+  for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const int cg = item / a.M;
+    const int mchunk = item - cg * a.M;
+    const long long o_begin = a.obs_begin + (long long)mchunk * a.chunk_len;
+    long long o_end = o_begin + a.chunk_len;
+    if (o_end > a.obs_end) o_end = a.obs_end;
+    const long long len = o_end > o_begin ? o_end - o_begin : 0;
+    const int ntiles = (int)((len + To - 1) / To);
+    int chain = cg * 32 + lane;
+    if (chain >= a.C) chain = a.C - 1;
+    double* pout = a.partial + (long long)item * a.NSLOT * 32;
+
+    cta_bar();
+    for (int s = 0; s <= ntiles; ++s) cta_bar();
+    cta_bar();
+    cta_bar();
+    (void)pout; (void)chain;
+  }
+  } else {
+#if PTM_RESPLIT
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PTM_RESPLIT_EVAL));
+#endif
+  for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const int cg = item / a.M;
+    const int mchunk = item - cg * a.M;
+    const long long o_begin = a.obs_begin + (long long)mchunk * a.chunk_len;
+    long long o_end = o_begin + a.chunk_len;
+    if (o_end > a.obs_end) o_end = a.obs_end;
+    const long long len = o_end > o_begin ? o_end - o_begin : 0;
+    const int ntiles = (int)((len + To - 1) / To);
+    int chain = cg * 32 + lane;
+    if (chain >= a.C) chain = a.C - 1;
+    double* pout = a.partial + (long long)item * a.NSLOT * 32;
+
       // =========================== eval warp ========================================
       for (int s = uw; s < NCC; s += NU) s_cc[s * 32 + lane] = a.cc[(long long)s * a.C + chain];
       R* gvp = s_gv + (uw * NGV) * 32 + lane;
@@ -369,7 +439,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
           const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
           // (interleaving two observations per warp by unrolling was measured slower: the
           //  extra live values push the eval warps over their 96-register budget)
-#pragma unroll 1
+#pragma unroll kEvalUnroll
           for (int o = uw; o < cnt; o += NU) {
             const R yv = a.y[base + o];
             // ---- additive predictors: banded gather from the shared coefficient table
@@ -549,25 +619,26 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
       rp[SL_GDL * 32] = a_gdl;
       rp[SL_GVR * 32] = a_gvr;
       rp[SL_GDR * 32] = a_gdr;
-    }
     // ---- item epilogue: cross-warp sums of the eval-warp partials to HBM ------------
-    __syncthreads();
+    cta_bar();
     if constexpr (!POINT) {
+      const int et = uw * 32 + lane, ne = NU * 32;
       const int nreg = GRAD ? kRegSlots : kLogpSlots;
-      for (int idx = tid; idx < nreg * 32; idx += blockDim.x) {
+      for (int idx = et; idx < nreg * 32; idx += ne) {
         double v = 0.0;
         for (int w = 0; w < NU; ++w) v += s_red[w * kRegSlots * 32 + idx];
         pout[idx] = v;
       }
       if (GRAD) {
-        for (int idx = tid; idx < NGV * 32; idx += blockDim.x) {
+        for (int idx = et; idx < NGV * 32; idx += ne) {
           double v = 0.0;
           for (int w = 0; w < NU; ++w) v += (double)s_gv[w * NGV * 32 + idx];
           pout[kRegSlots * 32 + idx] = v;
         }
       }
     }
-    __syncthreads();
+    cta_bar();
+  }
   }
 }
 
