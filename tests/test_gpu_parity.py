@@ -277,6 +277,18 @@ def test_shapes_no_terms_and_mixed_nbases():
         assert rel_err(g, g_ref) < TOL64, kw
 
 
+@pytest.mark.parametrize("n_loc,n_scale", [(7, 6), (10, 10), (12, 12)])
+def test_many_terms(n_loc, n_scale):
+    """13 .. 24 smooth terms: the CTA grows to 24 / 28 warps (768- and 1024-thread
+    instantiations of the sweep, 80 / 64 registers); config 5 has 20 terms."""
+    case = build_case(n=1500, C=33, n_loc=n_loc, n_scale=n_scale, nbases=10)
+    lp, g, lp_only = _eval(case)
+    lp_ref, g_ref = oracle_eval(case)
+    assert rel_err(lp, lp_ref) < TOL64
+    assert rel_err(lp_only, lp_ref) < TOL64
+    assert rel_err(g, g_ref) < TOL64
+
+
 def test_obs_shards_add_up():
     """set_shard: likelihood partials over disjoint observation ranges add up to the full
     evaluation (priors on one shard only) -- the N>1 observation-sharded path."""
