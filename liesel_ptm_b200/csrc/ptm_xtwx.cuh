@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(640, 1) k_xtwx(const XtwxArgs<R> a) {
               }
               // w = 1 / clip(sigma, sqrt(eps))^2 with sigma = exp(eta_sigma)
               const R sd = fast_exp(es);
-              const R sdc = sd > eps ? sd : eps;
+              const R sdc = sd < eps ? eps : sd;  // NaN propagates like jnp.clip
               wgt = fast_rcp(sdc * sdc);
             }
             wb[o * 32] = wgt;
@@ -252,7 +252,7 @@ __global__ void k_xtwx_post(const XtwxArgs<R> a, int term, int boff, R* __restri
   if (!precision) return;
   const D eps = (D)sqrt_eps<R>();
   const D tau = (D)a.params[(long long)c * a.P + a.tau_off + t];
-  const D tc_ = tau > eps ? tau : eps;
+  const D tc_ = tau < eps ? eps : tau;  // NaN propagates like jnp.clip
   const D is2 = 1.0 / (tc_ * tc_);
   const R* Kt = a.Kall + a.koff[t];
   if (a.add_penalty)

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(1024, 1) k_xtwx_tc(const XtwxTcArgs g) {
             es += f;
           }
           // w = 1/max(sigma, sqrt(eps))^2 = exp(-2 max(eta_sigma, log sqrt(eps)))
-          const float ec = es > kLogSqrtEpsF ? es : kLogSqrtEpsF;
+          const float ec = es < kLogSqrtEpsF ? kLogSqrtEpsF : es;  // NaN propagates like jnp.clip
           float wgt;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(wgt) : "f"(ec * -2.8853900817779268f));
           if (base + o >= o_end) wgt = 0.f;
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(1024, 1) k_xtwx_tc2(const XtwxTc2Args h) {
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const float es = gamma0 + (__uint_as_float(v[k4]) + (__uint_as_float(v1[k4]) + __uint_as_float(v2[k4])));
-          const float ec = es > kLogSqrtEpsF ? es : kLogSqrtEpsF;
+          const float ec = es < kLogSqrtEpsF ? kLogSqrtEpsF : es;  // NaN propagates like jnp.clip
           float wgt;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(wgt) : "f"(ec * -2.8853900817779268f));
           if (base + og * 4 + k4 >= o_end) wgt = 0.f;

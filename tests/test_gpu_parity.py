@@ -112,6 +112,37 @@ def test_pointwise_lppd_and_waic(n, C):
     assert rel_err(lp, ll.sum(axis=1)) < 1e-12
 
 
+def test_pointwise_on_new_data():
+    """Held-out evaluation (EvaluatePTM.lppdi(newdata), model/evaluate.py:106-133): a second
+    handle over the new observations with the TRAINING knots / Z / K, same samples."""
+    import liesel_ptm_b200 as lp_
+
+    train = build_case(n=400, n_loc=2, n_scale=1, nbases=12, C=6)
+    rng = np.random.default_rng(5)
+    n_new = 131
+    y_new = rng.normal(size=n_new)
+    X_new = rng.uniform(-1.9, 1.9, size=(3, n_new))
+    model = lp_.LocScalePTM(y_new, train.model.knots, to_float32=False, device="cuda:0")
+    oterms = []
+    for t, (tm, pred) in enumerate(train.model.terms):
+        b = lp_.Basis(x=X_new[t], xname=f"new{t}", knots=tm.basis.knots, Z=tm.basis.Z, penalty=tm.basis.penalty,
+                      nbases=tm.basis.nbases)
+        new_term = lp_.term.f_ig(b, fname=f"h{t}")
+        if pred == train.model.terms[0][1]:
+            model.loc += new_term
+        else:
+            model.scale += new_term
+        ot = train.omodel.terms[t]
+        oterms.append(o.term_from_reparam(X_new[t], ot.knots, ot.Z, ot.K, ot.rank, ot.predictor))
+    model.build()
+    om = o.PTMModel(y_new, oterms, nparam=20)
+    om.spline, om.Zd = train.omodel.spline, train.omodel.Zd
+    _, lppd_ref, p_ref = _oracle_pointwise(om, train.state, 6)
+    lppd, pwaic = model.pointwise(torch.from_numpy(train.params).cuda())
+    assert rel_err(lppd.cpu().numpy(), lppd_ref) < 1e-12
+    assert np.allclose(pwaic.cpu().numpy(), p_ref, rtol=1e-9, atol=1e-12)
+
+
 def test_pointwise_nan_response_and_f32():
     case = build_case(n=300, n_loc=1, n_scale=1, nbases=12, C=9, dtype=np.float32)
     om, st = _f64_oracle_of(case)
@@ -352,6 +383,32 @@ def test_xtwx_f32_tensor_core_several_sweeps():
         _, ref_P, ref_L = om.loc_precision(st, t)
         assert rel_err(Ps[t].cpu().numpy(), ref_P) < 2e-5
         assert rel_err(Ls[t].cpu().numpy(), ref_L) < 2e-4
+
+
+def test_xtwx_f32_tensor_core_clipped_and_nan_weights(monkeypatch):
+    """sigma below sqrt(eps) is clipped (w = 1/eps, iwls_proposals.py:76-79); a NaN chain
+    state gives NaN for that chain only, no hang."""
+    case = build_case(n=2500, n_loc=1, n_scale=1, nbases=12, nparam=20, C=5, dtype=np.float32)
+    om, st = _f64_oracle_of(case)  # oracle on the unmodified (finite) states
+    _, ref_P, _ = om.loc_precision(st, 0)
+    params = case.params.copy()
+    params[1, case.layout["gamma0"]] = -12.0   # sigma = exp(-12 + ...) << sqrt(eps_f32)
+    params[3, case.layout["gamma0"]] = np.nan
+    P_tc, _ = case.model.precision(0, torch.from_numpy(params).cuda(), with_chol=False)
+    assert case.model.last_xtwx_route().startswith("tcgen05")
+    monkeypatch.setenv("PTM_XTWX_TC", "0")
+    P_b, _ = case.model.precision(0, torch.from_numpy(params).cuda(), with_chol=False)
+    P_tc, P_b = P_tc.cpu().numpy(), P_b.cpu().numpy()
+    assert np.isnan(P_tc[3]).all() and np.isnan(P_b[3]).all()
+    assert np.isfinite(P_tc[[0, 1, 2, 4]]).all()
+    assert rel_err(P_tc[1], P_b[1]) < 2e-5  # the clipped chain: both routes agree
+    # clipped weights are the constant 1/eps: X'WX = X'X / eps for that chain
+    eps32 = float(np.finfo(np.float32).eps)
+    D = om.terms[0].design
+    penal = P_b[1] - (D.T @ D) / eps32
+    assert rel_err(P_b[1], (D.T @ D) / eps32 + penal) < 1e-6 and np.abs(penal).max() < 1e-3 * np.abs(P_b[1]).max()
+    for c in (0, 2, 4):
+        assert rel_err(P_tc[c], ref_P[c]) < 2e-5
 
 
 @pytest.mark.parametrize("n,C", [(37, 3), (5000, 130), (20011, 257)])

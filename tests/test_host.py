@@ -153,6 +153,17 @@ def test_capi_argument_validation_without_gpu():
     assert b"not inside the range of interior knots" in lib.ptm_last_error()
     assert lib.ptm_num_params(None) == -1
     assert lib.ptm_workspace_bytes(None, 4) == 0
+    assert lib.ptm_pointwise_workspace_bytes(None, 4) == 0
+    # every per-call entry point rejects a null problem / null arrays with PTM_ERR_NULL
+    # before touching the device
+    for sfx in ("f64", "f32"):
+        assert getattr(lib, f"ptm_logp_{sfx}")(None, None, 1, None, None, 0, None) == 1
+        assert getattr(lib, f"ptm_logp_grad_{sfx}")(None, None, 1, None, None, None, 0, None) == 1
+        assert getattr(lib, f"ptm_pointwise_{sfx}")(None, None, 1, None, None, None, 0, None) == 1
+        assert getattr(lib, f"ptm_loc_precision_all_{sfx}")(None, None, 1, None, None, None, 0, None) == 1
+        assert getattr(lib, f"ptm_intercept_stats_{sfx}")(None, None, 1, None, None, 0, None) == 1
+        assert getattr(lib, f"ptm_xtwx_{sfx}")(None, 0, None, 1, None, None, 0, None) == 1
+    assert lib.ptm_last_xtwx_route() in (0, 1, 2)
 
 
 def test_bench_workload_regions():
