@@ -385,6 +385,22 @@ def test_xtwx_f32_tensor_core_several_sweeps():
         assert rel_err(Ls[t].cpu().numpy(), ref_L) < 2e-4
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_xtwx_observation_shards_add_up(dtype):
+    """X'WX is additive over observation shards (the IWLS all-reduce of SURVEY.md 8e), on the
+    banded route (float64) and the tensor-core route (float32)."""
+    case = build_case(n=3000, n_loc=2, n_scale=1, nbases=12, C=37, dtype=dtype)
+    params = torch.from_numpy(case.params).cuda()
+    full = case.model.xtwx(1, params).cpu().numpy().astype(np.float64)
+    acc = np.zeros_like(full)
+    for lo, hi in ((0, 1), (1, 1777), (1777, 3000)):
+        case.model.set_shard(lo, hi, add_priors=False)
+        acc += case.model.xtwx(1, params).cpu().numpy().astype(np.float64)
+    case.model.set_shard(0, 3000, add_priors=True)
+    assert case.model.last_xtwx_route() == ("banded" if dtype == np.float64 else "tcgen05")
+    assert rel_err(acc, full) < (1e-12 if dtype == np.float64 else 2e-6)
+
+
 def test_xtwx_f32_tensor_core_clipped_and_nan_weights(monkeypatch):
     """sigma below sqrt(eps) is clipped (w = 1/eps, iwls_proposals.py:76-79); a NaN chain
     state gives NaN for that chain only, no hang."""
@@ -411,7 +427,7 @@ def test_xtwx_f32_tensor_core_clipped_and_nan_weights(monkeypatch):
         assert rel_err(P_tc[c], ref_P[c]) < 2e-5
 
 
-@pytest.mark.parametrize("n,C", [(37, 3), (5000, 130), (20011, 257)])
+@pytest.mark.parametrize("n,C", [(5, 2), (37, 3), (5000, 130), (20011, 257)])
 def test_xtwx_f32_tensor_core_and_banded_routes(n, C, monkeypatch):
     """float32 information of the location terms: the tcgen05 route (3xTF32, f32 TMEM
     accumulators promoted to double) and the banded CUDA-core route against the f64 oracle
