@@ -414,15 +414,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
       R* gvp = s_gv + (uw * NGV) * 32 + lane;
       if (GRAD)
         for (int s = 0; s < NGV; ++s) gvp[s * 32] = R(0);
-      ChainBoundary<R> cb;
-      make_boundary(ts, a.cc[(long long)(KK * 5 + 0) * a.C + chain],
-                    a.cc[(long long)(KK * 5 + 1) * a.C + chain],
-                    a.cc[(long long)(KK * 5 + 2) * a.C + chain],
-                    a.cc[(long long)(KK * 5 + 3) * a.C + chain], cb);
       const R beta0 = a.cc[(long long)(KK * 5 + 4) * a.C + chain];
       const R gamma0 = a.cc[(long long)(KK * 5 + 5) * a.C + chain];
-      const R cLe = cL_of(ts, ts.min_eps);
-      const R cRe = cR_of(ts, ts.max_eps);
       // scalar sums in double for both kernels (a handful of adds per observation)
       double a_z2 = 0, a_ls = 0, a_gb0 = 0, a_gg0 = 0;
       double a_gvl = 0, a_gdl = 0, a_gvr = 0, a_gdr = 0;
@@ -487,6 +480,11 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             core_eval(ts, cp[0], cp[32], cp[64], cp[96], cp[128], ev);
             R z = ev.z, d = ev.d, dzdr = ev.d, dddr = ev.d2;
             if (!core) {
+              // boundary constants of the chain: rebuilt from the shared table on the rare
+              // non-core path instead of living in 12 registers across the loop
+              ChainBoundary<R> cb;
+              make_boundary(ts, s_cc[(KK * 5 + 0) * 32 + lane], s_cc[(KK * 5 + 1) * 32 + lane],
+                            s_cc[(KK * 5 + 2) * 32 + lane], s_cc[(KK * 5 + 3) * 32 + lane], cb);
               if (code == 1) {
                 const R poly = r * ts.a - R(0.5) * r * r;
                 z = (ts.inv_w * poly + cb.dL * (r - poly * ts.inv_w)) + cb.constL;
@@ -591,10 +589,10 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                   a_gdr += (double)fma(lz, cR_of(ts, r), ld * (R(1) - q));
                 } else if (code == 0) {
                   a_gvl += (double)lz;
-                  a_gdl += (double)(lz * cLe);
+                  a_gdl += (double)(lz * cL_of(ts, ts.min_eps));
                 } else {
                   a_gvr += (double)lz;
-                  a_gdr += (double)(lz * cRe);
+                  a_gdr += (double)(lz * cR_of(ts, ts.max_eps));
                 }
               }
             }
