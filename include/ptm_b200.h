@@ -28,6 +28,12 @@
  *   ptm_xtwx_* / ptm_loc_precision_*  GaussianLocCholInfo.working_weights /
  *                                  precision / chol_info: iwls_proposals.py:55-89
  *                                  (scale terms, W == 2: 118-144).
+ *   ptm_loc_precision_all_*        the same for every location term of a sampler sweep
+ *                                  (the weights depend only on the scale predictor).
+ *   ptm_intercept_stats_*          LocationIntercept / LogScaleIntercept
+ *                                  .compute_intercept: predictor.py:80-100,126-130.
+ *   ptm_pointwise_*                EvaluatePTM._lppdi / .lppdi / .waic:
+ *                                  model/evaluate.py:106-133,177-236.
  *
  * Parameter vector of ONE chain (row of the [C, P] row-major `params` array, the
  * layout JAX hands over after ravel_pytree):
