@@ -34,7 +34,10 @@ from .model import LocScalePTM
 
 def _solve(chol: torch.Tensor, rhs: torch.Tensor) -> torch.Tensor:
     """P^-1 rhs from the lower Cholesky factor of P (iwls_utils.solve)."""
-    return torch.cholesky_solve(rhs.unsqueeze(-1), chol).squeeze(-1)
+    # two triangular solves (cuBLAS trsm, capturable in a CUDA graph; cholesky_solve goes
+    # through MAGMA, which allocates)
+    y = torch.linalg.solve_triangular(chol, rhs.unsqueeze(-1), upper=False)
+    return torch.linalg.solve_triangular(chol.transpose(-1, -2), y, upper=True).squeeze(-1)
 
 
 def _mvn_sample(gen, mean: torch.Tensor, chol_prec: torch.Tensor) -> torch.Tensor:
@@ -189,14 +192,15 @@ def hmc_transition(model: LocScalePTM, params: torch.Tensor, lo: int, width: int
 
 def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: int, seed: int = 0,
                iwls_step: float = 1.0, dz_step: float = 0.05, target_accept: float = 0.8, n_leapfrog: int = 8,
-               reuse_information: bool = True):
+               reuse_information: bool = True, use_graph: bool = True):
     """Sweep per iteration: an IWLS-MH transition per smooth term, an HMC transition on
     delta_z.  Warm-up adapts the per-chain step sizes (Robbins-Monro on the acceptance
     probability) and, at 2/8 ... 7/8 of its length, the dense metric of delta_z from the
     pooled across-chain covariance of the draws since the previous update.  With ``reuse_information`` the information matrices are
     evaluated once per sweep for all location terms (``precision_all``; they only change
     when a scale term or an intercept moves) and once per run for the scale terms (W == 2,
-    tau fixed) instead of twice per transition -- same transitions, fewer sweeps.
+    tau fixed) instead of twice per transition -- same transitions, fewer sweeps.  With
+    ``use_graph`` the posterior epoch replays one captured CUDA graph per iteration.
     Returns (draws [draws, C, P] on the host, info dict with timings and acceptance)."""
     gen = torch.Generator(device=params0.device)
     gen.manual_seed(seed)
@@ -213,53 +217,109 @@ def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: in
     istep = torch.full((max(T, 1), C), float(iwls_step), dtype=params.dtype, device=params.device)
     cache = None
     out = torch.empty((draws, C, params.shape[1]), dtype=params.dtype, device=params.device)
-    acc_iwls, acc_dz, n_it = 0.0, 0.0, 0
     scale_chol = {}
     if reuse_information:
         for t in range(T):
             if not is_loc[t]:
                 scale_chol[t] = model.precision(t, params)[1].clone()
     window = []
-    t0 = time.perf_counter()
-    for it in range(warmup + draws):
-        if it == warmup:
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
+
+    def sweep(params, cache, it_warm, gen=gen):
+        """One iteration at the current step sizes / metric; returns the new state and the
+        acceptance indicators of the IWLS blocks (mean over blocks) and of the HMC block."""
+        nonlocal istep, step, adapt_t
         loc_chol = None
         if reuse_information and any(is_loc):
             loc_chol = [c.clone() for c in model.precision_all(params)[1]]
         k_loc = 0
+        acc_i = torch.zeros((), dtype=torch.float64, device=params.device)
         for t in range(T):
             chol = None
             if reuse_information:
                 chol = loc_chol[k_loc] if is_loc[t] else scale_chol[t]
             k_loc += 1 if is_loc[t] else 0
             params, cache, info = iwls_transition(model, params, t, istep[t], gen, cache, chol=chol)
-            if it < warmup:
+            if it_warm is not None:
                 a = torch.exp(torch.clamp(info.log_alpha, max=0.0))
-                istep[t] = torch.clamp(istep[t] * torch.exp((a - 0.8) * (10.0 / (it + 10.0))), 1e-3, 2.0)
+                istep[t] = torch.clamp(istep[t] * torch.exp((a - 0.8) * (10.0 / (it_warm + 10.0))), 1e-3, 2.0)
             else:
-                acc_iwls += info.accepted.double().mean().item() / T
+                acc_i = acc_i + info.accepted.double().mean() / T
         params, cache, info = hmc_transition(model, params, dz_lo, dz_w, step, n_leapfrog, metric_chol, gen, cache)
-        if it < warmup:
-            a = torch.exp(torch.clamp(info.log_alpha, max=0.0))
-            step = step * torch.exp((a - target_accept) * (10.0 / (adapt_t + 10.0)))
-            adapt_t += 1
-            if it >= warmup // 8:
-                window.append(params[:, dz_lo: dz_lo + dz_w].clone())
-            if window and (it + 1) in metric_updates and C * len(window) >= 10 * dz_w:
-                cov = torch.cov(torch.cat(window, 0).T)
-                cov = cov + 1e-6 * torch.diagonal(cov).mean() * torch.eye(dz_w, dtype=cov.dtype, device=cov.device)
-                metric_chol = torch.linalg.cholesky(cov)
-                step = torch.full_like(step, 0.5 * dz_w ** -0.25)  # whitened scale; re-adapt from there
-                adapt_t = 0
-                window = []
+        return params, cache, info, acc_i
+
+    # ---- warm-up (eager: host-side adaptation logic) -----------------------------------
+    for it in range(warmup):
+        params, cache, info, _ = sweep(params, cache, it)
+        a = torch.exp(torch.clamp(info.log_alpha, max=0.0))
+        step = step * torch.exp((a - target_accept) * (10.0 / (adapt_t + 10.0)))
+        adapt_t += 1
+        if it >= warmup // 8:
+            window.append(params[:, dz_lo: dz_lo + dz_w].clone())
+        if window and (it + 1) in metric_updates and C * len(window) >= 10 * dz_w:
+            cov = torch.cov(torch.cat(window, 0).T)
+            cov = cov + 1e-6 * torch.diagonal(cov).mean() * torch.eye(dz_w, dtype=cov.dtype, device=cov.device)
+            metric_chol = torch.linalg.cholesky(cov)
+            step = torch.full_like(step, 0.5 * dz_w ** -0.25)  # whitened scale; re-adapt from there
+            adapt_t = 0
+            window = []
+    if cache is None:
+        lp0, g0 = model.log_prob_and_grad(params)
+        cache = (lp0.clone(), g0.clone())
+
+    # ---- posterior epoch: the whole sweep is one CUDA graph (fixed step sizes and metric;
+    #      the library enqueues on the capturing stream, no host synchronisation inside) ----
+    acc_i_sum = torch.zeros((), dtype=torch.float64, device=params.device)
+    acc_d_sum = torch.zeros((), dtype=torch.float64, device=params.device)
+    graph, graph_error = None, None
+    if use_graph and draws > 0:
+        try:
+            g_params, g_logp, g_grad = params.clone(), cache[0].clone(), cache[1].clone()
+            # the graph owns its generator: a generator registered with a graph is only
+            # usable inside captures afterwards
+            gen_g = torch.Generator(device=params0.device)
+            gen_g.manual_seed(seed + 1)
+            side = torch.cuda.Stream(device=params.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                sweep(g_params, (g_logp, g_grad), None)  # allocate workspaces outside the capture
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            graph.register_generator_state(gen_g)
+            with torch.cuda.graph(graph, stream=side):
+                p1, c1, info1, ai = sweep(g_params, (g_logp, g_grad), None, gen_g)
+                g_params.copy_(p1)
+                g_logp.copy_(c1[0])
+                g_grad.copy_(c1[1])
+                acc_i_sum += ai
+                acc_d_sum += info1.accepted.double().mean()
+            acc_i_sum.zero_()
+            acc_d_sum.zero_()
+            g_params.copy_(params)
+            g_logp.copy_(cache[0])
+            g_grad.copy_(cache[1])
+        except Exception as exc:  # capture not possible (old torch, unsupported op): eager sweeps
+            graph = None
+            graph_error = repr(exc)
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for it in range(draws):
+        if graph is not None:
+            graph.replay()
+            out[it].copy_(g_params)
         else:
-            acc_dz += info.accepted.double().mean().item()
-            out[it - warmup] = params
-            n_it += 1
+            params, cache, info, ai = sweep(params, cache, None)
+            acc_i_sum += ai
+            acc_d_sum += info.accepted.double().mean()
+            out[it] = params
     torch.cuda.synchronize()
     t_post = time.perf_counter() - t0
-    return out.cpu().numpy(), {"posterior_seconds": t_post, "accept_iwls": acc_iwls / max(n_it, 1),
-                               "accept_dz": acc_dz / max(n_it, 1), "dz_step_median": float(step.median()),
-                               "n_leapfrog": n_leapfrog}
+    n_it = max(draws, 1)
+    return out.cpu().numpy(), {"posterior_seconds": t_post, "accept_iwls": float(acc_i_sum) / n_it,
+                               "accept_dz": float(acc_d_sum) / n_it, "dz_step_median": float(step.median()),
+                               "n_leapfrog": n_leapfrog, "cuda_graph": graph is not None,
+                               "cuda_graph_error": graph_error}

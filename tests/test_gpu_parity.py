@@ -595,8 +595,9 @@ def test_sampler_runs_and_mixes():
 
     case = build_case(n=200, n_loc=1, n_scale=0, nbases=10, C=16)
     params = torch.from_numpy(case.params).cuda()
-    draws, info = mcmc.run_chains(case.model, params, warmup=60, draws=120, seed=1)
-    assert draws.shape == (120, 16, case.P) and np.isfinite(draws).all()
+    draws, info = mcmc.run_chains(case.model, params, warmup=60, draws=200, seed=1)
+    assert draws.shape == (200, 16, case.P) and np.isfinite(draws).all()
+    assert info["cuda_graph"], info.get("cuda_graph_error")  # the posterior epoch replays one CUDA graph
     assert 0.05 < info["accept_iwls"] <= 1.0 and 0.05 < info["accept_dz"] <= 1.0
     lo = case.layout["beta"][0]
     ess = mcmc.effective_sample_size(draws[:, :, lo].T)
@@ -605,3 +606,9 @@ def test_sampler_runs_and_mixes():
     draws2, _ = mcmc.run_chains(case.model, params, warmup=10, draws=10, seed=3, reuse_information=True)
     draws3, _ = mcmc.run_chains(case.model, params, warmup=10, draws=10, seed=3, reuse_information=False)
     assert np.allclose(draws2, draws3, rtol=1e-9, atol=1e-11)
+    # ... and neither does replaying the sweep as a CUDA graph instead of eager launches, given
+    # the same random numbers: eager run with the graph's generator seed for the posterior epoch
+    draws4, info4 = mcmc.run_chains(case.model, params, warmup=0, draws=5, seed=3, use_graph=True)
+    draws5, info5 = mcmc.run_chains(case.model, params, warmup=0, draws=5, seed=4, use_graph=False)
+    assert info4["cuda_graph"] and not info5["cuda_graph"]
+    assert np.allclose(draws4, draws5, rtol=1e-9, atol=1e-11)

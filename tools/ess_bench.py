@@ -24,7 +24,7 @@ for name, C, warm, draws in [("c1_readme_n100", 64, 300, 500), ("c2_n100k_3loc_1
            "min_ess": float(ess.min()), "median_ess": float(np.median(ess)),
            "min_ess_per_s": float(ess.min() / info["posterior_seconds"]),
            "iterations_per_s": draws / info["posterior_seconds"],
-           "accept_iwls": info["accept_iwls"], "accept_dz": info["accept_dz"], "n_leapfrog": info["n_leapfrog"]}
+           "accept_iwls": info["accept_iwls"], "accept_dz": info["accept_dz"], "n_leapfrog": info["n_leapfrog"], "cuda_graph": info["cuda_graph"]}
     out[name] = rec
     print(name, json.dumps(rec))
 json.dump(out, open("gpurun_out/r1_ess.json", "w"), indent=1)
