@@ -2,6 +2,8 @@
 on logp / gradient (north_star); knot-interval indices bit-exact; basis values
 bit-exact (same IEEE operation order, no FMA contraction)."""
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -612,3 +614,17 @@ def test_sampler_runs_and_mixes():
     draws5, info5 = mcmc.run_chains(case.model, params, warmup=0, draws=5, seed=4, use_graph=False)
     assert info4["cuda_graph"] and not info5["cuda_graph"]
     assert np.allclose(draws4, draws5, rtol=1e-9, atol=1e-11)
+
+
+def test_random_shapes_fuzz():
+    """tools/fuzz_parity.py: 30 seeded random (n, C, terms, nbases, dtype) models -- logp,
+    gradient, precision and pointwise records against the oracle."""
+    import subprocess
+    import sys as _sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "30", "7"], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "'ok': 30" in r.stdout
+
