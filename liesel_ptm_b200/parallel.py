@@ -62,3 +62,54 @@ class ObsShardedLogProb:
     def value_and_grad(self, params: torch.Tensor):
         logp, grad = self.model.log_prob_and_grad(params)
         return allreduce_logp_grad(logp, grad, self.group)
+
+    def xtwx(self, term_index: int, params: torch.Tensor) -> torch.Tensor:
+        """X'WX of a term over ALL observations: local sweep + one all-reduce of [C, p, p]."""
+        return allreduce_sum(self.model.xtwx(term_index, params), self.group)
+
+    def precision(self, term_index: int, params: torch.Tensor, penalty: torch.Tensor):
+        """IWLS precision and its Cholesky factor (iwls_proposals.py:82-89, 139-144) for
+        observation-sharded data: the all-reduced X'WX, then penalty / ridge / factorisation
+        (O(p^3) per chain) on every rank."""
+        tau = params[:, self.model.layout["tau"][term_index]]
+        return finish_precision(self.xtwx(term_index, params), penalty, tau)
+
+    def intercepts(self, params: torch.Tensor):
+        """LocationIntercept / LogScaleIntercept.compute_intercept (predictor.py:80-100,
+        126-130) over ALL observations: the three sums are additive over shards."""
+        stats = allreduce_sum(self.model.intercept_stats(params), self.group)
+        return intercepts_from_stats(stats, params, self.model.layout, self.model_n_total())
+
+    def model_n_total(self) -> int:
+        n = torch.tensor([self.bounds[1] - self.bounds[0]], dtype=torch.int64, device=self.model.device)
+        return int(allreduce_sum(n, self.group).item())
+
+
+def allreduce_sum(x: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        x = x.clone()
+        dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
+    return x
+
+
+def finish_precision(xtwx: torch.Tensor, penalty: torch.Tensor, tau: torch.Tensor):
+    """precision = X'WX + K / max(tau, sqrt(eps))^2 + 1e-6 mean(diag) I and its lower
+    Cholesky factor (iwls_proposals.py:82-89), batched over chains."""
+    eps = torch.finfo(xtwx.dtype).eps ** 0.5
+    inv_s2 = 1.0 / torch.clamp(tau, min=eps) ** 2
+    P = xtwx + inv_s2[:, None, None] * penalty.to(xtwx)[None]
+    p = P.shape[-1]
+    ridge = 1e-6 * torch.diagonal(P, dim1=-2, dim2=-1).mean(-1)
+    P = P + ridge[:, None, None] * torch.eye(p, dtype=P.dtype, device=P.device)[None]
+    return P, torch.linalg.cholesky(P)
+
+
+def intercepts_from_stats(stats: torch.Tensor, params: torch.Tensor, layout: dict, n_total: int):
+    """(beta0_new, gamma0_new) from the all-reduced sums [C, 3] = (sum exp(-eta_sigma), sum r,
+    sum r^2); same formulas as LocScalePTM.compute_intercepts."""
+    n = float(n_total)
+    m_e, m_r, m_r2 = stats[:, 0] / n, stats[:, 1] / n, stats[:, 2] / n
+    beta0 = params[:, layout["beta0"]] + m_r / m_e
+    gamma0 = params[:, layout["gamma0"]] + 0.5 * torch.log(m_r2 - m_r * m_r)
+    return beta0, gamma0
+

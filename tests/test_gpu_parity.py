@@ -387,6 +387,27 @@ def test_xtwx_f32_tensor_core_several_sweeps():
         assert rel_err(Ls[t].cpu().numpy(), ref_L) < 2e-4
 
 
+def test_obs_sharded_wrapper_single_rank():
+    """parallel.ObsShardedLogProb without a process group (world 1): same numbers as the
+    handle's own entry points -- the N > 1 arithmetic is covered by the gloo test."""
+    from liesel_ptm_b200 import parallel
+
+    case = build_case(n=900, n_loc=2, n_scale=1, nbases=12, C=5)
+    params = torch.from_numpy(case.params).cuda()
+    sh = parallel.ObsShardedLogProb(case.model)
+    lp, g = sh.value_and_grad(params)
+    lp0, g0 = case.model.log_prob_and_grad(params)
+    assert torch.equal(lp, lp0) and torch.equal(g, g0)
+    K = torch.from_numpy(case.omodel.terms[1].K).cuda()
+    P, L = sh.precision(1, params, K)
+    P0, L0 = case.model.precision(1, params)
+    assert rel_err(P.cpu().numpy(), P0.cpu().numpy()) < 1e-13
+    assert rel_err(L.cpu().numpy(), L0.cpu().numpy()) < 1e-11
+    b0, g0_ = sh.intercepts(params)
+    b1, g1 = case.model.compute_intercepts(params)
+    assert torch.allclose(b0, b1, rtol=0, atol=1e-14) and torch.allclose(g0_, g1, rtol=0, atol=1e-14)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_xtwx_observation_shards_add_up(dtype):
     """X'WX is additive over observation shards (the IWLS all-reduce of SURVEY.md 8e), on the

@@ -12,7 +12,10 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-from liesel_ptm_b200.parallel import allreduce_logp_grad, chain_shard, obs_shard, shard_bounds  # noqa: E402
+from liesel_ptm_b200.parallel import (  # noqa: E402
+    allreduce_logp_grad, allreduce_sum, chain_shard, finish_precision, intercepts_from_stats, obs_shard,
+    shard_bounds,
+)
 
 
 def test_shard_bounds_cover_everything():
@@ -49,6 +52,28 @@ def _worker(rank, world, port, q):
     lp_r, g_r = allreduce_logp_grad(torch.from_numpy(lp_s), torch.from_numpy(pack_grad(case, g_s)))
     err_obs = max(np.max(np.abs(lp_r.numpy() - lp_full) / np.abs(lp_full)),
                   np.max(np.abs(g_r.numpy() - g_full)) / np.max(np.abs(g_full)))
+
+    # --- IWLS information of a location term: all-reduce of X'WX, then penalty / ridge /
+    #     Cholesky on every rank (iwls_proposals.py:82-89) -----------------------------------
+    x_s, _, _ = sub.loc_precision(st, 0)
+    x_r = allreduce_sum(torch.from_numpy(x_s))
+    P_r, L_r = finish_precision(x_r, torch.from_numpy(om.terms[0].K), torch.from_numpy(st.tau[:, 0]))
+    _, P_full, L_full = om.loc_precision(st, 0)
+    err_info = max(np.max(np.abs(P_r.numpy() - P_full)) / np.max(np.abs(P_full)),
+                   np.max(np.abs(L_r.numpy() - L_full)) / np.max(np.abs(L_full)))
+
+    # --- intercept pseudo-Gibbs statistics: three sums per chain, additive over shards -----
+    stats = np.zeros((4, 3))
+    for c in range(4):
+        mu, ls = sub.predictors(st, c)
+        r = (sub.y - mu) / np.exp(ls)
+        stats[c] = [np.sum(np.exp(-ls)), np.sum(r), np.sum(r * r)]
+    stats_r = allreduce_sum(torch.from_numpy(stats))
+    params = torch.from_numpy(case.params)
+    b0, g0 = intercepts_from_stats(stats_r, params, case.layout, om.n)
+    ref = np.array([om.compute_intercepts(st, c) for c in range(4)])
+    err_int = max(np.max(np.abs(b0.numpy() - ref[:, 0])), np.max(np.abs(g0.numpy() - ref[:, 1])))
+    err_obs = max(err_obs, err_info, err_int * 1e-1)  # intercepts to 1e-11 absolute
 
     # --- chain-axis sharding: no collective on the data path ---------------------------
     clo, chi = chain_shard(4, world, rank)
