@@ -31,6 +31,18 @@ for k in range(ncase):
         e2 = rel_err(P.cpu().numpy(), rP)
         extra = f" prec {e2:.1e}"
         if e2 > 1e-10: status = "FAIL"
+    if dt == np.float32 and n_loc > 0:
+        # information sweeps: both tensor-core versions against the banded CUDA-core route
+        import os
+        mats = {}
+        for route in ("0", "1", "2"):
+            os.environ["PTM_XTWX_TC"] = route
+            Ps, _ = case.model.precision_all(p)
+            mats[route] = (np.stack([x.cpu().numpy() for x in Ps]).astype(np.float64), case.model.last_xtwx_route())
+        os.environ.pop("PTM_XTWX_TC", None)
+        e4 = max(rel_err(mats["1"][0], mats["0"][0]), rel_err(mats["2"][0], mats["0"][0]))
+        extra += f" info[{mats['1'][1]},{mats['2'][1]}] {e4:.1e}"
+        if not e4 < 5e-5: status = "FAIL"
     if dt == np.float64:
         lppd, pw = case.model.pointwise(p)
         ll = np.stack([case.omodel.loglik_terms(case.state, c)["ll"] for c in range(C)])
