@@ -289,6 +289,13 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   long long M = std::max<long long>(1, target_items / pl.CG);
   const long long max_m = std::max<long long>(1, len / ((long long)pl.To * 16));  // >= 16 tiles per item
   M = std::min(M, max_m);
+  {
+    // whole waves: make CG * M a multiple of the number of CTAs when the cap allows it
+    long long g = pl.CG, h = pr->num_sms;
+    while (h) { const long long t = g % h; g = h; h = t; }
+    const long long unit = pr->num_sms / g;  // smallest M with CG * M % num_sms == 0
+    if (M >= unit) M = M / unit * unit;
+  }
   long long chunk = (len + M - 1) / M;
   chunk = std::max<long long>(pl.To, (chunk + pl.To - 1) / pl.To * pl.To);
   M = std::max<long long>(1, (len + chunk - 1) / chunk);
