@@ -285,7 +285,9 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   while (pl.To > 8 && smem_for(pl.To) > 227 * 1024) pl.To -= 4;
   pl.smem_main = smem_for(pl.To);
   const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
-  const long long target_items = 8LL * pr->num_sms;
+  long long per_sm = 8;  // work items per CTA: amortises the per-item table loads, keeps the tail short
+  if (const char* e = getenv("PTM_ITEMS_PER_SM")) per_sm = std::max(1, atoi(e));  // tuning knob
+  const long long target_items = per_sm * pr->num_sms;
   long long M = std::max<long long>(1, target_items / pl.CG);
   const long long max_m = std::max<long long>(1, len / ((long long)pl.To * 16));  // >= 16 tiles per item
   M = std::min(M, max_m);
