@@ -180,3 +180,16 @@ def test_bench_workload_regions():
     st = state_from_params(om, wl.params, wl.model.param_layout()[0])
     frac = np.bincount(om.spline.region_code(om.loglik_terms(st, 0)["r"]), minlength=5) / wl.n
     assert frac[2] > 0.95 and frac.min() > 1e-4  # mostly core, all five regions exercised
+
+
+def test_generated_dispatch_header_is_current():
+    """liesel_ptm_b200/csrc/ptm_dispatch.cuh is the output of tools/gen_dispatch.py."""
+    import subprocess
+    import sys as _sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([_sys.executable, os.path.join(root, "tools", "gen_dispatch.py")], capture_output=True,
+                         text=True, check=True).stdout
+    with open(os.path.join(root, "liesel_ptm_b200", "csrc", "ptm_dispatch.cuh")) as f:
+        assert f.read() == out
+
