@@ -61,6 +61,9 @@ class LocScalePTM:
         self.knots = np.ascontiguousarray(np.asarray(knots), dtype=self.np_dtype)
         self.nparam = self.knots.shape[0] - 5
         self.trafo_lambda = float(trafo_lambda)
+        # Z_delta is reparameterisation DATA (LAPACK-dependent eigenvector order); a caller
+        # that exports it from the host model assigns it before build()
+        self.trafo_Z = None
         self._loc = _Predictor(_lib.PTM_LOC, "$\\mu$")
         self._scale = _Predictor(_lib.PTM_SCALE, "$\\sigma$")
         self.device = torch.device(device)
@@ -147,7 +150,11 @@ class LocScalePTM:
         d.rank = i32_array([t.penalty_rank for t, _ in self.terms] or [0])
         d.nparam = self.nparam
         d.trafo_knots = arr(self.knots).ctypes.data
-        self.trafo_Z = trafo_reparam(self.nparam, nd)
+        if self.trafo_Z is None:
+            self.trafo_Z = trafo_reparam(self.nparam, nd)
+        self.trafo_Z = np.ascontiguousarray(np.asarray(self.trafo_Z, dtype=nd))
+        if self.trafo_Z.shape != (self.nparam, self.nparam - 1):
+            raise ValueError(f"trafo_Z must have shape ({self.nparam}, {self.nparam - 1})")
         d.trafo_Z = arr(self.trafo_Z).ctypes.data
         d.trafo_lambda = self.trafo_lambda
         self.grid = approx_grid(self.knots)

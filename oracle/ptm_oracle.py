@@ -6,15 +6,23 @@ in BASELINE.json.  It is the *checker*: only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
 reference`` legs may import it.  Nothing under ``liesel_ptm_b200/`` imports it.
 
-PARITY UNPINNED (value level): the reference cannot be imported in this image
-(needs Python 3.13 + jax 0.8.2 + liesel 0.4.3 + tfp-nightly, none installed,
-no network) and its own tests hold no golden numbers for logp / grad / XtWX
-(SURVEY.md section 4).  The oracle is pinned only against the *properties* the
-reference tests assert (identity at delta=0, monotone h, sum-to-zero terms,
-penalty == I after diagonalisation, MVN-singular prior form) -- see
-tests/test_oracle_properties.py -- and against a literal forward-mode (JVP)
-restatement of the reference's custom_jvp rule (``jvp_logp`` below), which
-cross-checks the hand-derived reverse-mode gradient.
+PINNING: the reference cannot be imported as a package in this image (needs
+Python 3.13 + jax 0.8.2 + liesel 0.4.3 + tfp-nightly, none installed, no network)
+and its own tests hold no golden numbers for logp / grad / XtWX.
+The oracle is therefore pinned against outputs of the REFERENCE'S OWN SOURCE FILES
+executed here over NumPy stand-ins for jax / tfp (tests/golden/jaxshim,
+tests/golden/make_reference_golden.py -> tests/golden/ref_*.npz): bspline/approx.py,
+bspline/ptm.py, bspline/util.py, dist.py, gam/dist.py, constraint.py, penalty.py,
+iwls_proposals.py run unmodified.  tests/test_reference_golden.py: knots, dense bases,
+grid tables, theta(delta), h / h' over all five regions are BIT-EQUAL; per-observation
+log-densities agree to 1e-13, the gradient to 1e-14 of its norm against forward mode
+through the reference's code with its declared custom_jvp rules, precision / Cholesky to
+1e-13.  What stays unpinned: XLA's own rounding (FMA contraction, reduction order) and
+the stand-ins' restatement of jax primitives (``jnp.linspace`` arithmetic, clamped
+gathers, ``lax.switch``) and of tfp ``Normal.log_prob``.  In addition the oracle passes
+the *properties* the reference tests assert (identity at delta=0, monotone h,
+sum-to-zero terms, penalty == I, MVN-singular prior form; tests/test_oracle.py) and a
+literal forward-mode restatement of the custom_jvp rule (``jvp_logp`` below).
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference/liesel_ptm/).  Third-party arithmetic that is not in the tree

@@ -31,6 +31,8 @@ def model_from_fixture(d, dtype=np.float64, device="cuda:0"):
             model.loc += tm
         else:
             model.scale += tm
+    if "trafo_Z" in d:
+        model.trafo_Z = d["trafo_Z"].astype(dtype)
     return model
 
 
