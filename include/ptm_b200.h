@@ -203,6 +203,45 @@ int ptm_intercept_stats_f64(const PtmProblem* prob, const double* params, int64_
 int ptm_intercept_stats_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
                             float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Predictive evaluation on NEW data for n_samples posterior samples (params [S, P] like
+ * the chain states): y_new [m] and x_new [T, m] (term-major, the problem's term order) are
+ * device arrays; z, logpdf, cdf are [S, m] device outputs, each optional (NULL to skip):
+ *   z      = h((y - mu) / sigma)                        (dist.py:385-395, 718-740)
+ *   logpdf = -z^2/2 - log(2 pi)/2 + log max(h', tiny) - log sigma     (dist.py:185-188)
+ *   cdf    = Phi(z)                                      (dist.py:179-181)
+ * This is LocScalePTM.init_dist(samples, newdata=...).log_prob / .cdf and summarise_dist
+ * (model/model.py:698-790) as one sweep without materialising loc / scale per sample.
+ * Covariates outside a term's interior knots give NaN (the reference raises,
+ * approx.py:197-206; the host wrapper raises the same ValueError before the call).
+ * n_samples <= 65535 per call.  Workspace: ptm_predict_workspace_bytes(prob, n_samples). */
+size_t ptm_predict_workspace_bytes(const PtmProblem* prob, int64_t n_samples);
+int ptm_predict_f64(const PtmProblem* prob, const double* params, int64_t n_samples,
+                    const double* y_new, const double* x_new, int64_t m, double* z, double* logpdf,
+                    double* cdf, void* workspace, size_t workspace_bytes, void* stream);
+int ptm_predict_f32(const PtmProblem* prob, const float* params, int64_t n_samples,
+                    const float* y_new, const float* x_new, int64_t m, float* z, float* logpdf,
+                    float* cdf, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Predictive quantiles: yq[s, i] = mu_si + sigma_si * h_s^{-1}(Phi^{-1}(u_i)) for
+ * probabilities u [m] (one per new observation row) -- TransformationDist._quantile /
+ * inverse_transformation (dist.py:203-209, 575-650). */
+int ptm_predict_quantile_f64(const PtmProblem* prob, const double* params, int64_t n_samples,
+                             const double* u, const double* x_new, int64_t m, double* yq,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int ptm_predict_quantile_f32(const PtmProblem* prob, const float* params, int64_t n_samples,
+                             const float* u, const float* x_new, int64_t m, float* yq,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* r [C, m] with h_c(r) = z for raw shape coefficients delta [C, nparam] and z [m] --
+ * TransformationSpline.dot_inverse_n (bspline/util.py:105-122).  Exact inverse of the
+ * reference's forward function (lerp cells in the core, quadratic transitions, linear
+ * tails); the reference interpolates a 1000-point table with interpax and its tests accept
+ * 1e-5 .. 1e-4 (tests/test_bspline/test_ptm.py:167-301). */
+int ptm_inverse_f64(const PtmProblem* prob, const double* delta, int64_t n_chains,
+                    const double* z, int64_t m, double* r, void* stream);
+int ptm_inverse_f32(const PtmProblem* prob, const float* delta, int64_t n_chains,
+                    const float* z, int64_t m, float* r, void* stream);
+
 /* Pointwise predictive records over n_samples posterior samples -- the streaming WAIC /
  * lppd of the reference (EvaluatePTM._lppdi, .lppdi, .waic: model/evaluate.py:106-133,
  * 177-236) as one sweep.  params is [n_samples, P] like the chain states (draws x chains

@@ -126,6 +126,18 @@ def load() -> C.CDLL:
         f = getattr(lib, f"ptm_pointwise_{sfx}")
         f.argtypes = [vp, vp, i64, vp, vp, vp, sz, vp]
         f.restype = C.c_int
+    lib.ptm_predict_workspace_bytes.argtypes = [vp, i64]
+    lib.ptm_predict_workspace_bytes.restype = sz
+    for sfx in ("f64", "f32"):
+        f = getattr(lib, f"ptm_predict_{sfx}")
+        f.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, sz, vp]
+        f.restype = C.c_int
+        f = getattr(lib, f"ptm_predict_quantile_{sfx}")
+        f.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, sz, vp]
+        f.restype = C.c_int
+        f = getattr(lib, f"ptm_inverse_{sfx}")
+        f.argtypes = [vp, vp, i64, vp, i64, vp, vp]
+        f.restype = C.c_int
     lib.ptm_last_launch_count.restype = C.c_int
     lib.ptm_last_xtwx_route.restype = C.c_int
     lib.ptm_profile_enable.argtypes = [C.c_int]

@@ -17,6 +17,7 @@
 #include "ptm_kernels.cuh"
 #include "ptm_xtwx.cuh"
 #include "ptm_xtwx_tc.cuh"
+#include "ptm_predict.cuh"
 
 namespace {
 
@@ -536,6 +537,72 @@ int transform_impl(const PtmProblem* pr, const R* delta, long long C, const R* r
   return PTM_OK;
 }
 
+// ---- callers of the path on new data: predictive z / log-density / CDF, quantiles, inverse --
+size_t predict_ws_bytes(const PtmProblem* pr, long long S) {
+  const size_t w = pr->dtype == PTM_F64 ? 8 : 4;
+  const size_t gam = ((size_t)pr->T * ptm::kMaxNbases * S * w + 255) / 256 * 256;
+  const size_t cc = ((size_t)(pr->KK * 5 + 6) * S * w + 255) / 256 * 256;
+  return gam + cc;
+}
+
+template <typename R>
+int predict_impl(const PtmProblem* pr, const R* params, long long S, const R* y_or_u, const R* x_new,
+                 long long m, R* z, R* logpdf, R* cdf, R* yq, void* ws, size_t ws_bytes, void* stream) {
+  if (!pr || !params || !y_or_u || !ws) return fail(PTM_ERR_NULL, "null argument");
+  if (pr->T > 0 && !x_new) return fail(PTM_ERR_NULL, "x_new is null");
+  if (!z && !logpdf && !cdf && !yq) return fail(PTM_ERR_NULL, "no output requested");
+  if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  if (S < 1 || m < 0) return fail(PTM_ERR_SHAPE, "bad shape");
+  if (S > 65535) return fail(PTM_ERR_SHAPE, "at most 65535 samples per call");
+  if (ws_bytes < predict_ws_bytes(pr, S)) return fail(PTM_ERR_WORKSPACE, "workspace too small (see ptm_predict_workspace_bytes)");
+  if (m == 0) return PTM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* wsb = reinterpret_cast<char*>(ws);
+  R* Gamma = reinterpret_cast<R*>(wsb);
+  R* cc = reinterpret_cast<R*>(wsb + ((size_t)pr->T * ptm::kMaxNbases * S * sizeof(R) + 255) / 256 * 256);
+  ptm::PreArgs<R> pa;
+  fill_pre_args<R>(pr, params, S, Gamma, cc, pa);
+  ptm::k_pre<R><<<(unsigned)S, 128, pr->P * sizeof(R), st>>>(pa);
+  PTM_CUDA(cudaGetLastError());
+  ptm::PredictArgs<R> a;
+  memset(&a, 0, sizeof a);
+  a.y = y_or_u; a.X = x_new; a.m = m;
+  a.knots = reinterpret_cast<const R*>(pr->d_knots);
+  a.Gamma = Gamma; a.cc = cc; a.grid = reinterpret_cast<const R*>(pr->d_grid);
+  a.S = (int)S; a.T = pr->T; a.KK = pr->KK; a.sum_nb = pr->sum_nb;
+  for (int t = 0; t < pr->T; ++t) {
+    a.nb[t] = pr->nb[t]; a.pred[t] = pr->pred[t] == PTM_LOC ? 0 : 1;
+    a.goff[t] = pr->goff[t]; a.inv_dk[t] = (R)pr->inv_dk[t];
+  }
+  ptm::TrafoConst<R> tcr;
+  fill_tc<R>(pr->tc64, tcr);
+  a.ts = tcr;
+  a.out_z = z; a.out_logpdf = logpdf; a.out_cdf = cdf; a.out_q = yq;
+  const long long per_sample = std::max<long long>(1, ((long long)pr->num_sms * 8 + S - 1) / S);
+  const long long gx = std::max<long long>(1, std::min<long long>((m + 255) / 256, per_sample));
+  const dim3 grid((unsigned)gx, (unsigned)S);
+  const size_t smem = (size_t)(pr->sum_nb + pr->KK * 5 + (yq ? ptm::kGridN : 0)) * sizeof(R);
+  if (yq) ptm::k_predict<R, true><<<grid, 256, smem, st>>>(a);
+  else ptm::k_predict<R, false><<<grid, 256, smem, st>>>(a);
+  PTM_CUDA(cudaGetLastError());
+  return PTM_OK;
+}
+
+template <typename R>
+int inverse_impl(const PtmProblem* pr, const R* delta, long long C, const R* z, long long m, R* r,
+                 void* stream) {
+  if (!pr || !delta || !z || !r) return fail(PTM_ERR_NULL, "null argument");
+  if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  if (C < 1 || m < 0) return fail(PTM_ERR_SHAPE, "bad shape");
+  if (m == 0) return PTM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ptm::k_inverse<R><<<(unsigned)C, 256, 0, st>>>(
+      delta, (int)C, z, m, reinterpret_cast<const ptm::TrafoConst<R>*>(pr->d_tc),
+      reinterpret_cast<const R*>(pr->d_grid), r);
+  PTM_CUDA(cudaGetLastError());
+  return PTM_OK;
+}
+
 static thread_local int g_last_xtwx_route = 0;  // 0 = banded CUDA-core sweep, 1 = tcgen05 sweep
 static bool tc_route_enabled() {
   const char* e = getenv("PTM_XTWX_TC");
@@ -846,6 +913,39 @@ int ptm_loc_precision_all_f64(const PtmProblem* p, const double* params, int64_t
 int ptm_loc_precision_all_f32(const PtmProblem* p, const float* params, int64_t C, float* precision,
                               float* chol, void* ws, size_t wsb, void* st) {
   return precision_all_impl<float>(p, params, C, precision, chol, ws, wsb, st);
+}
+
+size_t ptm_predict_workspace_bytes(const PtmProblem* p, int64_t S) {
+  if (!p || S < 1) return 0;
+  return predict_ws_bytes(p, S);
+}
+int ptm_predict_f64(const PtmProblem* p, const double* params, int64_t S, const double* y_new,
+                    const double* x_new, int64_t m, double* z, double* logpdf, double* cdf, void* ws,
+                    size_t wsb, void* st) {
+  return predict_impl<double>(p, params, S, y_new, x_new, m, z, logpdf, cdf, nullptr, ws, wsb, st);
+}
+int ptm_predict_f32(const PtmProblem* p, const float* params, int64_t S, const float* y_new,
+                    const float* x_new, int64_t m, float* z, float* logpdf, float* cdf, void* ws,
+                    size_t wsb, void* st) {
+  return predict_impl<float>(p, params, S, y_new, x_new, m, z, logpdf, cdf, nullptr, ws, wsb, st);
+}
+int ptm_predict_quantile_f64(const PtmProblem* p, const double* params, int64_t S, const double* u,
+                             const double* x_new, int64_t m, double* yq, void* ws, size_t wsb, void* st) {
+  if (!yq) return fail(PTM_ERR_NULL, "yq is null");
+  return predict_impl<double>(p, params, S, u, x_new, m, nullptr, nullptr, nullptr, yq, ws, wsb, st);
+}
+int ptm_predict_quantile_f32(const PtmProblem* p, const float* params, int64_t S, const float* u,
+                             const float* x_new, int64_t m, float* yq, void* ws, size_t wsb, void* st) {
+  if (!yq) return fail(PTM_ERR_NULL, "yq is null");
+  return predict_impl<float>(p, params, S, u, x_new, m, nullptr, nullptr, nullptr, yq, ws, wsb, st);
+}
+int ptm_inverse_f64(const PtmProblem* p, const double* delta, int64_t C, const double* z, int64_t m,
+                    double* r, void* st) {
+  return inverse_impl<double>(p, delta, C, z, m, r, st);
+}
+int ptm_inverse_f32(const PtmProblem* p, const float* delta, int64_t C, const float* z, int64_t m,
+                    float* r, void* st) {
+  return inverse_impl<float>(p, delta, C, z, m, r, st);
 }
 
 size_t ptm_pointwise_workspace_bytes(const PtmProblem* p, int64_t S) {

@@ -344,6 +344,103 @@ class LocScalePTM:
             z, dz = z[..., 0], dz[..., 0]
         return z, dz
 
+    def inverse(self, delta: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+        """r with h(r) = z for raw shape coefficients delta [C, nparam] or [nparam]
+        (TransformationSpline.dot_inverse_n, bspline/util.py:105-122): exact inverse of the
+        reference's forward function."""
+        squeeze = delta.dim() == 1
+        d2 = (delta[None, :] if squeeze else delta).contiguous()
+        if d2.dim() != 2 or d2.shape[1] != self.nparam:
+            raise ValueError(f"coef must have shape ({self.nparam},) or (C, {self.nparam})")
+        if z.dim() > 1:
+            raise TypeError("dot_inverse_n expects y of shape (n,) or ()")
+        was_scalar = z.dim() == 0
+        zv = z.reshape(-1).contiguous()
+        Cn, m = d2.shape[0], zv.shape[0]
+        r = torch.empty((Cn, m), dtype=self.dtype, device=self.device)
+        f = getattr(self._lib, f"ptm_inverse_{self._sfx}")
+        _lib.check(f(self._handle, d2.data_ptr(), Cn, zv.data_ptr(), m, r.data_ptr(), self._stream()))
+        if squeeze:
+            r = r[0]
+        if was_scalar:
+            r = r[..., 0]
+        return r
+
+    def _newdata(self, newdata, grid):
+        """Device arrays (y_or_grid [m], X [T, m]) for a predictive sweep.  ``newdata`` maps
+        covariate names (``basis.xname``) to arrays like the reference's ``newdata`` dicts;
+        None means the training covariates.  Values outside a term's interior knots raise
+        like ``Basis.bspline`` (approx.py:197-206)."""
+        if not self.is_built:
+            raise ValueError("Model must be built with .build() first.")
+        nd = self.np_dtype
+        cols = []
+        for t, _ in self.terms:
+            if newdata is None:
+                x = t.basis.x
+            else:
+                if t.basis.xname not in newdata:
+                    raise KeyError(f"newdata has no entry for covariate {t.basis.xname!r}")
+                x = np.asarray(newdata[t.basis.xname], dtype=nd).reshape(-1)
+            kn = t.basis.knots
+            lo, hi = kn[3], kn[t.basis.nbases]
+            if x.size and not (np.nanmin(x) >= lo and np.nanmax(x) <= hi):
+                raise ValueError(f"Values of x are not inside the range of interior knots, [{lo}, {hi}]")
+            cols.append(x)
+        g = self.response if grid is None else np.asarray(grid, dtype=nd).reshape(-1)
+        m = cols[0].shape[0] if cols else g.shape[0]
+        if g.shape[0] == 1 and m > 1:
+            g = np.full(m, g[0], dtype=nd)
+        if any(c.shape[0] != m for c in cols) or g.shape[0] != m:
+            raise ValueError("newdata columns and grid must have the same length")
+        X = np.stack(cols) if cols else np.zeros((0, m), dtype=nd)
+        return (torch.from_numpy(np.ascontiguousarray(g, dtype=nd)).to(self.device),
+                torch.from_numpy(np.ascontiguousarray(X, dtype=nd)).to(self.device), m)
+
+    def summarise_dist(self, samples: torch.Tensor, grid=None, newdata=None,
+                       which=("z", "prob", "log_prob", "cdf")) -> dict:
+        """z, prob, log_prob, cdf over posterior samples [S, P] at ``grid`` (default: the
+        observed response) and ``newdata`` (default: the training covariates) -- each
+        [S, m]; LocScalePTM.init_dist + summarise_dist (model/model.py:698-790)."""
+        samples = self._check_params(samples)
+        g, X, m = self._newdata(newdata, grid)
+        S = samples.shape[0]
+        ws = torch.empty(max(int(self._lib.ptm_predict_workspace_bytes(self._handle, S)), 1),
+                         dtype=torch.uint8, device=self.device)
+        want_lp = "log_prob" in which or "prob" in which
+        out = {}
+        z = torch.empty((S, m), dtype=self.dtype, device=self.device) if "z" in which else None
+        lpdf = torch.empty((S, m), dtype=self.dtype, device=self.device) if want_lp else None
+        cdf = torch.empty((S, m), dtype=self.dtype, device=self.device) if "cdf" in which else None
+        f = getattr(self._lib, f"ptm_predict_{self._sfx}")
+        ptr = lambda t: 0 if t is None else t.data_ptr()  # noqa: E731
+        _lib.check(f(self._handle, samples.data_ptr(), S, g.data_ptr(), X.data_ptr(), m, ptr(z), ptr(lpdf),
+                     ptr(cdf), ws.data_ptr(), ws.numel(), self._stream()))
+        if z is not None:
+            out["z"] = z
+        if "prob" in which:
+            out["prob"] = torch.exp(lpdf)
+        if "log_prob" in which:
+            out["log_prob"] = lpdf
+        if cdf is not None:
+            out["cdf"] = cdf
+        return out
+
+    def predict_quantile(self, samples: torch.Tensor, u, newdata=None) -> torch.Tensor:
+        """Predictive quantiles [S, m] at probabilities ``u`` (scalar or one per row):
+        init_dist(samples, newdata=...).quantile(u) (dist.py:203-209)."""
+        samples = self._check_params(samples)
+        uv = np.asarray(u, dtype=self.np_dtype).reshape(-1)
+        g, X, m = self._newdata(newdata, uv)
+        S = samples.shape[0]
+        ws = torch.empty(max(int(self._lib.ptm_predict_workspace_bytes(self._handle, S)), 1),
+                         dtype=torch.uint8, device=self.device)
+        yq = torch.empty((S, m), dtype=self.dtype, device=self.device)
+        f = getattr(self._lib, f"ptm_predict_quantile_{self._sfx}")
+        _lib.check(f(self._handle, samples.data_ptr(), S, g.data_ptr(), X.data_ptr(), m, yq.data_ptr(),
+                     ws.data_ptr(), ws.numel(), self._stream()))
+        return yq
+
     def intercept_stats(self, params: torch.Tensor) -> torch.Tensor:
         """[C, 3] sufficient statistics of the intercept pseudo-Gibbs updates: sum exp(-eta_sigma),
         sum r, sum r^2 over this handle's observation range (additive over shards)."""

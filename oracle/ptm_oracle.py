@@ -391,6 +391,49 @@ class PTMSpline:
         v, d = self.dot_and_deriv_coef(xv, self.compute_coef(delta))
         return (v[0], d[0]) if was_scalar else (v, d)
 
+    # -- inverse ----------------------------------------------------------------
+    def dot_inverse_exact(self, z, delta):
+        """Exact inverse of ``dot_and_deriv_n_fullbatch``'s value: r with h(r) = z.
+
+        Checker for ``ptm_inverse_*`` / the predictive quantiles.  The reference
+        (bspline/util.py:105-122 -> util/inverse_interpax.py:60-113) interpolates a
+        1000-point table of (h(x), x) pairs with interpax ("monotonic"; third party, absent
+        here) and its tests accept 1e-5 .. 1e-4 on the round trip
+        (tests/test_bspline/test_ptm.py:167-301); this restates the inverse of the forward
+        function itself instead: in the core the forward is the lerp of the samples
+        H[i] = h(grid[i]) with weight (r - grid[i]) / step (approx.py:425-432), the
+        transitions are quadratics in the distance from the boundary knot (ptm.py:349-394),
+        the tails are linear (396-410)."""
+        z = np.atleast_1d(np.asarray(z, dtype=self.knots.dtype))
+        theta = self.compute_coef(np.asarray(delta))
+        ap = self.bspline
+        g = ap.grid[1:-1]
+        H, _ = ap.dot_and_deriv_n(g, theta)
+        bv, bd = ap.dot_and_deriv_n(self.boundaries, theta)
+        vl, dl, vr, dr = bv[0], bd[0], bv[1], bd[1]
+        w, a, b = self.transition_width, self.min_knot, self.max_knot
+        ztl = self._left_transition(self.min_eps, vl, dl)[0]
+        ztr = self._right_transition(self.max_eps, vr, dr)[0]
+        r = np.full(z.shape, np.nan, dtype=z.dtype)
+        m = z < ztl
+        r[m] = self.min_eps - (ztl - z[m])
+        m = z > ztr
+        r[m] = self.max_eps + (z[m] - ztr)
+        m = (z >= ztl) & (z < vl)
+        c = vl - z[m]
+        r[m] = np.maximum(a - 2 * c / (dl + np.sqrt(np.maximum(dl * dl + 2 * (1 - dl) / w * c, 0.0))),
+                          self.min_eps)
+        m = (z <= ztr) & (z > vr)
+        c = z[m] - vr
+        r[m] = np.minimum(b + 2 * c / (dr + np.sqrt(np.maximum(dr * dr + 2 * (1 - dr) / w * c, 0.0))),
+                          self.max_eps)
+        m = (z >= vl) & (z <= vr)
+        i = np.clip(np.searchsorted(H, z[m], side="right") - 1, 0, H.size - 2)
+        den = H[i + 1] - H[i]
+        kap = np.clip(np.where(den > 0, (z[m] - H[i]) / np.where(den > 0, den, 1.0), 0.0), 0.0, 1.0)
+        r[m] = np.minimum(g[i] + kap * ap.step, b)
+        return r
+
 
 # --------------------------------------------------------------------------
 # penalty.py / constraint.py / gam
@@ -583,6 +626,34 @@ class PTMModel:
         dclip = np.clip(d, tiny, None)
         ll = (-0.5 * z * z - self.dtype.type(LOG_2PI_HALF)) + (logdet_param + np.log(dclip))
         return dict(mu=mu, ls=ls, sd=sd, r=r, z=z, d=d, dclip=dclip, ll=ll, theta=theta, delta=delta)
+
+    def predict(self, st: ChainState, c: int, y_new, X_new):
+        """init_dist(samples, newdata=...) -> transformation_and_logdet / log_prob / cdf for
+        sample c at new data (model/model.py:698-790, dist.py:179-188, 385-395, 718-740):
+        X_new[t] is the new covariate of term t; designs are rebuilt densely like
+        ``graph.predict`` does.  Returns z, log_prob, cdf (each (m,)), mu, sigma."""
+        from scipy.special import ndtr
+
+        y_new = np.asarray(y_new, dtype=self.dtype)
+        mu = np.full(y_new.shape[0], st.beta0[c], dtype=self.dtype)
+        ls = np.full(y_new.shape[0], st.gamma0[c], dtype=self.dtype)
+        for t, term in enumerate(self.terms):
+            B = basis_matrix(np.asarray(X_new[t], dtype=self.dtype), term.knots, 3, outer_ok=False)
+            f = (B @ term.Z) @ st.beta[t][c]
+            if term.predictor == "loc":
+                mu = mu + f
+            else:
+                ls = ls + f
+        sd = np.exp(ls)
+        r = (y_new - mu) / sd
+        theta = self.spline.compute_coef(st.delta_z[c] @ self.Zd.T)
+        z, d = self.spline.dot_and_deriv_coef(r, theta)
+        nan_mask = np.isnan(r)
+        z = np.where(nan_mask, np.nan, z)
+        d = np.where(nan_mask, np.nan, d)
+        dclip = np.clip(d, np.finfo(self.dtype).tiny, None)
+        lp = (-0.5 * z * z - self.dtype.type(LOG_2PI_HALF)) + (-np.log(sd) + np.log(dclip))
+        return z, lp, ndtr(z), mu, sd
 
     def prior(self, st: ChainState, c: int):
         lp = self.dtype.type(0)
