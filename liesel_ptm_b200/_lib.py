@@ -32,6 +32,8 @@ SYMBOLS = [
     "ptm_quadform_f64", "ptm_quadform_f32", "ptm_intercept_stats_f64", "ptm_intercept_stats_f32",
     "ptm_loc_precision_all_f64", "ptm_loc_precision_all_f32",
     "ptm_pointwise_workspace_bytes", "ptm_pointwise_f64", "ptm_pointwise_f32",
+    "ptm_predict_workspace_bytes", "ptm_predict_f64", "ptm_predict_f32",
+    "ptm_predict_quantile_f64", "ptm_predict_quantile_f32", "ptm_inverse_f64", "ptm_inverse_f32",
     "ptm_last_launch_count", "ptm_last_xtwx_route", "ptm_profile_enable", "ptm_last_kernel_ms", "ptm_last_error",
     "ptm_version",
 ]
