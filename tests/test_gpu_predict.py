@@ -57,7 +57,13 @@ def test_inverse_vs_oracle(dtype, tol):
         r_ref = sp.dot_inverse_exact(z.astype(np.float64), delta[c].astype(np.float64))
         scale = np.max(np.abs(r_ref))
         if dtype == np.float64:
-            assert np.max(np.abs(r.cpu().numpy() - r_ref)) < tol * scale
+            # the forward is a saw-tooth of 0.1 % of a grid cell at every grid point
+            # (lerp weight up to 1000/999, approx.py:375-376), so a z within rounding of a
+            # sample H[i] has two exact pre-images 8e-6 apart: accept either
+            err = np.abs(r.cpu().numpy() - r_ref)
+            fwd, _ = sp.dot_and_deriv_n_fullbatch(r.cpu().numpy(), delta[c].astype(np.float64))
+            twin = (err < 8.1e-6) & (np.abs(fwd - z) < 1e-13 * max(1.0, np.max(np.abs(z))))
+            assert np.all((err < tol * scale) | twin) and twin.sum() - (err < tol * scale)[twin].sum() < 8
         else:  # float cells are decided on float samples: compare through the round trip
             assert np.max(np.abs(r.cpu().numpy() - r_ref)) < 1e-4
         # round trip through the CUDA forward
