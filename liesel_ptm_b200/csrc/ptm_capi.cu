@@ -542,7 +542,8 @@ size_t predict_ws_bytes(const PtmProblem* pr, long long S) {
   const size_t w = pr->dtype == PTM_F64 ? 8 : 4;
   const size_t gam = ((size_t)pr->T * ptm::kMaxNbases * S * w + 255) / 256 * 256;
   const size_t cc = ((size_t)(pr->KK * 5 + 6) * S * w + 255) / 256 * 256;
-  return gam + cc;
+  const size_t H = (size_t)S * ptm::kGridN * w;  // spline samples of every sample (quantile mode)
+  return gam + cc + H;
 }
 
 template <typename R>
@@ -553,7 +554,7 @@ int predict_impl(const PtmProblem* pr, const R* params, long long S, const R* y_
   if (!z && !logpdf && !cdf && !yq) return fail(PTM_ERR_NULL, "no output requested");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
   if (S < 1 || m < 0) return fail(PTM_ERR_SHAPE, "bad shape");
-  if (S > 65535) return fail(PTM_ERR_SHAPE, "at most 65535 samples per call");
+  if (S > 65535 && pr->T > 12) return fail(PTM_ERR_SHAPE, "at most 65535 samples per call beyond 12 terms");
   if (ws_bytes < predict_ws_bytes(pr, S)) return fail(PTM_ERR_WORKSPACE, "workspace too small (see ptm_predict_workspace_bytes)");
   if (m == 0) return PTM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -578,6 +579,35 @@ int predict_impl(const PtmProblem* pr, const R* params, long long S, const R* y_
   fill_tc<R>(pr->tc64, tcr);
   a.ts = tcr;
   a.out_z = z; a.out_logpdf = logpdf; a.out_cdf = cdf; a.out_q = yq;
+  if (pr->T <= 12) {
+    // observation-major sweep: basis windows once per observation, samples staged in groups
+    const long long bx = (m + ptm::kPredThreads - 1) / ptm::kPredThreads;
+    const long long groups = (S + ptm::kPredSG - 1) / ptm::kPredSG;
+    long long by = std::max<long long>(1, std::min<long long>(groups, (2LL * pr->num_sms + bx - 1) / bx));
+    by = std::min<long long>(by, 65535);
+    const int s_per_block = (int)((groups + by - 1) / by) * ptm::kPredSG;
+    by = (S + s_per_block - 1) / s_per_block;
+    R* H = nullptr;
+    if (yq) {
+      H = reinterpret_cast<R*>(wsb + predict_ws_bytes(pr, S) - (size_t)S * ptm::kGridN * sizeof(R));
+      ptm::k_grid_samples<R><<<(unsigned)S, 256, 0, st>>>(cc, (int)S, pr->KK, a.ts, H);
+      PTM_CUDA(cudaGetLastError());
+    }
+    const dim3 grid((unsigned)bx, (unsigned)by);
+    const size_t smem = (size_t)ptm::kPredSG * (pr->sum_nb + pr->KK * 5 + 6) * sizeof(R);
+#define PTM_PREDICT_LAUNCH(TT)                                                                         \
+    do {                                                                                               \
+      if (yq) ptm::k_predict_obs<R, true, TT><<<grid, ptm::kPredThreads, smem, st>>>(a, H, s_per_block); \
+      else ptm::k_predict_obs<R, false, TT><<<grid, ptm::kPredThreads, smem, st>>>(a, H, s_per_block);   \
+    } while (0)
+    if (pr->T <= 4) PTM_PREDICT_LAUNCH(4);
+    else if (pr->T <= 8) PTM_PREDICT_LAUNCH(8);
+    else PTM_PREDICT_LAUNCH(12);
+#undef PTM_PREDICT_LAUNCH
+    PTM_CUDA(cudaGetLastError());
+    return PTM_OK;
+  }
+  // more than 12 terms: sample-major sweep (basis windows recomputed per sample)
   const long long per_sample = std::max<long long>(1, ((long long)pr->num_sms * 8 + S - 1) / S);
   const long long gx = std::max<long long>(1, std::min<long long>((m + 255) / 256, per_sample));
   const dim3 grid((unsigned)gx, (unsigned)S);

@@ -206,6 +206,125 @@ __global__ void __launch_bounds__(256) k_predict(const PredictArgs<R> a) {
   }
 }
 
+// Spline samples H[s][kGridN] of every posterior sample (quantile mode of k_predict_obs).
+template <typename R>
+__global__ void k_grid_samples(const R* __restrict__ cc, int S, int KK, const TrafoScal<R> ts,
+                               R* __restrict__ H) {
+  __shared__ R s_pc[kMaxJ * 5];
+  const int s = blockIdx.x;
+  for (int k = threadIdx.x; k < KK * 5; k += blockDim.x) s_pc[k] = cc[(long long)k * S + s];
+  __syncthreads();
+  for (int i = threadIdx.x; i < kGridN; i += blockDim.x) {
+    CoreEval<R> ev;
+    core_locate(ts, i, R(0), ev);
+    const R* cp = s_pc + ev.kk * 5;
+    core_eval(ts, cp[0], cp[1], cp[2], cp[3], cp[4], ev);
+    H[(long long)s * kGridN + i] = ev.z;
+  }
+}
+
+// Observation-major predictive sweep: thread = new observation, its T basis windows are
+// evaluated ONCE and stay in registers; the block then walks over the samples in groups of
+// kPredSG whose gamma tables / cubic pieces are staged in shared memory.  blockIdx.y splits
+// the samples when there are too few observation blocks to fill the GPU.
+constexpr int kPredSG = 4;       // samples per shared-memory stage
+constexpr int kPredThreads = 128;
+
+template <typename R, bool QUANTILE, int TT>
+__global__ void __launch_bounds__(kPredThreads) k_predict_obs(const PredictArgs<R> a, const R* __restrict__ Hall,
+                                                              int s_per_block) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int KK = a.KK;
+  const int NCC = KK * 5 + 6;
+  R* s_gam = reinterpret_cast<R*>(smem_raw);  // [kPredSG][sum_nb]
+  R* s_cc = s_gam + kPredSG * a.sum_nb;       // [kPredSG][NCC]
+  __shared__ ChainBoundary<R> s_cb[kPredSG];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < a.m;
+  const TrafoScal<R> ts = a.ts;
+  const R nan = sizeof(R) == 8 ? (R)__longlong_as_double(0x7ff8000000000000LL) : (R)__int_as_float(0x7fc00000);
+
+  // ---- chain-independent part, once per observation --------------------------------
+  R bb[TT][4];
+  int joff[TT];
+  bool inside = true;
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    joff[t] = 0;
+    bb[t][0] = bb[t][1] = bb[t][2] = bb[t][3] = R(0);
+    if (t < a.T && live) {
+      const R x = a.X[(long long)t * a.m + i];
+      const R* kn = a.knots + t * kKnotStride;
+      const int nb = a.nb[t];
+      const bool ok = x >= kn[3] && x <= kn[nb];
+      inside = inside && ok;
+      const int jj = basis_window(ok ? x : kn[3], kn, nb, a.inv_dk[t], bb[t]);
+      joff[t] = a.goff[t] + jj;
+    }
+  }
+  const R yv = live ? a.y[i] : R(0);
+  R zq = R(0);
+  if constexpr (QUANTILE) zq = std_normal_quantile(yv);
+
+  const int s_begin = blockIdx.y * s_per_block;
+  const int s_end = min(a.S, s_begin + s_per_block);
+  for (int s0 = s_begin; s0 < s_end; s0 += kPredSG) {
+    const int ns = min(kPredSG, s_end - s0);
+    __syncthreads();  // the previous group's tables are no longer read
+    for (int idx = threadIdx.x; idx < ns * a.sum_nb; idx += blockDim.x) {
+      const int g = idx / a.sum_nb, k = idx - g * a.sum_nb;
+      int t = 0;
+      while (t + 1 < a.T && k >= a.goff[t + 1]) ++t;
+      s_gam[g * a.sum_nb + k] = a.Gamma[((long long)t * kMaxNbases + (k - a.goff[t])) * a.S + s0 + g];
+    }
+    for (int idx = threadIdx.x; idx < ns * NCC; idx += blockDim.x) {
+      const int g = idx / NCC, k = idx - g * NCC;
+      s_cc[g * NCC + k] = a.cc[(long long)k * a.S + s0 + g];
+    }
+    __syncthreads();
+    if (threadIdx.x < ns) {
+      const R* c = s_cc + threadIdx.x * NCC + KK * 5;
+      make_boundary(ts, c[0], c[1], c[2], c[3], s_cb[threadIdx.x]);
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int g = 0; g < ns; ++g) {
+      const R* gam = s_gam + g * a.sum_nb;
+      const R* pc = s_cc + g * NCC;
+      R em = pc[KK * 5 + 4], es = pc[KK * 5 + 5];
+#pragma unroll
+      for (int t = 0; t < TT; ++t) {
+        if (t < a.T) {
+          const R* gp = gam + joff[t];
+          R f = bb[t][0] * gp[0];
+          f = fma(bb[t][1], gp[1], f);
+          f = fma(bb[t][2], gp[2], f);
+          f = fma(bb[t][3], gp[3], f);
+          if (a.pred[t] == 0) em += f; else es += f;
+        }
+      }
+      const long long oi = (long long)(s0 + g) * a.m + i;
+      if constexpr (QUANTILE) {
+        const R rq = trafo_inverse(ts, s_cb[g], Hall + (long long)(s0 + g) * kGridN, a.grid, zq);
+        a.out_q[oi] = inside ? fma(exp(es), rq, em) : nan;
+      } else {
+        const R sd = exp(es);
+        const R r = (yv - em) / sd;  // dist.py:735-736
+        R z, d;
+        trafo_forward(ts, s_cb[g], pc, a.grid, r, z, d);
+        if (!(r == r) || !inside) { z = nan; d = nan; }
+        if (a.out_z) a.out_z[oi] = z;
+        if (a.out_logpdf) {
+          const R tiny = tiny_of<R>();
+          const R dcl = d > tiny ? d : (d == d ? tiny : d);
+          a.out_logpdf[oi] = (R(-0.5) * z * z - R(0.91893853320467274178)) + (log(dcl) - es);
+        }
+        if (a.out_cdf) a.out_cdf[oi] = std_normal_cdf(z);
+      }
+    }
+  }
+}
+
 // One block per chain: pieces from raw shape coefficients (as k_transform), then the exact
 // inverse for every z.
 template <typename R>

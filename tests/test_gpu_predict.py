@@ -149,3 +149,29 @@ def test_predict_quantile_vs_oracle():
     # scalar probability broadcasts over the rows
     med = case.model.predict_quantile(params, 0.5, newdata=newdata)
     assert med.shape == (5, m)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_loc,n_scale,C,m", [(1, 0, 1, 5), (6, 3, 7, 300), (8, 5, 3, 1000), (2, 2, 37, 129)])
+def test_predict_shapes_vs_oracle(n_loc, n_scale, C, m):
+    """Register tiers of the observation-major sweep (T <= 4, 8, 12), the sample-major sweep
+    beyond 12 terms, ragged sample groups and a ragged last observation block."""
+    case = build_case(n=200, n_loc=n_loc, n_scale=n_scale, nbases=10, nparam=20, C=C, amp=0.3)
+    T = n_loc + n_scale
+    rng = np.random.default_rng(20 + T)
+    newdata = {f"x{t}": rng.uniform(-1.99, 1.99, size=m) for t in range(T)}
+    grid = rng.normal(scale=2.5, size=m)
+    u = rng.uniform(0.01, 0.99, size=m)
+    params = torch.from_numpy(case.params).cuda()
+    out = case.model.summarise_dist(params, grid=grid, newdata=newdata)
+    yq = case.model.predict_quantile(params, u, newdata=newdata).cpu().numpy()
+    X = [newdata[f"x{t}"] for t in range(T)]
+    zq = ndtri(u)
+    for c in range(C):
+        z, lp, cdf, mu, sd = case.omodel.predict(case.state, c, grid, X)
+        assert rel_err(out["z"][c].cpu().numpy(), z) < 1e-12
+        assert rel_err(out["log_prob"][c].cpu().numpy(), lp) < 1e-12
+        assert rel_err(out["cdf"][c].cpu().numpy(), cdf) < 1e-12
+        delta = case.state.delta_z[c] @ case.omodel.Zd.T
+        ref = mu + sd * case.omodel.spline.dot_inverse_exact(zq, delta)
+        assert rel_err(yq[c], ref) < 1e-11
