@@ -77,6 +77,10 @@ constexpr int kTermUnroll = PTM_TERM_UNROLL;
 #ifndef PTM_RESPLIT_TERM
 #define PTM_RESPLIT_TERM 72
 #endif
+// Experiment: the eval warps carry two observations in lockstep (see the eval loop).
+#ifndef PTM_EVAL_PAIR
+#define PTM_EVAL_PAIR 0
+#endif
 #ifndef PTM_EVAL_UNROLL
 #define PTM_EVAL_UNROLL 1
 #endif
@@ -432,6 +436,192 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
           const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
           // (interleaving two observations per warp by unrolling was measured slower: the
           //  extra live values push the eval warps over their 96-register budget)
+#if PTM_EVAL_PAIR
+          if constexpr (!POINT) {
+          // Two observations per eval warp in lockstep (o0 and o0 + NU): every straight-line
+          // stage below carries both, so the scheduler can overlap their dependency chains.
+          for (int o0 = uw; o0 < cnt; o0 += 2 * NU) {
+            const bool vB = o0 + NU < cnt;  // the second slot repeats the first one when absent
+            const int oo[2] = {o0, vB ? o0 + NU : o0};
+            R yv[2], em[2], es[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { yv[k] = a.y[base + oo[k]]; em[k] = beta0; es[k] = gamma0; }
+            {
+              const R* bqA = s_b + (slot * To + oo[0]) * 4;
+              const R* bqB = s_b + (slot * To + oo[1]) * 4;
+              const int* jqA = s_j + slot * To + oo[0];
+              const int* jqB = s_j + slot * To + oo[1];
+              const R* gl = s_gam + lane;
+              const int qstep = 3 * To;
+              int q = 0;
+#pragma unroll kTermUnroll
+              for (; q < a.T_loc; ++q, bqA += qstep * 4, bqB += qstep * 4, jqA += qstep, jqB += qstep) {
+                R b0, b1, b2, b3, c0, c1, c2, c3;
+                load4(bqA, b0, b1, b2, b3);
+                load4(bqB, c0, c1, c2, c3);
+                const R* gA = gl + *jqA;
+                const R* gB = gl + *jqB;
+                R fA = b0 * gA[0], fB = c0 * gB[0];
+                fA = fma(b1, gA[32], fA); fB = fma(c1, gB[32], fB);
+                fA = fma(b2, gA[64], fA); fB = fma(c2, gB[64], fB);
+                fA = fma(b3, gA[96], fA); fB = fma(c3, gB[96], fB);
+                em[0] += fA; em[1] += fB;
+              }
+#pragma unroll kTermUnroll
+              for (; q < T; ++q, bqA += qstep * 4, bqB += qstep * 4, jqA += qstep, jqB += qstep) {
+                R b0, b1, b2, b3, c0, c1, c2, c3;
+                load4(bqA, b0, b1, b2, b3);
+                load4(bqB, c0, c1, c2, c3);
+                const R* gA = gl + *jqA;
+                const R* gB = gl + *jqB;
+                R fA = b0 * gA[0], fB = c0 * gB[0];
+                fA = fma(b1, gA[32], fA); fB = fma(c1, gB[32], fB);
+                fA = fma(b2, gA[64], fA); fB = fma(c2, gB[64], fB);
+                fA = fma(b3, gA[96], fA); fB = fma(c3, gB[96], fB);
+                es[0] += fA; es[1] += fB;
+              }
+            }
+            R einv[2], r[2], rc[2];
+            int code[2];
+            CoreEval<R> ev[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              einv[k] = fast_exp(-es[k]);
+              r[k] = (yv[k] - em[k]) * einv[k];
+              code[k] = region_code(ts, r[k]);
+              rc[k] = r[k] < ts.a ? ts.a : (r[k] > ts.b ? ts.b : (r[k] == r[k] ? r[k] : ts.a));
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) core_locate_fast(ts, a.grid, rc[k], ev[k]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const R* cp = s_cc + (ev[k].kk * 5) * 32 + lane;
+              core_eval(ts, cp[0], cp[32], cp[64], cp[96], cp[128], ev[k]);
+            }
+            R z[2], d[2], dzdr[2], dddr[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { z[k] = ev[k].z; d[k] = ev[k].d; dzdr[k] = ev[k].d; dddr[k] = ev[k].d2; }
+            const bool all_core = code[0] == 2 && code[1] == 2;
+            if (!all_core) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                if (code[k] != 2) {
+                  ChainBoundary<R> cb;
+                  make_boundary(ts, s_cc[(KK * 5 + 0) * 32 + lane], s_cc[(KK * 5 + 1) * 32 + lane],
+                                s_cc[(KK * 5 + 2) * 32 + lane], s_cc[(KK * 5 + 3) * 32 + lane], cb);
+                  const R rr = r[k];
+                  if (code[k] == 1) {
+                    const R poly = rr * ts.a - R(0.5) * rr * rr;
+                    z[k] = (ts.inv_w * poly + cb.dL * (rr - poly * ts.inv_w)) + cb.constL;
+                    const R q = (ts.a - rr) * ts.inv_w;
+                    d[k] = (R(1) - q) * cb.dL + q;
+                    dzdr[k] = d[k]; dddr[k] = (cb.dL - R(1)) * ts.inv_w;
+                  } else if (code[k] == 3) {
+                    const R poly = R(0.5) * rr * rr - rr * ts.b;
+                    z[k] = (ts.inv_w * poly + cb.dR * (rr - poly * ts.inv_w)) + cb.constR;
+                    const R q = (rr - ts.b) * ts.inv_w;
+                    d[k] = (R(1) - q) * cb.dR + q;
+                    dzdr[k] = d[k]; dddr[k] = (R(1) - cb.dR) * ts.inv_w;
+                  } else if (code[k] == 0) {
+                    z[k] = cb.ztailL - (ts.min_eps - rr);
+                    d[k] = R(1); dzdr[k] = R(1); dddr[k] = R(0);
+                  } else {
+                    z[k] = cb.ztailR + (rr - ts.max_eps);
+                    d[k] = R(1); dzdr[k] = R(1); dddr[k] = R(0);
+                  }
+                }
+              }
+            }
+            const R tiny = tiny_of<R>();
+            bool above[2];
+            R dcl[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const bool val = k == 0 || vB;
+              above[k] = d[k] > tiny;
+              dcl[k] = above[k] ? d[k] : tiny;
+              a_z2 += val ? (double)(z[k] * z[k]) : 0.0;
+              a_ls += val ? (double)es[k] : 0.0;
+              if (MODE == kModeLogp) {
+                a_gb0 += val ? (double)einv[k] : 0.0;
+                a_gg0 += val ? (double)r[k] : 0.0;
+                a_gvl += val ? (double)(r[k] * r[k]) : 0.0;
+              }
+              R mant; int ex;
+              split_mant(dcl[k], mant, ex);
+              a_pm *= val ? mant : R(1);
+              a_pe += val ? ex : 0;
+            }
+            if (GRAD) {
+              R lz[2], ld[2];
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const bool val = k == 0 || vB;
+                lz[k] = val ? -z[k] : R(0);
+                ld[k] = (val && above[k]) ? fast_rcp(dcl[k]) : R(0);
+                const R gr = fma(lz[k], dzdr[k], ld[k] * dddr[k]);
+                const R gmu = -gr * einv[k];
+                const R gls = fma(-gr, r[k], R(-1));
+                if (val) {
+                  gb[oo[k] * 64] = gmu;
+                  gb[oo[k] * 64 + 32] = gls;
+                  a_gb0 += (double)gmu;
+                  a_gg0 += (double)gls;
+                }
+              }
+              R w[2][5];
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                core_backward(ts, ev[k], code[k] == 2 ? lz[k] : R(0), code[k] == 2 ? ld[k] : R(0), w[k]);
+              R u0[2], u1[2], u2[2], u3[2], u4[2];
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const bool lastp = ev[k].kk + 1 >= KK;
+                const R w4 = lastp ? R(0) : w[k][4];
+                const R g3 = w[k][3] - w4;
+                u0[k] = (w[k][0] - g3) * sixth + (w[k][2] - w[k][1]) * R(0.5);
+                u1[k] = (R(4) * w[k][0] - w4) * sixth - w[k][2] + g3 * R(0.5);
+                u2[k] = w[k][0] * sixth + (w[k][1] + w[k][2] - g3 + w4) * R(0.5);
+                u3[k] = g3 * sixth - w4 * R(0.5);
+                u4[k] = w4 * sixth;
+              }
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                R* gp = gvp + ev[k].kk * 32;
+                gp[0] += u0[k];
+                gp[32] += u1[k];
+                gp[64] += u2[k];
+                gp[96] += u3[k];
+                gp[128] += u4[k];
+              }
+              if (!all_core) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  if (code[k] != 2 && (k == 0 || vB)) {
+                    const R rr = r[k];
+                    if (code[k] == 1) {
+                      const R q = (ts.a - rr) * ts.inv_w;
+                      a_gvl += (double)lz[k];
+                      a_gdl += (double)fma(lz[k], cL_of(ts, rr), ld[k] * (R(1) - q));
+                    } else if (code[k] == 3) {
+                      const R q = (rr - ts.b) * ts.inv_w;
+                      a_gvr += (double)lz[k];
+                      a_gdr += (double)fma(lz[k], cR_of(ts, rr), ld[k] * (R(1) - q));
+                    } else if (code[k] == 0) {
+                      a_gvl += (double)lz[k];
+                      a_gdl += (double)(lz[k] * cL_of(ts, ts.min_eps));
+                    } else {
+                      a_gvr += (double)lz[k];
+                      a_gdr += (double)(lz[k] * cR_of(ts, ts.max_eps));
+                    }
+                  }
+                }
+              }
+            }
+          }
+          } else
+#endif
+          {
 #pragma unroll kEvalUnroll
           for (int o = uw; o < cnt; o += NU) {
             const R yv = a.y[base + o];
@@ -596,6 +786,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                 }
               }
             }
+          }
           }
           // renormalise the running mantissa product once per tile
           {
