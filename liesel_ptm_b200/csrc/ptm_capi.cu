@@ -42,6 +42,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Plan {
   int CG, M, n_items, grid, NSLOT, To, NU;
+  int TPW, NTW;  // smooth terms per term warp, term warps
   long long chunk_len;
   size_t smem_main;
   size_t off_gamma, off_cc, off_partial, off_xt, off_scratch, total;
@@ -267,8 +268,20 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   // eval warps: fill the CTA up to 20 warps (96 registers per thread; registers are
   // granted per 4 warps), measured best at c3 (T = 10 -> NU = 10); beyond 12 terms up to
   // 28 warps (72 registers; T = 20 -> NU = 8 measured 5 % faster than 4)
-  pl.NU = T <= 12 ? std::min(12, std::max(8, 20 - T)) : std::max(4, std::min(8, 28 - T));
-  if (const char* e = getenv("PTM_NU")) pl.NU = std::max(1, std::min(32 - T, atoi(e)));  // tuning knob
+  // beyond 12 terms a term warp owns two terms (two accumulator sets in registers): T = 20
+  // -> 10 term warps + 6 eval warps = 512 threads at 128 registers, instead of 20 + 8 warps
+  // at 72 (where the eval warps spill)
+  pl.TPW = T > 12 ? 2 : 1;
+  if (const char* e = getenv("PTM_TPW")) pl.TPW = atoi(e) == 2 ? 2 : 1;  // tuning knob
+#if PTM_RESPLIT
+  pl.TPW = 1;
+#endif
+  pl.NTW = (T + pl.TPW - 1) / pl.TPW;
+  if (pl.TPW == 1)
+    pl.NU = T <= 12 ? std::min(12, std::max(8, 20 - T)) : std::max(4, std::min(8, 28 - T));
+  else  // 16 warps (128 registers per thread) while that leaves at least 4 eval warps
+    pl.NU = pl.NTW <= 12 ? std::max(4, 16 - pl.NTW) : 4;
+  if (const char* e = getenv("PTM_NU")) pl.NU = std::max(1, std::min(32 - pl.NTW, atoi(e)));  // tuning knob
   auto smem_for = [&](int To) {
     size_t b = 0;
     b += (size_t)pr->sum_nb * 32 * sizeof(R);                 // gamma [coef][lane]
@@ -316,33 +329,40 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   return pl;
 }
 
-template <typename R, int NB, int MODE, int MAXT>
+template <typename R, int NB, int MODE, int MAXT, int TPW>
 int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
-  auto kern = ptm::k_main<R, NB, MODE, MAXT>;
+  auto kern = ptm::k_main<R, NB, MODE, MAXT, TPW>;
   PTM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_main));
 #if PTM_RESPLIT
   kern<<<pl.grid, 32 * ((T + pl.NU + 3) / 4 * 4), pl.smem_main, st>>>(a);
 #else
-  kern<<<pl.grid, 32 * (T + pl.NU), pl.smem_main, st>>>(a);
+  kern<<<pl.grid, 32 * (pl.NTW + pl.NU), pl.smem_main, st>>>(a);
 #endif
   PTM_CUDA(cudaGetLastError());
   return PTM_OK;
 }
 
-// CTA = T term warps + NU eval warps (c3: 18 warps, 96 registers per thread); the
-// 1024-thread variant covers up to 24 terms.
+// CTA = term warps + NU eval warps (c3: 10 + 10 warps, 96 registers per thread); with two
+// terms per term warp (T > 12) 512 threads at 128 registers cover up to 24 terms.
 template <typename R, int NB, int MODE>
 int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
-  // registers are granted per 4 warps: <= 16 warps -> 128/thread, 20 -> 96, 24 -> 80, 32 -> 64
+  // registers are granted per 4 warps: <= 16 warps -> 128/thread, 18 -> 112, 20 -> 96, 24 -> 80, 32 -> 64
 #if PTM_RESPLIT
   const int threads = 32 * ((T + pl.NU + 3) / 4 * 4);
 #else
-  const int threads = 32 * (T + pl.NU);
+  const int threads = 32 * (pl.NTW + pl.NU);
 #endif
-  if (threads <= 512) return launch_main_t<R, NB, MODE, 512>(a, pl, T, st);
-  if (threads <= 640) return launch_main_t<R, NB, MODE, 640>(a, pl, T, st);
-  if (threads <= 768) return launch_main_t<R, NB, MODE, 768>(a, pl, T, st);
-  return launch_main_t<R, NB, MODE, 1024>(a, pl, T, st);
+  if (pl.TPW == 2) {
+#if !PTM_RESPLIT
+    if (threads <= 512) return launch_main_t<R, NB, MODE, 512, 2>(a, pl, T, st);
+    if (threads <= 640) return launch_main_t<R, NB, MODE, 640, 2>(a, pl, T, st);
+    return launch_main_t<R, NB, MODE, 768, 2>(a, pl, T, st);
+#endif
+  }
+  if (threads <= 512) return launch_main_t<R, NB, MODE, 512, 1>(a, pl, T, st);
+  if (threads <= 640) return launch_main_t<R, NB, MODE, 640, 1>(a, pl, T, st);
+  if (threads <= 768) return launch_main_t<R, NB, MODE, 768, 1>(a, pl, T, st);
+  return launch_main_t<R, NB, MODE, 1024, 1>(a, pl, T, st);
 }
 
 template <typename R>
@@ -397,7 +417,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   const Plan pl = make_plan<R>(pr, C);
   if (ws_bytes < pl.total) return fail(PTM_ERR_WORKSPACE, "workspace too small");
   if (pl.smem_main > 227 * 1024) return fail(PTM_ERR_SHAPE, "shared-memory budget exceeded");
-  if (pr->T + pl.NU > 32) return fail(PTM_ERR_SHAPE, "too many smooth terms for one CTA");
+  if (pl.NTW + pl.NU > 32) return fail(PTM_ERR_SHAPE, "too many smooth terms for one CTA");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   char* wsb = reinterpret_cast<char*>(ws);
   R* Gamma = reinterpret_cast<R*>(wsb + pl.off_gamma);
@@ -472,7 +492,7 @@ int pointwise_impl(const PtmProblem* pr, const R* params, long long S, R* lppd, 
   const size_t need = pl.total + (size_t)pr->n * 4 * sizeof(double);
   if (ws_bytes < need) return fail(PTM_ERR_WORKSPACE, "workspace too small (see ptm_pointwise_workspace_bytes)");
   if (pl.smem_main > 227 * 1024) return fail(PTM_ERR_SHAPE, "shared-memory budget exceeded");
-  if (pr->T + pl.NU > 32) return fail(PTM_ERR_SHAPE, "too many smooth terms for one CTA");
+  if (pl.NTW + pl.NU > 32) return fail(PTM_ERR_SHAPE, "too many smooth terms for one CTA");
   const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
   if (len == 0) return PTM_OK;
   // one CTA per observation chunk, all sample groups of a chunk on the same CTA:

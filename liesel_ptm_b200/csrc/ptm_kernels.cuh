@@ -81,6 +81,9 @@ constexpr int kTermUnroll = PTM_TERM_UNROLL;
 #ifndef PTM_EVAL_PAIR
 #define PTM_EVAL_PAIR 0
 #endif
+#ifndef PTM_PAIR_TPW2
+#define PTM_PAIR_TPW2 0  // measured: 26.3 ms with, 25.7 ms without (c5 shape, per-GPU slice of 2M)
+#endif
 #ifndef PTM_EVAL_UNROLL
 #define PTM_EVAL_UNROLL 1
 #endif
@@ -222,10 +225,16 @@ __device__ __forceinline__ void store4(float* p, const float (&b)[4]) {
 // (per-observation log-density reduced over the chains of the CTA: lppd / WAIC records).
 constexpr int kModeLogp = 0, kModeGrad = 1, kModePoint = 2;
 
-template <typename R, int NB, int MODE, int MAXTHREADS>
+template <typename R, int NB, int MODE, int MAXTHREADS, int TPW = 1>
 __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
+  // TPW = smooth terms per term warp: 1 up to 12 terms; 2 beyond (the CTA then has
+  // ceil(T/2) term warps with two accumulator sets each, which leaves room for eval warps
+  // at their full register budget)
+  static_assert(TPW == 1 || TPW == 2, "one or two terms per term warp");
+  static_assert(!(PTM_RESPLIT && TPW > 1), "the register re-split experiment is single-term only");
   constexpr bool GRAD = MODE == kModeGrad;
   constexpr bool POINT = MODE == kModePoint;
+  constexpr bool kPair = (PTM_EVAL_PAIR != 0) || PTM_PAIR_TPW2 && TPW == 2;  // lockstep pairs in the eval warps
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -252,29 +261,38 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   const int uw = warp;       // eval warp index when warp < NU
   const int tq = warp - NU;  // term slot
 #else
-  const bool is_term = warp < T;
+  const int NTW = (T + TPW - 1) / TPW;  // term warps
+  const bool is_term = warp < NTW;
   constexpr bool is_pad = false;
-  const int uw = warp - T;  // eval warp index when !is_term
-  const int tq = warp;      // term slot
+  const int uw = warp - NTW;  // eval warp index when !is_term
+  const int tq = warp;        // term warp index: owns the staging slots q = tq * TPW + k
 #endif
 
-  // term-warp constants
-  int t_nb = 0, t_pred = 0;
-  R t_invdk = R(0);
-  const R* t_x = nullptr;
-  const int term = is_term ? a.order[tq] : 0;  // staging / hand-off are indexed by warp (= q)
-  if (is_term) {
-    t_nb = a.nb[term];
-    t_pred = a.pred[term];
-    t_invdk = a.inv_dk[term];
-    t_x = a.X + (long long)term * a.n;
-    R* kn = s_kn + tq * 4 * kKnotStride;
-    const R* gk = a.knots + term * kKnotStride;
-    for (int i = lane; i < t_nb + 4; i += 32) {
-      kn[i] = gk[i];
-      kn[kKnotStride + i] = i + 1 < t_nb + 4 ? R(1) / (gk[i + 1] - gk[i]) : R(0);
-      kn[2 * kKnotStride + i] = i + 2 < t_nb + 4 ? R(1) / (gk[i + 2] - gk[i]) : R(0);
-      kn[3 * kKnotStride + i] = i + 3 < t_nb + 4 ? R(1) / (gk[i + 3] - gk[i]) : R(0);
+  // term-warp constants (per owned term k)
+  int t_nb[TPW], t_pred[TPW], t_term[TPW];
+  bool t_has[TPW];
+  R t_invdk[TPW];
+  const R* t_x[TPW];
+#pragma unroll
+  for (int k = 0; k < TPW; ++k) {
+    const int q = tq * TPW + k;
+    t_has[k] = is_term && q < T;
+    t_term[k] = t_has[k] ? a.order[q] : 0;  // staging / hand-off are indexed by q
+    t_nb[k] = 0; t_pred[k] = 0; t_invdk[k] = R(0); t_x[k] = nullptr;
+    if (t_has[k]) {
+      const int term = t_term[k];
+      t_nb[k] = a.nb[term];
+      t_pred[k] = a.pred[term];
+      t_invdk[k] = a.inv_dk[term];
+      t_x[k] = a.X + (long long)term * a.n;
+      R* kn = s_kn + q * 4 * kKnotStride;
+      const R* gk = a.knots + term * kKnotStride;
+      for (int i = lane; i < t_nb[k] + 4; i += 32) {
+        kn[i] = gk[i];
+        kn[kKnotStride + i] = i + 1 < t_nb[k] + 4 ? R(1) / (gk[i + 1] - gk[i]) : R(0);
+        kn[2 * kKnotStride + i] = i + 2 < t_nb[k] + 4 ? R(1) / (gk[i + 2] - gk[i]) : R(0);
+        kn[3 * kKnotStride + i] = i + 3 < t_nb[k] + 4 ? R(1) / (gk[i + 3] - gk[i]) : R(0);
+      }
     }
   }
   const TrafoScal<R> ts = a.ts;
@@ -299,37 +317,52 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
     double* pout = a.partial + (long long)item * a.NSLOT * 32;
 
       // =========================== term warp ========================================
-      // this term's spline coefficients of the 32 chains -> shared [coef][lane]
-      for (int j = 0; j < t_nb; ++j)
-        s_gam[(a.goff[term] + j) * 32 + lane] = a.Gamma[((long long)term * kMaxNbases + j) * a.C + chain];
-      R acc[GRAD ? NB : 1];
+      // the owned terms' spline coefficients of the 32 chains -> shared [coef][lane]
+#pragma unroll
+      for (int k = 0; k < TPW; ++k)
+        if (t_has[k])
+          for (int j = 0; j < t_nb[k]; ++j)
+            s_gam[(a.goff[t_term[k]] + j) * 32 + lane] =
+                a.Gamma[((long long)t_term[k] * kMaxNbases + j) * a.C + chain];
+      R acc[TPW][GRAD ? NB : 1];
       // float kernel: the register accumulators are flushed into doubles every 8 tiles so
       // that a chunk of ~10^4..10^5 observations does not accumulate float round-off
       constexpr bool kFlush = GRAD && sizeof(R) == 4;
-      double dacc[kFlush ? NB : 1];
+      double dacc[TPW][kFlush ? NB : 1];
       if constexpr (GRAD) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) acc[j] = R(0);
+        for (int k = 0; k < TPW; ++k)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) acc[k][j] = R(0);
       }
       if constexpr (kFlush) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) dacc[j] = 0.0;
+        for (int k = 0; k < TPW; ++k)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) dacc[k][j] = 0.0;
       }
-      const R* kn = s_kn + tq * 4 * kKnotStride;
-      const int goff32 = a.goff[term] * 32;
+      int goff32[TPW];
+#pragma unroll
+      for (int k = 0; k < TPW; ++k) goff32[k] = a.goff[t_has[k] ? t_term[k] : t_term[0]] * 32;
       auto stage = [&](int tile) {
         const long long base = o_begin + (long long)tile * To;
         const int slot = tile % 3;
-        R* bst = s_b + ((tq * 3 + slot) * To) * 4;
-        int* jst = s_j + (tq * 3 + slot) * To;
-        for (int o = lane; o < To; o += 32) {
-          const long long gi = base + o;
-          if (gi < o_end) {
-            R bb[4];
-            const int jj = basis_window_fast(t_x[gi], kn, kn + kKnotStride, kn + 2 * kKnotStride,
-                                             kn + 3 * kKnotStride, t_nb, t_invdk, bb);
-            store4(bst + o * 4, bb);
-            jst[o] = goff32 + jj * 32;  // row offset into the shared gamma table
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+          if (!t_has[k]) continue;
+          const int q = tq * TPW + k;
+          const R* kn = s_kn + q * 4 * kKnotStride;
+          R* bst = s_b + ((q * 3 + slot) * To) * 4;
+          int* jst = s_j + (q * 3 + slot) * To;
+          for (int o = lane; o < To; o += 32) {
+            const long long gi = base + o;
+            if (gi < o_end) {
+              R bb[4];
+              const int jj = basis_window_fast(t_x[k][gi], kn, kn + kKnotStride, kn + 2 * kKnotStride,
+                                               kn + 3 * kKnotStride, t_nb[k], t_invdk[k], bb);
+              store4(bst + o * 4, bb);
+              jst[o] = goff32[k] + jj * 32;  // row offset into the shared gamma table
+            }
           }
         }
       };
@@ -343,34 +376,59 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             const int tile = s - 1;
             const long long base = o_begin + (long long)tile * To;
             const int slot = tile % 3;
-            const R* bp = s_b + ((tq * 3 + slot) * To) * 4;
-            const int* jp = s_j + (tq * 3 + slot) * To;
-            const R* hp = s_g + (((tile & 1) * To) * 2 + t_pred) * 32 + lane;
             const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
+            if constexpr (TPW == 1) {
+              const R* bp = s_b + ((tq * 3 + slot) * To) * 4;
+              const int* jp = s_j + (tq * 3 + slot) * To;
+              const R* hp = s_g + (((tile & 1) * To) * 2 + t_pred[0]) * 32 + lane;
 #pragma unroll 2
-            for (int o = 0; o < cnt; ++o, bp += 4, ++jp, hp += 64) {
-              R b0, b1, b2, b3;
-              load4(bp, b0, b1, b2, b3);
-              Dispatch<R, NB>::scatter(acc, (*jp - goff32) >> 5, b0, b1, b2, b3, *hp);
+              for (int o = 0; o < cnt; ++o, bp += 4, ++jp, hp += 64) {
+                R b0, b1, b2, b3;
+                load4(bp, b0, b1, b2, b3);
+                Dispatch<R, NB>::scatter(acc[0], (*jp - goff32[0]) >> 5, b0, b1, b2, b3, *hp);
+              }
+            } else {
+              // two owned terms per observation: two independent dispatches in flight
+              const int qA = tq * TPW, qB = t_has[TPW - 1] ? qA + 1 : qA;
+              const R* bpA = s_b + ((qA * 3 + slot) * To) * 4;
+              const R* bpB = s_b + ((qB * 3 + slot) * To) * 4;
+              const int* jpA = s_j + (qA * 3 + slot) * To;
+              const int* jpB = s_j + (qB * 3 + slot) * To;
+              const R* hpA = s_g + (((tile & 1) * To) * 2 + t_pred[0]) * 32 + lane;
+              const R* hpB = s_g + (((tile & 1) * To) * 2 + t_pred[TPW - 1]) * 32 + lane;
+              const bool hasB = t_has[TPW - 1];
+              for (int o = 0; o < cnt; ++o, bpA += 4, bpB += 4, ++jpA, ++jpB, hpA += 64, hpB += 64) {
+                R b0, b1, b2, b3, c0, c1, c2, c3;
+                load4(bpA, b0, b1, b2, b3);
+                load4(bpB, c0, c1, c2, c3);
+                const R hA = *hpA;
+                const R hB = hasB ? *hpB : R(0);
+                Dispatch<R, NB>::scatter(acc[0], (*jpA - goff32[0]) >> 5, b0, b1, b2, b3, hA);
+                Dispatch<R, NB>::scatter(acc[TPW - 1], (*jpB - goff32[TPW - 1]) >> 5, c0, c1, c2, c3, hB);
+              }
             }
           }
         }
         if constexpr (kFlush) {
           if ((s & 7) == 7) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j) { dacc[j] += (double)acc[j]; acc[j] = R(0); }
+            for (int k = 0; k < TPW; ++k)
+#pragma unroll
+              for (int j = 0; j < NB; ++j) { dacc[k][j] += (double)acc[k][j]; acc[k][j] = R(0); }
           }
         }
         cta_bar();
       }
       if constexpr (GRAD) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j)
-          if (j < t_nb) {
-            double v = (double)acc[j];
-            if constexpr (kFlush) v += dacc[j];
-            pout[(kRegSlots + NGV + a.goff[term] + j) * 32 + lane] = v;
-          }
+        for (int k = 0; k < TPW; ++k)
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            if (t_has[k] && j < t_nb[k]) {
+              double v = (double)acc[k][j];
+              if constexpr (kFlush) v += dacc[k][j];
+              pout[(kRegSlots + NGV + a.goff[t_term[k]] + j) * 32 + lane] = v;
+            }
       }
     cta_bar();
     cta_bar();
@@ -436,8 +494,9 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
           const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
           // (interleaving two observations per warp by unrolling was measured slower: the
           //  extra live values push the eval warps over their 96-register budget)
-#if PTM_EVAL_PAIR
-          if constexpr (!POINT) {
+          // (PTM_EVAL_PAIR forces it everywhere; by default only the two-terms-per-warp
+          //  layout, whose 16-warp CTAs have 128 registers per thread, uses it)
+          if constexpr (kPair && !POINT) {
           // Two observations per eval warp in lockstep (o0 and o0 + NU): every straight-line
           // stage below carries both, so the scheduler can overlap their dependency chains.
           for (int o0 = uw; o0 < cnt; o0 += 2 * NU) {
@@ -620,7 +679,6 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             }
           }
           } else
-#endif
           {
 #pragma unroll kEvalUnroll
           for (int o = uw; o < cnt; o += NU) {

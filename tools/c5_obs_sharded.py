@@ -29,6 +29,7 @@ ap.add_argument("--n", type=int, default=50_000_000)
 ap.add_argument("--chains", type=int, default=128)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
 args = ap.parse_args()
 
 rank = int(os.environ.get("RANK", 0))
@@ -39,22 +40,25 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
 n_loc = n_scale = 10
+F32 = args.dtype == "f32"
+DT = np.float32 if F32 else np.float64
 T, nbases, C = n_loc + n_scale, 20, args.chains
 lo, hi = parallel.obs_shard(args.n, world, rank)
 n_local = hi - lo
 
 # common subsample -> response map, knots, Z, K (identical on every rank)
 y_sub, X_sub = bw.make_data(200_000, n_loc, n_scale, seed=1234)
-bases = [lp.ps(X_sub[t], nbases=nbases, xname=f"x{t}", knots=lp.equidistant_knots(np.array([-2.0, 2.0]), nbases))
+bases = [lp.ps(X_sub[t].astype(DT), nbases=nbases, xname=f"x{t}", dtype=DT,
+               knots=lp.equidistant_knots(np.array([-2.0, 2.0]), nbases, dtype=DT))
          for t in range(T)]
 
 # this rank's slice (own seed); same generator as the other configs, response mapped by its
 # own quantiles (synthetic data: only the shapes and value ranges matter)
 y, X = bw.make_data(n_local, n_loc, n_scale, seed=100 + rank)
 X = np.clip(X, -2.0 + 1e-9, 2.0 - 1e-9)
-model = lp.LocScalePTM.new_ptm(y, nparam=20, to_float32=False, device=f"cuda:{local}")
+model = lp.LocScalePTM.new_ptm(y.astype(DT), nparam=20, to_float32=F32, device=f"cuda:{local}")
 for t in range(T):
-    b = lp.Basis(x=X[t], xname=f"x{t}", knots=bases[t].knots, Z=bases[t].Z, penalty=bases[t].penalty, nbases=nbases)
+    b = lp.Basis(x=X[t].astype(DT), xname=f"x{t}", knots=bases[t].knots, Z=bases[t].Z, penalty=bases[t].penalty, nbases=nbases)
     tm = lp.term.f_ig(b, fname="f" if t < n_loc else "g")
     if t < n_loc:
         model.loc += tm
@@ -65,14 +69,14 @@ model.set_shard(0, n_local, add_priors=(rank == 0))
 del X
 
 # chain states: identical on every rank (seeded), small so that every term has sd ~ 0.1
-sub_model = lp.LocScalePTM.new_ptm(y_sub, nparam=20, to_float32=False, device=f"cuda:{local}")
+sub_model = lp.LocScalePTM.new_ptm(y_sub.astype(DT), nparam=20, to_float32=F32, device=f"cuda:{local}")
 for t in range(T):
     tm = lp.term.f_ig(bases[t], fname="f" if t < n_loc else "g")
     if t < n_loc:
         sub_model.loc += tm
     else:
         sub_model.scale += tm
-params = torch.from_numpy(bw.make_states(sub_model, C, seed=7)).cuda()
+params = torch.from_numpy(bw.make_states(sub_model, C, seed=7).astype(DT)).cuda()
 P = params.shape[1]
 
 
