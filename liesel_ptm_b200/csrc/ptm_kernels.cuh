@@ -81,6 +81,9 @@ constexpr int kTermUnroll = PTM_TERM_UNROLL;
 #ifndef PTM_EVAL_PAIR
 #define PTM_EVAL_PAIR 0
 #endif
+#ifndef PTM_BWD_PREFETCH
+#define PTM_BWD_PREFETCH 0  // measured neutral at c3 (41.9 vs 41.6 ms): the term warps are not critical there
+#endif
 #ifndef PTM_PAIR_TPW2
 #define PTM_PAIR_TPW2 0  // measured: 26.3 ms with, 25.7 ms without (c5 shape, per-GPU slice of 2M)
 #endif
@@ -381,12 +384,33 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               const R* bp = s_b + ((tq * 3 + slot) * To) * 4;
               const int* jp = s_j + (tq * 3 + slot) * To;
               const R* hp = s_g + (((tile & 1) * To) * 2 + t_pred[0]) * 32 + lane;
+#if PTM_BWD_PREFETCH
+              // experiment: the operands of observation o+1 are loaded before the
+              // dispatch of observation o (an indirect branch the loads cannot cross), which
+              // takes the shared-memory latency off the term warp's critical path.  Reading
+              // one entry past the tile stays inside the shared-memory carve-up.
+              R n0, n1, n2, n3;
+              load4(bp, n0, n1, n2, n3);
+              int nj = (*jp - goff32[0]) >> 5;
+              R nh = *hp;
+#pragma unroll 2
+              for (int o = 0; o < cnt; ++o) {
+                const R b0 = n0, b1 = n1, b2 = n2, b3 = n3, h = nh;
+                const int j = nj;
+                bp += 4; ++jp; hp += 64;
+                load4(bp, n0, n1, n2, n3);
+                nj = (*jp - goff32[0]) >> 5;
+                nh = *hp;
+                Dispatch<R, NB>::scatter(acc[0], j, b0, b1, b2, b3, h);
+              }
+#else
 #pragma unroll 2
               for (int o = 0; o < cnt; ++o, bp += 4, ++jp, hp += 64) {
                 R b0, b1, b2, b3;
                 load4(bp, b0, b1, b2, b3);
                 Dispatch<R, NB>::scatter(acc[0], (*jp - goff32[0]) >> 5, b0, b1, b2, b3, *hp);
               }
+#endif
             } else {
               // two owned terms per observation: two independent dispatches in flight
               const int qA = tq * TPW, qB = t_has[TPW - 1] ? qA + 1 : qA;
