@@ -649,3 +649,30 @@ def test_random_shapes_fuzz():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "'ok': 30" in r.stdout
 
+
+
+def test_many_terms_pointwise_and_f32():
+    """Two terms per term warp (T > 12) in the pointwise mode and in the float kernel
+    (whose register accumulators are flushed into doubles), odd and even term counts."""
+    case = build_case(n=1200, C=9, n_loc=7, n_scale=6, nbases=10)
+    ll, lppd_ref, p_ref = _oracle_pointwise(case.omodel, case.state, 9)
+    lppd, pwaic = case.model.pointwise(torch.from_numpy(case.params).cuda())
+    assert rel_err(lppd.cpu().numpy(), lppd_ref) < 1e-12
+    assert np.allclose(pwaic.cpu().numpy(), p_ref, rtol=1e-9, atol=1e-13 * max(1.0, float(np.abs(ll).max()) ** 2))
+    for n_loc, n_scale in [(7, 6), (10, 10)]:
+        case = build_case(n=900, n_loc=n_loc, n_scale=n_scale, nbases=10, nparam=20, C=5, dtype=np.float32)
+        lp, g, lp_only = _eval(case)
+        om32 = case.omodel
+        terms = [o.term_from_reparam(t.x.astype(np.float64), t.knots.astype(np.float64), t.Z.astype(np.float64),
+                                     t.K.astype(np.float64), t.rank, t.predictor) for t in om32.terms]
+        om = o.PTMModel(om32.y.astype(np.float64), terms, nparam=20)
+        om.spline = o.PTMSpline(om32.knots.knots.astype(np.float64))
+        om.Zd = om32.Zd.astype(np.float64)
+        st = golden_io.state_from_params(om, case.params.astype(np.float64), case.layout)
+        lp_ref, gd = om.logp_and_grad(st)
+        from tests.helpers import pack_grad
+
+        g_ref = pack_grad(case, gd)
+        assert rel_err(lp, lp_ref) < 1e-5 and rel_err(lp_only, lp_ref) < 1e-5
+        for c in range(5):
+            assert rel_err(g[c], g_ref[c]) < 1e-5
