@@ -25,6 +25,7 @@
 // 167-301); the exact inverse is inside that band.
 #pragma once
 #include "ptm_math.cuh"
+#include "ptm_kernels.cuh"  // fast_exp
 
 namespace ptm {
 
@@ -308,8 +309,7 @@ __global__ void __launch_bounds__(kPredThreads) k_predict_obs(const PredictArgs<
         const R rq = trafo_inverse(ts, s_cb[g], Hall + (long long)(s0 + g) * kGridN, a.grid, zq);
         a.out_q[oi] = inside ? fma(exp(es), rq, em) : nan;
       } else {
-        const R sd = exp(es);
-        const R r = (yv - em) / sd;  // dist.py:735-736
+        const R r = (yv - em) * fast_exp(-es);  // dist.py:735-736, as in the fused sweep
         R z, d;
         trafo_forward(ts, s_cb[g], pc, a.grid, r, z, d);
         if (!(r == r) || !inside) { z = nan; d = nan; }
