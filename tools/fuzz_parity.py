@@ -12,6 +12,8 @@ for k in range(ncase):
     n = int(rng.choice([1, 2, 3, 17, 40, 41, 79, 80, 81, 333, 1000, 2049, 7001]))
     C = int(rng.choice([1, 2, 31, 32, 33, 64, 65, 129]))
     n_loc, n_scale = int(rng.integers(0, 5)), int(rng.integers(0, 4))
+    if rng.uniform() < 0.3:  # more than 12 terms: two terms per term warp
+        n_loc, n_scale = int(rng.integers(6, 13)), int(rng.integers(5, 13))
     nb = int(rng.choice([6, 8, 12, 20, 21, 30]))
     dt = np.float64 if rng.uniform() < 0.7 else np.float32
     case = build_case(n=n, C=C, n_loc=n_loc, n_scale=n_scale, nbases=nb, dtype=dt)
