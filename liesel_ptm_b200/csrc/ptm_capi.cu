@@ -297,6 +297,12 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   pl.To = 4 * pl.NU;  // four observations per eval warp and tile
   if (const char* e = getenv("PTM_TO")) pl.To = std::max(8, atoi(e));  // tuning knob
   while (pl.To > 8 && smem_for(pl.To) > 227 * 1024) pl.To -= 4;
+  // large coefficient tables (many terms x many bases): give up eval warps (their private
+  // gradient tables) before giving up
+  while (pl.NU > 4 && smem_for(pl.To) > 227 * 1024) {
+    --pl.NU;
+    pl.To = std::max(8, std::min(pl.To, 4 * pl.NU));
+  }
   pl.smem_main = smem_for(pl.To);
   const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
   long long per_sm = 8;  // work items per CTA: amortises the per-item table loads, keeps the tail short
