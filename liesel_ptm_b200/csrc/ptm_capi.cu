@@ -64,6 +64,10 @@ struct PtmProblem {
   int dz_off = 0, tau_off = 0, taud_off = 0;
   long long obs_begin = 0, obs_end = 0;
   int add_priors = 1;
+  // every scale term k evaluates the same design (covariate, knots) as location term k:
+  // twin[q] = scale term paired with the q-th location term (staged and dispatched once)
+  int shared = 0;
+  int twin[ptm::kMaxTerms] = {0};
   int num_sms = 148;
   int device = 0;
   // device buffers (element type by dtype)
@@ -148,6 +152,22 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
   }
   pr->sum_nb = go;
   pr->T = T;
+  // shared designs: the k-th scale term has the same covariate values, knots and basis count
+  // as the k-th location term (the usual "same covariates in both predictors" model)
+  pr->shared = 0;
+  if (pr->T_loc == pr->T_scale && pr->T_loc > 0 && !getenv("PTM_NO_SHARED")) {
+    std::vector<int> loc, sc;
+    for (int t = 0; t < T; ++t) (d->predictor[t] == PTM_LOC ? loc : sc).push_back(t);
+    bool ok = true;
+    for (size_t k = 0; k < loc.size() && ok; ++k) {
+      const int a = loc[k], b = sc[k];
+      ok = pr->nb[a] == pr->nb[b] &&
+           memcmp(d->knots[a], d->knots[b], (size_t)(pr->nb[a] + 4) * sizeof(R)) == 0 &&
+           (d->x[a] == d->x[b] || memcmp(d->x[a], d->x[b], (size_t)n * sizeof(R)) == 0);
+      pr->twin[k] = b;
+    }
+    pr->shared = ok ? 1 : 0;
+  }
   pr->n = n;
   pr->nparam = d->nparam;
   pr->J = d->nparam + 1;
@@ -271,10 +291,10 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   // beyond 12 terms a term warp owns two terms (two accumulator sets in registers): T = 20
   // -> 10 term warps + 6 eval warps = 512 threads at 128 registers, instead of 20 + 8 warps
   // at 72 (where the eval warps spill)
-  pl.TPW = T > 12 ? 2 : 1;
-  if (const char* e = getenv("PTM_TPW")) pl.TPW = atoi(e) == 2 ? 2 : 1;  // tuning knob
+  pl.TPW = (T > 12 || pr->shared) ? 2 : 1;
+  if (const char* e = getenv("PTM_TPW")) pl.TPW = (atoi(e) == 2 || pr->shared) ? 2 : 1;  // tuning knob
 #if PTM_RESPLIT
-  pl.TPW = 1;
+  pl.TPW = pr->shared ? 2 : 1;  // (the re-split experiment cannot run shared designs)
 #endif
   pl.NTW = (T + pl.TPW - 1) / pl.TPW;
   if (pl.TPW == 1)
@@ -335,9 +355,9 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   return pl;
 }
 
-template <typename R, int NB, int MODE, int MAXT, int TPW>
+template <typename R, int NB, int MODE, int MAXT, int TPW, bool SHARED = false>
 int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
-  auto kern = ptm::k_main<R, NB, MODE, MAXT, TPW>;
+  auto kern = ptm::k_main<R, NB, MODE, MAXT, TPW, SHARED>;
   PTM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_main));
 #if PTM_RESPLIT
   kern<<<pl.grid, 32 * ((T + pl.NU + 3) / 4 * 4), pl.smem_main, st>>>(a);
@@ -349,7 +369,8 @@ int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t
 }
 
 // CTA = term warps + NU eval warps (c3: 10 + 10 warps, 96 registers per thread); with two
-// terms per term warp (T > 12) 512 threads at 128 registers cover up to 24 terms.
+// terms per term warp (T > 12, or shared designs) 512 threads at 128 registers cover up to
+// 24 terms.
 template <typename R, int NB, int MODE>
 int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
   // registers are granted per 4 warps: <= 16 warps -> 128/thread, 18 -> 112, 20 -> 96, 24 -> 80, 32 -> 64
@@ -360,6 +381,10 @@ int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t s
 #endif
   if (pl.TPW == 2) {
 #if !PTM_RESPLIT
+    if (a.shared) {
+      if (threads <= 512) return launch_main_t<R, NB, MODE, 512, 2, true>(a, pl, T, st);
+      return launch_main_t<R, NB, MODE, 640, 2, true>(a, pl, T, st);
+    }
     if (threads <= 512) return launch_main_t<R, NB, MODE, 512, 2>(a, pl, T, st);
     if (threads <= 640) return launch_main_t<R, NB, MODE, 640, 2>(a, pl, T, st);
     return launch_main_t<R, NB, MODE, 768, 2>(a, pl, T, st);
@@ -391,6 +416,18 @@ void fill_main_args(const PtmProblem* pr, const Plan& pl, long long C, R* Gamma,
     int q = 0;
     for (int t = 0; t < pr->T; ++t) if (pr->pred[t] == PTM_LOC) ma.order[q++] = t;
     for (int t = 0; t < pr->T; ++t) if (pr->pred[t] == PTM_SCALE) ma.order[q++] = t;
+  }
+  ma.shared = pr->shared;
+  if (pr->shared) {
+    // slots 2k / 2k+1 = location term k and its twin: one term warp, one staged design
+    int k = 0;
+    for (int t = 0; t < pr->T; ++t)
+      if (pr->pred[t] == PTM_LOC) {
+        ma.order[2 * k] = t;
+        ma.order[2 * k + 1] = pr->twin[k];
+        ma.dgo[k] = (pr->goff[pr->twin[k]] - pr->goff[t]) * 32;
+        ++k;
+      }
   }
   for (int t = 0; t < pr->T; ++t) {
     ma.nb[t] = pr->nb[t]; ma.pred[t] = pr->pred[t];

@@ -57,6 +57,8 @@ struct MainArgs {
   int pred[kMaxTerms];
   int goff[kMaxTerms];   // offset of the term's block in the packed coefficient tables
   int order[kMaxTerms];  // term indices, location terms first: term warp q owns term order[q]
+  int shared;            // shared designs: order = [loc 0, twin 0, loc 1, twin 1, ...]
+  int dgo[kMaxTerms];    // shared designs: (goff[twin k] - goff[loc k]) * 32
   R inv_dk[kMaxTerms];
   TrafoScal<R> ts;
 };
@@ -228,8 +230,14 @@ __device__ __forceinline__ void store4(float* p, const float (&b)[4]) {
 // (per-observation log-density reduced over the chains of the CTA: lppd / WAIC records).
 constexpr int kModeLogp = 0, kModeGrad = 1, kModePoint = 2;
 
-template <typename R, int NB, int MODE, int MAXTHREADS, int TPW = 1>
+template <typename R, int NB, int MODE, int MAXTHREADS, int TPW = 1, bool SHARED = false>
 __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
+  // SHARED (with TPW = 2): the two terms of a term warp evaluate the same design (a
+  // location term and the scale term on the same covariate and knots); the design is staged
+  // once (slot 2 tq), the eval warps read its values once for both predictors and the
+  // backward loads them once for both accumulator sets.
+  static_assert(!SHARED || TPW == 2, "shared designs pair a location and a scale term");
+  static_assert(!(SHARED && (PTM_EVAL_PAIR || PTM_PAIR_TPW2)), "the lockstep-pair experiment has no shared-design gather");
   // TPW = smooth terms per term warp: 1 up to 12 terms; 2 beyond (the CTA then has
   // ceil(T/2) term warps with two accumulator sets each, which leaves room for eval warps
   // at their full register budget)
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
         const int slot = tile % 3;
 #pragma unroll
         for (int k = 0; k < TPW; ++k) {
-          if (!t_has[k]) continue;
+          if (!t_has[k] || (SHARED && k > 0)) continue;
           const int q = tq * TPW + k;
           const R* kn = s_kn + q * 4 * kKnotStride;
           R* bst = s_b + ((q * 3 + slot) * To) * 4;
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
 #endif
             } else {
               // two owned terms per observation: two independent dispatches in flight
-              const int qA = tq * TPW, qB = t_has[TPW - 1] ? qA + 1 : qA;
+              const int qA = tq * TPW, qB = (t_has[TPW - 1] && !SHARED) ? qA + 1 : qA;
               const R* bpA = s_b + ((qA * 3 + slot) * To) * 4;
               const R* bpB = s_b + ((qB * 3 + slot) * To) * 4;
               const int* jpA = s_j + (qA * 3 + slot) * To;
@@ -421,6 +429,17 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               const R* hpA = s_g + (((tile & 1) * To) * 2 + t_pred[0]) * 32 + lane;
               const R* hpB = s_g + (((tile & 1) * To) * 2 + t_pred[TPW - 1]) * 32 + lane;
               const bool hasB = t_has[TPW - 1];
+              if constexpr (SHARED) {
+                // one set of staged values and one interval for both accumulator sets
+                for (int o = 0; o < cnt; ++o, bpA += 4, ++jpA, hpA += 64, hpB += 64) {
+                  R b0, b1, b2, b3;
+                  load4(bpA, b0, b1, b2, b3);
+                  const int jj = (*jpA - goff32[0]) >> 5;
+                  const R hA = *hpA, hB = *hpB;
+                  Dispatch<R, NB>::scatter(acc[0], jj, b0, b1, b2, b3, hA);
+                  Dispatch<R, NB>::scatter(acc[TPW - 1], jj, b0, b1, b2, b3, hB);
+                }
+              } else
               for (int o = 0; o < cnt; ++o, bpA += 4, bpB += 4, ++jpA, ++jpB, hpA += 64, hpB += 64) {
                 R b0, b1, b2, b3, c0, c1, c2, c3;
                 load4(bpA, b0, b1, b2, b3);
@@ -716,6 +735,24 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               const R* gl = s_gam + lane;
               const int qstep = 3 * To;
               int q = 0;
+              if constexpr (SHARED) {
+                // design k lives in staging slot 2k: its values and interval serve the
+                // location term and, dgo[k] rows further down the table, its scale twin
+                const int D = T >> 1;
+#pragma unroll kTermUnroll
+                for (; q < D; ++q, bq += 2 * qstep * 4, jq += 2 * qstep) {
+                  R b0, b1, b2, b3;
+                  load4(bq, b0, b1, b2, b3);
+                  const R* gp = gl + *jq;
+                  const R* gs = gp + a.dgo[q];
+                  R f = b0 * gp[0], h = b0 * gs[0];
+                  f = fma(b1, gp[32], f); h = fma(b1, gs[32], h);
+                  f = fma(b2, gp[64], f); h = fma(b2, gs[64], h);
+                  f = fma(b3, gp[96], f); h = fma(b3, gs[96], h);
+                  em += f;
+                  es += h;
+                }
+              } else {
 #pragma unroll kTermUnroll
               for (; q < a.T_loc; ++q, bq += qstep * 4, jq += qstep) {
                 R b0, b1, b2, b3;
@@ -737,6 +774,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                 f = fma(b2, gp[64], f);
                 f = fma(b3, gp[96], f);
                 es += f;
+              }
               }
             }
             const R einv = fast_exp(-es);

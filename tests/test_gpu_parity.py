@@ -676,3 +676,73 @@ def test_many_terms_pointwise_and_f32():
         assert rel_err(lp, lp_ref) < 1e-5 and rel_err(lp_only, lp_ref) < 1e-5
         for c in range(5):
             assert rel_err(g[c], g_ref[c]) < 1e-5
+
+
+@pytest.mark.parametrize("n_pairs,dtype,C", [(1, np.float64, 3), (3, np.float64, 37), (5, np.float64, 8), (2, np.float32, 5)])
+def test_shared_designs(n_pairs, dtype, C, monkeypatch):
+    """Scale term k on the same covariate and knots as location term k: the design is staged
+    once and dispatched once for both accumulator sets.  Same numbers as the oracle, and as
+    the unshared path (PTM_NO_SHARED=1) on the same model."""
+    n = 2300
+    rng = np.random.default_rng(40 + n_pairs)
+    y, X = o.synth_data(n, n_pairs, n_pairs, seed=5, dtype=dtype)
+    X = X[:n_pairs]
+    nb = 12
+
+    def make():
+        model = lp.LocScalePTM.new_ptm(y, nparam=20, to_float32=(dtype == np.float32), device="cuda:0")
+        oterms = []
+        for t in range(2 * n_pairs):
+            k = t % n_pairs
+            knots = lp.equidistant_knots(np.array([-2.0, 2.0]), n_param=nb, dtype=dtype)
+            basis = lp.ps(X[k], nbases=nb, xname=f"x{k}", knots=knots, dtype=dtype)
+            tm = lp.term.f_ig(basis, fname="f" if t < n_pairs else "g")
+            if t < n_pairs:
+                model.loc += tm
+            else:
+                model.scale += tm
+            oterms.append(o.term_from_reparam(X[k].astype(np.float64), basis.knots.astype(np.float64),
+                                              basis.Z.astype(np.float64), basis.penalty.astype(np.float64),
+                                              tm.penalty_rank, "loc" if t < n_pairs else "scale"))
+        return model, oterms
+
+    model, oterms = make()
+    om = o.PTMModel(y.astype(np.float64), oterms, nparam=20)
+    om.Zd = lp.trafo_reparam(20, dtype).astype(np.float64)
+    st = o.synth_state(oterms, 20, C, seed=9, amp=0.2)
+    st.tau[:] = rng.uniform(0.6, 1.5, size=st.tau.shape)
+    st.tau_delta[:] = rng.uniform(0.4, 0.9, size=C)
+    params = model.pack(st.beta, st.delta_z, tau=st.tau, tau_delta=st.tau_delta, beta0=st.beta0,
+                        gamma0=st.gamma0).astype(dtype)
+    if dtype == np.float32:  # oracle on the float-rounded parameters
+        st = golden_io.state_from_params(om, params.astype(np.float64), model.param_layout()[0])
+    model.build()
+    p = torch.from_numpy(params).cuda()
+    lp_, g = model.log_prob_and_grad(p)
+    lp_only = model.log_prob(p)
+    lppd, pw = model.pointwise(p)
+    lp_ref, gd = om.logp_and_grad(st)
+
+    class _C:
+        pass
+
+    c = _C()
+    c.layout, c.P = model.param_layout()
+    from tests.helpers import pack_grad
+
+    g_ref = pack_grad(c, gd)
+    tol = TOL64 if dtype == np.float64 else 1e-5
+    assert rel_err(lp_.cpu().numpy(), lp_ref) < tol
+    assert rel_err(lp_only.cpu().numpy(), lp_ref) < tol
+    for ch in range(C):
+        assert rel_err(g.cpu().numpy()[ch], g_ref[ch]) < tol
+    _, lppd_ref, _ = _oracle_pointwise(om, st, C)
+    assert rel_err(lppd.cpu().numpy(), lppd_ref) < (1e-12 if dtype == np.float64 else 1e-5)
+    # the unshared path on the same model
+    monkeypatch.setenv("PTM_NO_SHARED", "1")
+    model2, _ = make()
+    model2.build()
+    lp2, g2 = model2.log_prob_and_grad(p)
+    rt = 1e-13 if dtype == np.float64 else 1e-5
+    assert rel_err(lp2.cpu().numpy(), lp_.cpu().numpy()) < rt
+    assert rel_err(g2.cpu().numpy(), g.cpu().numpy()) < rt * 10
