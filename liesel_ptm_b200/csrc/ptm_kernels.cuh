@@ -190,6 +190,29 @@ __device__ __forceinline__ void scatter4(R (&acc)[NB], int jj, R b0, R b1, R b2,
 #undef PTM_BWD_CASE
 }
 
+// Two accumulator sets that share the interval and the basis values (shared designs): one
+// dispatch, eight FMAs per target.  (A PTX jump table cannot carry 2 x NB read-write operands
+// -- inline asm takes at most 30 -- so this one is left to the compiler's switch lowering.)
+template <typename R, int NB>
+__device__ __forceinline__ void scatter4x2(R (&accA)[NB], R (&accB)[NB], int jj, R b0, R b1, R b2, R b3,
+                                           R ga, R gb) {
+#define PTM_BWD2_CASE(J)                                       \
+  case J:                                                      \
+    if constexpr (J + 3 < NB) {                                \
+      accA[J] = fma(b0, ga, accA[J]);                          \
+      accB[J] = fma(b0, gb, accB[J]);                          \
+      accA[J + 1] = fma(b1, ga, accA[J + 1]);                  \
+      accB[J + 1] = fma(b1, gb, accB[J + 1]);                  \
+      accA[J + 2] = fma(b2, ga, accA[J + 2]);                  \
+      accB[J + 2] = fma(b2, gb, accB[J + 2]);                  \
+      accA[J + 3] = fma(b3, ga, accA[J + 3]);                  \
+      accB[J + 3] = fma(b3, gb, accB[J + 3]);                  \
+    }                                                          \
+    break;
+  switch (jj) { PTM_REP29(PTM_BWD2_CASE) default: break; }
+#undef PTM_BWD2_CASE
+}
+
 // Generic (C++ switch) dispatch; ptm_dispatch.cuh specialises the hot shapes with a
 // single PTX jump table.
 template <typename R, int NB>
@@ -436,8 +459,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                   load4(bpA, b0, b1, b2, b3);
                   const int jj = (*jpA - goff32[0]) >> 5;
                   const R hA = *hpA, hB = *hpB;
-                  Dispatch<R, NB>::scatter(acc[0], jj, b0, b1, b2, b3, hA);
-                  Dispatch<R, NB>::scatter(acc[TPW - 1], jj, b0, b1, b2, b3, hB);
+                  scatter4x2<R, NB>(acc[0], acc[TPW - 1], jj, b0, b1, b2, b3, hA, hB);
                 }
               } else
               for (int o = 0; o < cnt; ++o, bpA += 4, bpB += 4, ++jpA, ++jpB, hpA += 64, hpB += 64) {

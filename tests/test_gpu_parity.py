@@ -683,6 +683,8 @@ def test_shared_designs(n_pairs, dtype, C, monkeypatch):
     """Scale term k on the same covariate and knots as location term k: the design is staged
     once and dispatched once for both accumulator sets.  Same numbers as the oracle, and as
     the unshared path (PTM_NO_SHARED=1) on the same model."""
+    import liesel_ptm_b200 as lp
+
     n = 2300
     rng = np.random.default_rng(40 + n_pairs)
     y, X = o.synth_data(n, n_pairs, n_pairs, seed=5, dtype=dtype)
