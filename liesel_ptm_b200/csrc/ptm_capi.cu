@@ -291,10 +291,10 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   // beyond 12 terms a term warp owns two terms (two accumulator sets in registers): T = 20
   // -> 10 term warps + 6 eval warps = 512 threads at 128 registers, instead of 20 + 8 warps
   // at 72 (where the eval warps spill)
-  pl.TPW = (T > 12 || pr->shared) ? 2 : 1;
-  if (const char* e = getenv("PTM_TPW")) pl.TPW = (atoi(e) == 2 || pr->shared) ? 2 : 1;  // tuning knob
+  pl.TPW = T > 12 ? 2 : 1;  // (shared designs keep one term per warp: see k_main)
+  if (const char* e = getenv("PTM_TPW")) pl.TPW = atoi(e) == 2 ? 2 : 1;  // tuning knob
 #if PTM_RESPLIT
-  pl.TPW = pr->shared ? 2 : 1;  // (the re-split experiment cannot run shared designs)
+  pl.TPW = 1;
 #endif
   pl.NTW = (T + pl.TPW - 1) / pl.TPW;
   if (pl.TPW == 1)
@@ -381,15 +381,15 @@ int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t s
 #endif
   if (pl.TPW == 2) {
 #if !PTM_RESPLIT
-    if (a.shared) {
-      if (threads <= 512) return launch_main_t<R, NB, MODE, 512, 2, true>(a, pl, T, st);
-      return launch_main_t<R, NB, MODE, 640, 2, true>(a, pl, T, st);
-    }
+    if (a.shared) return launch_main_t<R, NB, MODE, 512, 2, true>(a, pl, T, st);
     if (threads <= 512) return launch_main_t<R, NB, MODE, 512, 2>(a, pl, T, st);
     if (threads <= 640) return launch_main_t<R, NB, MODE, 640, 2>(a, pl, T, st);
     return launch_main_t<R, NB, MODE, 768, 2>(a, pl, T, st);
 #endif
   }
+#if !PTM_RESPLIT
+  if (a.shared && threads <= 640) return launch_main_t<R, NB, MODE, 640, 1, true>(a, pl, T, st);
+#endif
   if (threads <= 512) return launch_main_t<R, NB, MODE, 512, 1>(a, pl, T, st);
   if (threads <= 640) return launch_main_t<R, NB, MODE, 640, 1>(a, pl, T, st);
   if (threads <= 768) return launch_main_t<R, NB, MODE, 768, 1>(a, pl, T, st);
@@ -417,8 +417,11 @@ void fill_main_args(const PtmProblem* pr, const Plan& pl, long long C, R* Gamma,
     for (int t = 0; t < pr->T; ++t) if (pr->pred[t] == PTM_LOC) ma.order[q++] = t;
     for (int t = 0; t < pr->T; ++t) if (pr->pred[t] == PTM_SCALE) ma.order[q++] = t;
   }
-  ma.shared = pr->shared;
-  if (pr->shared) {
+  // the shared-design kernels exist for the CTA sizes the planner picks (<= 640 threads with
+  // one term per warp, <= 512 with two); anything else runs the general kernel
+  const int cta_threads = 32 * (pl.NTW + pl.NU);
+  ma.shared = pr->shared && !PTM_RESPLIT && cta_threads <= (pl.TPW == 2 ? 512 : 640);
+  if (ma.shared) {
     // slots 2k / 2k+1 = location term k and its twin: one term warp, one staged design
     int k = 0;
     for (int t = 0; t < pr->T; ++t)

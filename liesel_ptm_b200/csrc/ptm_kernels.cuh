@@ -255,11 +255,12 @@ constexpr int kModeLogp = 0, kModeGrad = 1, kModePoint = 2;
 
 template <typename R, int NB, int MODE, int MAXTHREADS, int TPW = 1, bool SHARED = false>
 __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
-  // SHARED (with TPW = 2): the two terms of a term warp evaluate the same design (a
-  // location term and the scale term on the same covariate and knots); the design is staged
-  // once (slot 2 tq), the eval warps read its values once for both predictors and the
-  // backward loads them once for both accumulator sets.
-  static_assert(!SHARED || TPW == 2, "shared designs pair a location and a scale term");
+  // SHARED: term slots 2k and 2k+1 (a location term and the scale term on the same covariate
+  // and knots) evaluate the same design.  It is staged once (slot 2k) and the eval warps read
+  // its values and interval once for both predictors.  With one term per term warp (the
+  // layout that is used) the two term warps of a pair read the same staged slot for their
+  // backward; with TPW = 2 one warp runs both accumulator sets through one switch-lowered
+  // dispatch (measured slower: 44.8 vs 42.7 ms at the shared c3 variant, kept for reference).
   static_assert(!(SHARED && (PTM_EVAL_PAIR || PTM_PAIR_TPW2)), "the lockstep-pair experiment has no shared-design gather");
   // TPW = smooth terms per term warp: 1 up to 12 terms; 2 beyond (the CTA then has
   // ceil(T/2) term warps with two accumulator sets each, which leaves room for eval warps
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
         const int slot = tile % 3;
 #pragma unroll
         for (int k = 0; k < TPW; ++k) {
-          if (!t_has[k] || (SHARED && k > 0)) continue;
+          if (!t_has[k] || (SHARED && (TPW == 2 ? k > 0 : (tq & 1) != 0))) continue;
           const int q = tq * TPW + k;
           const R* kn = s_kn + q * 4 * kKnotStride;
           R* bst = s_b + ((q * 3 + slot) * To) * 4;
@@ -412,8 +413,10 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             const int slot = tile % 3;
             const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
             if constexpr (TPW == 1) {
-              const R* bp = s_b + ((tq * 3 + slot) * To) * 4;
-              const int* jp = s_j + (tq * 3 + slot) * To;
+              const int qs = SHARED ? (tq & ~1) : tq;  // the twin reads its location term's slot
+              const int gsh = SHARED ? a.goff[a.order[qs]] * 32 : goff32[0];
+              const R* bp = s_b + ((qs * 3 + slot) * To) * 4;
+              const int* jp = s_j + (qs * 3 + slot) * To;
               const R* hp = s_g + (((tile & 1) * To) * 2 + t_pred[0]) * 32 + lane;
 #if PTM_BWD_PREFETCH
               // experiment: the operands of observation o+1 are loaded before the
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               // one entry past the tile stays inside the shared-memory carve-up.
               R n0, n1, n2, n3;
               load4(bp, n0, n1, n2, n3);
-              int nj = (*jp - goff32[0]) >> 5;
+              int nj = (*jp - gsh) >> 5;
               R nh = *hp;
 #pragma unroll 2
               for (int o = 0; o < cnt; ++o) {
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                 const int j = nj;
                 bp += 4; ++jp; hp += 64;
                 load4(bp, n0, n1, n2, n3);
-                nj = (*jp - goff32[0]) >> 5;
+                nj = (*jp - gsh) >> 5;
                 nh = *hp;
                 Dispatch<R, NB>::scatter(acc[0], j, b0, b1, b2, b3, h);
               }
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               for (int o = 0; o < cnt; ++o, bp += 4, ++jp, hp += 64) {
                 R b0, b1, b2, b3;
                 load4(bp, b0, b1, b2, b3);
-                Dispatch<R, NB>::scatter(acc[0], (*jp - goff32[0]) >> 5, b0, b1, b2, b3, *hp);
+                Dispatch<R, NB>::scatter(acc[0], (*jp - gsh) >> 5, b0, b1, b2, b3, *hp);
               }
 #endif
             } else {
