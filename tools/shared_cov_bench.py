@@ -1,7 +1,7 @@
 """c3 variant of SURVEY.md 8(d): the five scale terms use the SAME covariates as the five
-location terms (11 distinct columns -> 6).  The kernels do not exploit the sharing yet: every
-term is staged on its own, so the time equals c3's; the algorithmic bytes per evaluation drop
-to w * (1 + 5) = 48 B (f64)."""
+location terms (11 distinct columns -> 6).  ptm_problem_create detects the pairing and the
+sweep stages / gathers every design once (PTM_NO_SHARED=1 turns that off); the algorithmic
+bytes per evaluation drop to w * (1 + 5) = 48 B (f64)."""
 import json, sys
 sys.path.insert(0, '.')
 import numpy as np, torch
