@@ -83,12 +83,6 @@ constexpr int kTermUnroll = PTM_TERM_UNROLL;
 #ifndef PTM_EVAL_PAIR
 #define PTM_EVAL_PAIR 0
 #endif
-#ifndef PTM_BWD_PREFETCH
-#define PTM_BWD_PREFETCH 0  // measured neutral at c3 (41.9 vs 41.6 ms): the term warps are not critical there
-#endif
-#ifndef PTM_PAIR_TPW2
-#define PTM_PAIR_TPW2 0  // measured: 26.3 ms with, 25.7 ms without (c5 shape, per-GPU slice of 2M)
-#endif
 #ifndef PTM_EVAL_UNROLL
 #define PTM_EVAL_UNROLL 1
 #endif
@@ -261,7 +255,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   // layout that is used) the two term warps of a pair read the same staged slot for their
   // backward; with TPW = 2 one warp runs both accumulator sets through one switch-lowered
   // dispatch (measured slower: 44.8 vs 42.7 ms at the shared c3 variant, kept for reference).
-  static_assert(!(SHARED && (PTM_EVAL_PAIR || PTM_PAIR_TPW2)), "the lockstep-pair experiment has no shared-design gather");
+  static_assert(!(SHARED && PTM_EVAL_PAIR), "the lockstep-pair experiment has no shared-design gather");
   // TPW = smooth terms per term warp: 1 up to 12 terms; 2 beyond (the CTA then has
   // ceil(T/2) term warps with two accumulator sets each, which leaves room for eval warps
   // at their full register budget)
@@ -269,7 +263,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   static_assert(!(PTM_RESPLIT && TPW > 1), "the register re-split experiment is single-term only");
   constexpr bool GRAD = MODE == kModeGrad;
   constexpr bool POINT = MODE == kModePoint;
-  constexpr bool kPair = (PTM_EVAL_PAIR != 0) || PTM_PAIR_TPW2 && TPW == 2;  // lockstep pairs in the eval warps
+  constexpr bool kPair = PTM_EVAL_PAIR != 0;  // lockstep pairs in the eval warps (experiment)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -418,33 +412,12 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               const R* bp = s_b + ((qs * 3 + slot) * To) * 4;
               const int* jp = s_j + (qs * 3 + slot) * To;
               const R* hp = s_g + (((tile & 1) * To) * 2 + t_pred[0]) * 32 + lane;
-#if PTM_BWD_PREFETCH
-              // experiment: the operands of observation o+1 are loaded before the
-              // dispatch of observation o (an indirect branch the loads cannot cross), which
-              // takes the shared-memory latency off the term warp's critical path.  Reading
-              // one entry past the tile stays inside the shared-memory carve-up.
-              R n0, n1, n2, n3;
-              load4(bp, n0, n1, n2, n3);
-              int nj = (*jp - gsh) >> 5;
-              R nh = *hp;
-#pragma unroll 2
-              for (int o = 0; o < cnt; ++o) {
-                const R b0 = n0, b1 = n1, b2 = n2, b3 = n3, h = nh;
-                const int j = nj;
-                bp += 4; ++jp; hp += 64;
-                load4(bp, n0, n1, n2, n3);
-                nj = (*jp - gsh) >> 5;
-                nh = *hp;
-                Dispatch<R, NB>::scatter(acc[0], j, b0, b1, b2, b3, h);
-              }
-#else
 #pragma unroll 2
               for (int o = 0; o < cnt; ++o, bp += 4, ++jp, hp += 64) {
                 R b0, b1, b2, b3;
                 load4(bp, b0, b1, b2, b3);
                 Dispatch<R, NB>::scatter(acc[0], (*jp - gsh) >> 5, b0, b1, b2, b3, *hp);
               }
-#endif
             } else {
               // two owned terms per observation: two independent dispatches in flight
               const int qA = tq * TPW, qB = (t_has[TPW - 1] && !SHARED) ? qA + 1 : qA;
@@ -562,8 +535,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
           const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
           // (interleaving two observations per warp by unrolling was measured slower: the
           //  extra live values push the eval warps over their 96-register budget)
-          // (PTM_EVAL_PAIR forces it everywhere; by default only the two-terms-per-warp
-          //  layout, whose 16-warp CTAs have 128 registers per thread, uses it)
+          // (off by default: 40.5 vs 41.5 ms at c3 with the register re-split, no gain with two
+          //  terms per warp -- DESIGN.md section 4.2)
           if constexpr (kPair && !POINT) {
           // Two observations per eval warp in lockstep (o0 and o0 + NU): every straight-line
           // stage below carries both, so the scheduler can overlap their dependency chains.
