@@ -203,6 +203,13 @@ int ptm_intercept_stats_f64(const PtmProblem* prob, const double* params, int64_
 int ptm_intercept_stats_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
                             float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Number of location / scale term pairs that evaluate the same design (same covariate
+ * values, knots and basis count -- the usual "same covariates in both predictors" model,
+ * model/model.py:345-420 adds terms to .loc and .scale independently).  ptm_problem_create
+ * detects them; the sweeps then stage and gather every such design once.  0 = general
+ * layout (also with PTM_NO_SHARED=1 in the environment at create time). */
+int ptm_problem_shared_designs(const PtmProblem* prob);
+
 /* Predictive evaluation on NEW data for n_samples posterior samples (params [S, P] like
  * the chain states): y_new [m] and x_new [T, m] (term-major, the problem's term order) are
  * device arrays; z, logpdf, cdf are [S, m] device outputs, each optional (NULL to skip):

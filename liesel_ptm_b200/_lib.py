@@ -32,7 +32,7 @@ SYMBOLS = [
     "ptm_quadform_f64", "ptm_quadform_f32", "ptm_intercept_stats_f64", "ptm_intercept_stats_f32",
     "ptm_loc_precision_all_f64", "ptm_loc_precision_all_f32",
     "ptm_pointwise_workspace_bytes", "ptm_pointwise_f64", "ptm_pointwise_f32",
-    "ptm_predict_workspace_bytes", "ptm_predict_f64", "ptm_predict_f32",
+    "ptm_problem_shared_designs", "ptm_predict_workspace_bytes", "ptm_predict_f64", "ptm_predict_f32",
     "ptm_predict_quantile_f64", "ptm_predict_quantile_f32", "ptm_inverse_f64", "ptm_inverse_f32",
     "ptm_last_launch_count", "ptm_last_xtwx_route", "ptm_profile_enable", "ptm_last_kernel_ms", "ptm_last_error",
     "ptm_version",
@@ -128,6 +128,8 @@ def load() -> C.CDLL:
         f = getattr(lib, f"ptm_pointwise_{sfx}")
         f.argtypes = [vp, vp, i64, vp, vp, vp, sz, vp]
         f.restype = C.c_int
+    lib.ptm_problem_shared_designs.argtypes = [vp]
+    lib.ptm_problem_shared_designs.restype = C.c_int
     lib.ptm_predict_workspace_bytes.argtypes = [vp, i64]
     lib.ptm_predict_workspace_bytes.restype = sz
     for sfx in ("f64", "f32"):

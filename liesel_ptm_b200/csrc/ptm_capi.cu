@@ -152,19 +152,27 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
   }
   pr->sum_nb = go;
   pr->T = T;
-  // shared designs: the k-th scale term has the same covariate values, knots and basis count
-  // as the k-th location term (the usual "same covariates in both predictors" model)
+  // shared designs: every scale term has the same covariate values, knots and basis count as
+  // one location term (the usual "same covariates in both predictors" model)
   pr->shared = 0;
   if (pr->T_loc == pr->T_scale && pr->T_loc > 0 && !getenv("PTM_NO_SHARED")) {
     std::vector<int> loc, sc;
     for (int t = 0; t < T; ++t) (d->predictor[t] == PTM_LOC ? loc : sc).push_back(t);
+    // one-to-one matching in any order: the first unmatched scale term with the same design
     bool ok = true;
+    std::vector<char> used(sc.size(), 0);
     for (size_t k = 0; k < loc.size() && ok; ++k) {
-      const int a = loc[k], b = sc[k];
-      ok = pr->nb[a] == pr->nb[b] &&
-           memcmp(d->knots[a], d->knots[b], (size_t)(pr->nb[a] + 4) * sizeof(R)) == 0 &&
-           (d->x[a] == d->x[b] || memcmp(d->x[a], d->x[b], (size_t)n * sizeof(R)) == 0);
-      pr->twin[k] = b;
+      const int a = loc[k];
+      int found = -1;
+      for (size_t m = 0; m < sc.size() && found < 0; ++m) {
+        const int b = sc[m];
+        if (used[m] || pr->nb[a] != pr->nb[b]) continue;
+        if (memcmp(d->knots[a], d->knots[b], (size_t)(pr->nb[a] + 4) * sizeof(R)) != 0) continue;
+        if (d->x[a] != d->x[b] && memcmp(d->x[a], d->x[b], (size_t)n * sizeof(R)) != 0) continue;
+        found = (int)m;
+      }
+      ok = found >= 0;
+      if (ok) { used[found] = 1; pr->twin[k] = sc[found]; }
     }
     pr->shared = ok ? 1 : 0;
   }
@@ -1010,6 +1018,8 @@ int ptm_loc_precision_all_f32(const PtmProblem* p, const float* params, int64_t 
                               float* chol, void* ws, size_t wsb, void* st) {
   return precision_all_impl<float>(p, params, C, precision, chol, ws, wsb, st);
 }
+
+int ptm_problem_shared_designs(const PtmProblem* p) { return (p && p->shared) ? p->T_loc : 0; }
 
 size_t ptm_predict_workspace_bytes(const PtmProblem* p, int64_t S) {
   if (!p || S < 1) return 0;

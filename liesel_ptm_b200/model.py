@@ -306,6 +306,12 @@ class LocScalePTM:
         contraction, weights on CUDA cores) or "tcgen05" (scale predictor on the tensor cores too)."""
         return {0: "banded", 1: "tcgen05-w", 2: "tcgen05"}[self._lib.ptm_last_xtwx_route()]
 
+    @property
+    def shared_designs(self) -> int:
+        """Location / scale term pairs on the same covariate and knots that the sweeps stage
+        and gather once (0 = general layout)."""
+        return int(self._lib.ptm_problem_shared_designs(self._handle)) if self.is_built else 0
+
     def last_kernel_ms(self) -> tuple[float, float, float]:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         _lib.check(self._lib.ptm_last_kernel_ms(C.byref(a), C.byref(b), C.byref(c)))

@@ -651,6 +651,11 @@ def test_random_shapes_fuzz():
 
 
 
+def test_distinct_covariates_are_not_shared():
+    case = build_case(n=300, n_loc=2, n_scale=2, nbases=10, C=2)
+    assert case.model.shared_designs == 0
+
+
 def test_many_terms_pointwise_and_f32():
     """Two terms per term warp (T > 12) in the pointwise mode and in the float kernel
     (whose register accumulators are flushed into doubles), odd and even term counts."""
@@ -695,7 +700,7 @@ def test_shared_designs(n_pairs, dtype, C, monkeypatch):
         model = lp.LocScalePTM.new_ptm(y, nparam=20, to_float32=(dtype == np.float32), device="cuda:0")
         oterms = []
         for t in range(2 * n_pairs):
-            k = t % n_pairs
+            k = t % n_pairs if t < n_pairs else (n_pairs - 1 - t % n_pairs)  # scale terms in reverse order
             knots = lp.equidistant_knots(np.array([-2.0, 2.0]), n_param=nb, dtype=dtype)
             basis = lp.ps(X[k], nbases=nb, xname=f"x{k}", knots=knots, dtype=dtype)
             tm = lp.term.f_ig(basis, fname="f" if t < n_pairs else "g")
@@ -719,6 +724,7 @@ def test_shared_designs(n_pairs, dtype, C, monkeypatch):
     if dtype == np.float32:  # oracle on the float-rounded parameters
         st = golden_io.state_from_params(om, params.astype(np.float64), model.param_layout()[0])
     model.build()
+    assert model.shared_designs == n_pairs
     p = torch.from_numpy(params).cuda()
     lp_, g = model.log_prob_and_grad(p)
     lp_only = model.log_prob(p)
@@ -744,6 +750,7 @@ def test_shared_designs(n_pairs, dtype, C, monkeypatch):
     monkeypatch.setenv("PTM_NO_SHARED", "1")
     model2, _ = make()
     model2.build()
+    assert model2.shared_designs == 0
     lp2, g2 = model2.log_prob_and_grad(p)
     rt = 1e-13 if dtype == np.float64 else 1e-5
     assert rel_err(lp2.cpu().numpy(), lp_.cpu().numpy()) < rt
