@@ -328,11 +328,12 @@ def ref_logp(m, out):
 def main():
     warnings.filterwarnings("ignore")
     np.seterr(all="ignore")
+    out = os.environ.get("PTM_GOLDEN_OUT", HERE)  # tests regenerate into a scratch directory
     m = load_reference()
-    ref_basis(m, HERE)
-    ref_trafo(m, HERE)
-    ref_logp(m, HERE)
-    print("reference fixtures written to", HERE)
+    ref_basis(m, out)
+    ref_trafo(m, out)
+    ref_logp(m, out)
+    print("reference fixtures written to", out)
 
 
 if __name__ == "__main__":

@@ -10,6 +10,8 @@ CPU part: the oracle (and the host mirror's setup code) against the fixtures.
 GPU part: the CUDA path against the same fixtures, through the C ABI.
 """
 
+import os
+
 import numpy as np
 import pytest
 
@@ -139,6 +141,24 @@ def test_oracle_logp_grad_information_match_reference_code():
     assert rel_err(P0, d["precision"][:, 0]) < 1e-14 and rel_err(L0, d["chol"][:, 0]) < 1e-13
     assert rel_err(P1, d["precision"][:, 1]) < 1e-14
     assert rel_err(np.linalg.cholesky(P1), d["chol"][:, 1]) < 1e-13
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/liesel_ptm"),
+                    reason="the reference tree only exists in the build container")
+def test_reference_fixtures_are_reproducible(tmp_path):
+    """Re-runs the reference's source files over the stand-ins and compares with the
+    committed fixtures: they are what that code produces, not hand-edited numbers."""
+    import subprocess
+    import sys
+
+    script = os.path.join(golden_io.GOLDEN, "make_reference_golden.py")
+    env = dict(os.environ, PTM_GOLDEN_OUT=str(tmp_path))
+    subprocess.run([sys.executable, script], check=True, env=env, capture_output=True, timeout=600)
+    for name in ("ref_basis_nb20.npz", "ref_trafo_nparam20.npz", "ref_logp_n257.npz"):
+        new, old = np.load(tmp_path / name), golden_io.load(name)
+        assert sorted(new.files) == sorted(old.files)
+        for k in old.files:
+            assert np.array_equal(new[k], old[k], equal_nan=True), (name, k)
 
 
 # ---------------------------------------------------------------------------------------
