@@ -317,9 +317,9 @@ Plan make_plan(const PtmProblem* pr, long long C) {
     b += (size_t)pl.NU * NGV * 32 * sizeof(R);                // private grad tables
     b += std::max((size_t)2 * To * 2 * 32 * sizeof(R),        // dl/deta hand-off, reused for the
                   (size_t)pl.NU * ptm::kRegSlots * 32 * sizeof(double));  // scalar partials at item end
-    b += (size_t)T * 3 * To * 4 * sizeof(R);                  // staged basis values
+    b += (size_t)T * 3 * To * 4 * sizeof(R);                  // staged records: 3 basis values + row offset
     b += (size_t)T * 4 * ptm::kKnotStride * sizeof(R);        // knots + reciprocals
-    b += (size_t)(T * 3 * To + 8) * sizeof(int);              // staged intervals
+    b += 64;                                                  // tail pad
     return b;
   };
   pl.To = 4 * pl.NU;  // four observations per eval warp and tile

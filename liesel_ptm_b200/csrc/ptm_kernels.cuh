@@ -230,6 +230,30 @@ __device__ __forceinline__ void load4(const float* p, float& b0, float& b1, floa
   const float4 v = *reinterpret_cast<const float4*>(p);
   b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
 }
+// Staged record of one (term, observation): b0, b1, b2 and, in the fourth slot, the row offset
+// of the term's window in the shared gamma table (an int); the fourth basis value is
+// 1 - (b0 + b1 + b2) (partition of unity on [knots[3], knots[nb]]), which saves the separate
+// interval array and one shared-memory load per term and observation-row in both roles.
+__device__ __forceinline__ void load3j(const double* p, double& b0, double& b1, double& b2, double& b3, int& j) {
+  const double2 lo = *reinterpret_cast<const double2*>(p);
+  const double2 hi = *reinterpret_cast<const double2*>(p + 2);
+  b0 = lo.x; b1 = lo.y; b2 = hi.x;
+  j = __double2loint(hi.y);
+  b3 = 1.0 - ((b0 + b1) + b2);
+}
+__device__ __forceinline__ void load3j(const float* p, float& b0, float& b1, float& b2, float& b3, int& j) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  b0 = v.x; b1 = v.y; b2 = v.z;
+  j = __float_as_int(v.w);
+  b3 = 1.0f - ((b0 + b1) + b2);
+}
+__device__ __forceinline__ void store3j(double* p, const double (&b)[4], int j) {
+  *reinterpret_cast<double2*>(p) = make_double2(b[0], b[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(b[2], __hiloint2double(0, j));
+}
+__device__ __forceinline__ void store3j(float* p, const float (&b)[4], int j) {
+  *reinterpret_cast<float4*>(p) = make_float4(b[0], b[1], b[2], __int_as_float(j));
+}
 __device__ __forceinline__ void store4(double* p, const double (&b)[4]) {
   *reinterpret_cast<double2*>(p) = make_double2(b[0], b[1]);
   *reinterpret_cast<double2*>(p + 2) = make_double2(b[2], b[3]);
@@ -282,7 +306,6 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   R* s_kn = s_b + T * 3 * To * 4;                           // [T][4][kKnotStride]
   double* s_red = reinterpret_cast<double*>(s_g);  // [NU][kRegSlots][32] scalar partials (double),
                    // written after the last tile only: they reuse the dl/deta tiles
-  int* s_j = reinterpret_cast<int*>(s_kn + T * 4 * kKnotStride);  // [T][3][To] (+ pad)
 
 #if PTM_RESPLIT
   const bool is_term = warp >= NU && warp < NU + T;
@@ -382,15 +405,13 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
           const int q = tq * TPW + k;
           const R* kn = s_kn + q * 4 * kKnotStride;
           R* bst = s_b + ((q * 3 + slot) * To) * 4;
-          int* jst = s_j + (q * 3 + slot) * To;
           for (int o = lane; o < To; o += 32) {
             const long long gi = base + o;
             if (gi < o_end) {
               R bb[4];
               const int jj = basis_window_fast(t_x[k][gi], kn, kn + kKnotStride, kn + 2 * kKnotStride,
                                                kn + 3 * kKnotStride, t_nb[k], t_invdk[k], bb);
-              store4(bst + o * 4, bb);
-              jst[o] = goff32[k] + jj * 32;  // row offset into the shared gamma table
+              store3j(bst + o * 4, bb, goff32[k] + jj * 32);  // + row offset into the gamma table
             }
           }
         }
@@ -410,42 +431,42 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               const int qs = SHARED ? (tq & ~1) : tq;  // the twin reads its location term's slot
               const int gsh = SHARED ? a.goff[a.order[qs]] * 32 : goff32[0];
               const R* bp = s_b + ((qs * 3 + slot) * To) * 4;
-              const int* jp = s_j + (qs * 3 + slot) * To;
               const R* hp = s_g + (((tile & 1) * To) * 2 + t_pred[0]) * 32 + lane;
 #pragma unroll 2
-              for (int o = 0; o < cnt; ++o, bp += 4, ++jp, hp += 64) {
+              for (int o = 0; o < cnt; ++o, bp += 4, hp += 64) {
                 R b0, b1, b2, b3;
-                load4(bp, b0, b1, b2, b3);
-                Dispatch<R, NB>::scatter(acc[0], (*jp - gsh) >> 5, b0, b1, b2, b3, *hp);
+                int jo;
+                load3j(bp, b0, b1, b2, b3, jo);
+                Dispatch<R, NB>::scatter(acc[0], (jo - gsh) >> 5, b0, b1, b2, b3, *hp);
               }
             } else {
               // two owned terms per observation: two independent dispatches in flight
               const int qA = tq * TPW, qB = (t_has[TPW - 1] && !SHARED) ? qA + 1 : qA;
               const R* bpA = s_b + ((qA * 3 + slot) * To) * 4;
               const R* bpB = s_b + ((qB * 3 + slot) * To) * 4;
-              const int* jpA = s_j + (qA * 3 + slot) * To;
-              const int* jpB = s_j + (qB * 3 + slot) * To;
               const R* hpA = s_g + (((tile & 1) * To) * 2 + t_pred[0]) * 32 + lane;
               const R* hpB = s_g + (((tile & 1) * To) * 2 + t_pred[TPW - 1]) * 32 + lane;
               const bool hasB = t_has[TPW - 1];
               if constexpr (SHARED) {
                 // one set of staged values and one interval for both accumulator sets
-                for (int o = 0; o < cnt; ++o, bpA += 4, ++jpA, hpA += 64, hpB += 64) {
+                for (int o = 0; o < cnt; ++o, bpA += 4, hpA += 64, hpB += 64) {
                   R b0, b1, b2, b3;
-                  load4(bpA, b0, b1, b2, b3);
-                  const int jj = (*jpA - goff32[0]) >> 5;
+                  int jo;
+                  load3j(bpA, b0, b1, b2, b3, jo);
+                  const int jj = (jo - goff32[0]) >> 5;
                   const R hA = *hpA, hB = *hpB;
                   scatter4x2<R, NB>(acc[0], acc[TPW - 1], jj, b0, b1, b2, b3, hA, hB);
                 }
               } else
-              for (int o = 0; o < cnt; ++o, bpA += 4, bpB += 4, ++jpA, ++jpB, hpA += 64, hpB += 64) {
+              for (int o = 0; o < cnt; ++o, bpA += 4, bpB += 4, hpA += 64, hpB += 64) {
                 R b0, b1, b2, b3, c0, c1, c2, c3;
-                load4(bpA, b0, b1, b2, b3);
-                load4(bpB, c0, c1, c2, c3);
+                int joA, joB;
+                load3j(bpA, b0, b1, b2, b3, joA);
+                load3j(bpB, c0, c1, c2, c3, joB);
                 const R hA = *hpA;
                 const R hB = hasB ? *hpB : R(0);
-                Dispatch<R, NB>::scatter(acc[0], (*jpA - goff32[0]) >> 5, b0, b1, b2, b3, hA);
-                Dispatch<R, NB>::scatter(acc[TPW - 1], (*jpB - goff32[TPW - 1]) >> 5, c0, c1, c2, c3, hB);
+                Dispatch<R, NB>::scatter(acc[0], (joA - goff32[0]) >> 5, b0, b1, b2, b3, hA);
+                Dispatch<R, NB>::scatter(acc[TPW - 1], (joB - goff32[TPW - 1]) >> 5, c0, c1, c2, c3, hB);
               }
             }
           }
@@ -549,18 +570,17 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             {
               const R* bqA = s_b + (slot * To + oo[0]) * 4;
               const R* bqB = s_b + (slot * To + oo[1]) * 4;
-              const int* jqA = s_j + slot * To + oo[0];
-              const int* jqB = s_j + slot * To + oo[1];
               const R* gl = s_gam + lane;
               const int qstep = 3 * To;
               int q = 0;
 #pragma unroll kTermUnroll
-              for (; q < a.T_loc; ++q, bqA += qstep * 4, bqB += qstep * 4, jqA += qstep, jqB += qstep) {
+              for (; q < a.T_loc; ++q, bqA += qstep * 4, bqB += qstep * 4) {
                 R b0, b1, b2, b3, c0, c1, c2, c3;
-                load4(bqA, b0, b1, b2, b3);
-                load4(bqB, c0, c1, c2, c3);
-                const R* gA = gl + *jqA;
-                const R* gB = gl + *jqB;
+                int joA, joB;
+                load3j(bqA, b0, b1, b2, b3, joA);
+                load3j(bqB, c0, c1, c2, c3, joB);
+                const R* gA = gl + joA;
+                const R* gB = gl + joB;
                 R fA = b0 * gA[0], fB = c0 * gB[0];
                 fA = fma(b1, gA[32], fA); fB = fma(c1, gB[32], fB);
                 fA = fma(b2, gA[64], fA); fB = fma(c2, gB[64], fB);
@@ -568,12 +588,13 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                 em[0] += fA; em[1] += fB;
               }
 #pragma unroll kTermUnroll
-              for (; q < T; ++q, bqA += qstep * 4, bqB += qstep * 4, jqA += qstep, jqB += qstep) {
+              for (; q < T; ++q, bqA += qstep * 4, bqB += qstep * 4) {
                 R b0, b1, b2, b3, c0, c1, c2, c3;
-                load4(bqA, b0, b1, b2, b3);
-                load4(bqB, c0, c1, c2, c3);
-                const R* gA = gl + *jqA;
-                const R* gB = gl + *jqB;
+                int joA, joB;
+                load3j(bqA, b0, b1, b2, b3, joA);
+                load3j(bqB, c0, c1, c2, c3, joB);
+                const R* gA = gl + joA;
+                const R* gB = gl + joB;
                 R fA = b0 * gA[0], fB = c0 * gB[0];
                 fA = fma(b1, gA[32], fA); fB = fma(c1, gB[32], fB);
                 fA = fma(b2, gA[64], fA); fB = fma(c2, gB[64], fB);
@@ -729,7 +750,6 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             R em = beta0, es = gamma0;
             {
               const R* bq = s_b + (slot * To + o) * 4;
-              const int* jq = s_j + slot * To + o;
               const R* gl = s_gam + lane;
               const int qstep = 3 * To;
               int q = 0;
@@ -738,10 +758,11 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                 // location term and, dgo[k] rows further down the table, its scale twin
                 const int D = T >> 1;
 #pragma unroll kTermUnroll
-                for (; q < D; ++q, bq += 2 * qstep * 4, jq += 2 * qstep) {
+                for (; q < D; ++q, bq += 2 * qstep * 4) {
                   R b0, b1, b2, b3;
-                  load4(bq, b0, b1, b2, b3);
-                  const R* gp = gl + *jq;
+                  int jo;
+                  load3j(bq, b0, b1, b2, b3, jo);
+                  const R* gp = gl + jo;
                   const R* gs = gp + a.dgo[q];
                   R f = b0 * gp[0], h = b0 * gs[0];
                   f = fma(b1, gp[32], f); h = fma(b1, gs[32], h);
@@ -752,10 +773,11 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                 }
               } else {
 #pragma unroll kTermUnroll
-              for (; q < a.T_loc; ++q, bq += qstep * 4, jq += qstep) {
+              for (; q < a.T_loc; ++q, bq += qstep * 4) {
                 R b0, b1, b2, b3;
-                load4(bq, b0, b1, b2, b3);
-                const R* gp = gl + *jq;
+                int jo;
+                load3j(bq, b0, b1, b2, b3, jo);
+                const R* gp = gl + jo;
                 R f = b0 * gp[0];
                 f = fma(b1, gp[32], f);
                 f = fma(b2, gp[64], f);
@@ -763,10 +785,11 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
                 em += f;
               }
 #pragma unroll kTermUnroll
-              for (; q < T; ++q, bq += qstep * 4, jq += qstep) {
+              for (; q < T; ++q, bq += qstep * 4) {
                 R b0, b1, b2, b3;
-                load4(bq, b0, b1, b2, b3);
-                const R* gp = gl + *jq;
+                int jo;
+                load3j(bq, b0, b1, b2, b3, jo);
+                const R* gp = gl + jo;
                 R f = b0 * gp[0];
                 f = fma(b1, gp[32], f);
                 f = fma(b2, gp[64], f);
