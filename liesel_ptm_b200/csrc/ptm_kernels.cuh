@@ -107,6 +107,12 @@ __device__ __forceinline__ void split_mant(float x, float& mant, int& ex) {
 // instructions), degree-13 Taylor polynomial in Estrin form (dependency depth 5 instead
 // of 13), exponent patched in with integer arithmetic.  |x| is clamped to 700 (such
 // sigma are far outside any model).  Max relative error 4.4e-16; NaN propagates.
+#ifndef PTM_EXP_CONST
+#define PTM_EXP_CONST 1
+#endif
+__constant__ double kExpC[12] = {1.0 / 6.0, 0.5, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 5040.0, 1.0 / 720.0,
+                                 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 39916800.0, 1.0 / 3628800.0,
+                                 1.0 / 6227020800.0, 1.0 / 479001600.0};
 __device__ __forceinline__ double fast_exp(double x) {
   const double xc = fmin(fmax(x, -700.0), 700.0);
   const double magic = 6755399441055744.0;  // 1.5 * 2^52
@@ -115,6 +121,16 @@ __device__ __forceinline__ double fast_exp(double x) {
   const double t = tm - magic;
   double r = fma(t, -6.93147180369123816490e-01, xc);
   r = fma(t, -1.90821492927058770002e-10, r);
+#if PTM_EXP_CONST
+  // coefficients as constant-bank operands of the FMAs instead of two immediate moves each
+  const double a0 = r + 1.0;
+  const double a1 = fma(r, kExpC[0], kExpC[1]);
+  const double a2 = fma(r, kExpC[2], kExpC[3]);
+  const double a3 = fma(r, kExpC[4], kExpC[5]);
+  const double a4 = fma(r, kExpC[6], kExpC[7]);
+  const double a5 = fma(r, kExpC[8], kExpC[9]);
+  const double a6 = fma(r, kExpC[10], kExpC[11]);
+#else
   const double a0 = r + 1.0;
   const double a1 = fma(r, 1.0 / 6.0, 0.5);
   const double a2 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
@@ -122,6 +138,7 @@ __device__ __forceinline__ double fast_exp(double x) {
   const double a4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
   const double a5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
   const double a6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+#endif
   const double r2 = r * r;
   const double b0 = fma(r2, a1, a0);
   const double b1 = fma(r2, a3, a2);
