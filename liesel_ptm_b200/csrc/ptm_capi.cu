@@ -313,7 +313,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   auto smem_for = [&](int To) {
     size_t b = 0;
     b += (size_t)pr->sum_nb * 32 * sizeof(R);                 // gamma [coef][lane]
-    b += (size_t)NCC * 32 * sizeof(R);                        // cubic pieces of h
+    b += (size_t)(NCC + 4) * 32 * sizeof(R);                  // cubic pieces of h + 4 derived boundary rows
     b += (size_t)pl.NU * NGV * 32 * sizeof(R);                // private grad tables
     b += std::max((size_t)2 * To * 2 * 32 * sizeof(R),        // dl/deta hand-off, reused for the
                   (size_t)pl.NU * ptm::kRegSlots * 32 * sizeof(double));  // scalar partials at item end

@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   // ---- shared memory carve-up --------------------------------------------------
   R* s_gam = reinterpret_cast<R*>(smem_raw);                // [sum_nb][32]
   R* s_cc = s_gam + a.sum_nb * 32;                          // [NCC][32]
-  R* s_gv = s_cc + NCC * 32;                                // [NU][NGV][32]
+  R* s_gv = s_cc + (NCC + 4) * 32;                          // [NU][NGV][32]  (s_cc has 4 derived rows:
+                                                            //  constL, constR, ztailL, ztailR of ChainBoundary)
   R* s_g = s_gv + (GRAD ? NU * NGV * 32 : 0);               // [2][To][2][32]
   const int g_elems = max(2 * To * 2 * 32, NU * kRegSlots * 32 * (int)(sizeof(double) / sizeof(R)));
   R* s_b = s_g + g_elems;                                   // [T][3][To][4]
@@ -552,6 +553,17 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
 
       // =========================== eval warp ========================================
       for (int s = uw; s < NCC; s += NU) s_cc[s * 32 + lane] = a.cc[(long long)s * a.C + chain];
+      if (uw == 0) {
+        // constants of the transitions / tails (ptm.py:362-365, 386-389, 435, 440), once per
+        // work item: the non-core path below then loads the one or two it needs
+        ChainBoundary<R> cb;
+        make_boundary(ts, a.cc[(long long)(KK * 5 + 0) * a.C + chain], a.cc[(long long)(KK * 5 + 1) * a.C + chain],
+                      a.cc[(long long)(KK * 5 + 2) * a.C + chain], a.cc[(long long)(KK * 5 + 3) * a.C + chain], cb);
+        s_cc[(NCC + 0) * 32 + lane] = cb.constL;
+        s_cc[(NCC + 1) * 32 + lane] = cb.constR;
+        s_cc[(NCC + 2) * 32 + lane] = cb.ztailL;
+        s_cc[(NCC + 3) * 32 + lane] = cb.ztailR;
+      }
       R* gvp = s_gv + (uw * NGV) * 32 + lane;
       if (GRAD)
         for (int s = 0; s < NGV; ++s) gvp[s * 32] = R(0);
@@ -828,28 +840,28 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             core_eval(ts, cp[0], cp[32], cp[64], cp[96], cp[128], ev);
             R z = ev.z, d = ev.d, dzdr = ev.d, dddr = ev.d2;
             if (!core) {
-              // boundary constants of the chain: rebuilt from the shared table on the rare
-              // non-core path instead of living in 12 registers across the loop
-              ChainBoundary<R> cb;
-              make_boundary(ts, s_cc[(KK * 5 + 0) * 32 + lane], s_cc[(KK * 5 + 1) * 32 + lane],
-                            s_cc[(KK * 5 + 2) * 32 + lane], s_cc[(KK * 5 + 3) * 32 + lane], cb);
+              // boundary constants of the chain: one or two loads from the shared table on
+              // the non-core path (about half of the observation-rows of the c3 workload have
+              // at least one of their 32 chains outside the core)
               if (code == 1) {
+                const R dL = s_cc[(KK * 5 + 1) * 32 + lane], constL = s_cc[(NCC + 0) * 32 + lane];
                 const R poly = r * ts.a - R(0.5) * r * r;
-                z = (ts.inv_w * poly + cb.dL * (r - poly * ts.inv_w)) + cb.constL;
+                z = (ts.inv_w * poly + dL * (r - poly * ts.inv_w)) + constL;
                 const R q = (ts.a - r) * ts.inv_w;
-                d = (R(1) - q) * cb.dL + q;
-                dzdr = d; dddr = (cb.dL - R(1)) * ts.inv_w;
+                d = (R(1) - q) * dL + q;
+                dzdr = d; dddr = (dL - R(1)) * ts.inv_w;
               } else if (code == 3) {
+                const R dR = s_cc[(KK * 5 + 3) * 32 + lane], constR = s_cc[(NCC + 1) * 32 + lane];
                 const R poly = R(0.5) * r * r - r * ts.b;
-                z = (ts.inv_w * poly + cb.dR * (r - poly * ts.inv_w)) + cb.constR;
+                z = (ts.inv_w * poly + dR * (r - poly * ts.inv_w)) + constR;
                 const R q = (r - ts.b) * ts.inv_w;
-                d = (R(1) - q) * cb.dR + q;
-                dzdr = d; dddr = (R(1) - cb.dR) * ts.inv_w;
+                d = (R(1) - q) * dR + q;
+                dzdr = d; dddr = (R(1) - dR) * ts.inv_w;
               } else if (code == 0) {
-                z = cb.ztailL - (ts.min_eps - r);
+                z = s_cc[(NCC + 2) * 32 + lane] - (ts.min_eps - r);
                 d = R(1); dzdr = R(1); dddr = R(0);
               } else {
-                z = cb.ztailR + (r - ts.max_eps);
+                z = s_cc[(NCC + 3) * 32 + lane] + (r - ts.max_eps);
                 d = R(1); dzdr = R(1); dddr = R(0);
               }
             }
