@@ -839,30 +839,43 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
             const R* cp = s_cc + (ev.kk * 5) * 32 + lane;
             core_eval(ts, cp[0], cp[32], cp[64], cp[96], cp[128], ev);
             R z = ev.z, d = ev.d, dzdr = ev.d, dddr = ev.d2;
+            R cfac = R(0), qfac = R(0);
             if (!core) {
               // boundary constants of the chain: one or two loads from the shared table on
               // the non-core path (about half of the observation-rows of the c3 workload have
               // at least one of their 32 chains outside the core)
+              // (cfac, qfac: d z / d dL|dR and d h' / d dL|dR of this evaluation, used by the
+              //  gradient block further down: cL_of / cR_of share the terms computed here)
               if (code == 1) {
                 const R dL = s_cc[(KK * 5 + 1) * 32 + lane], constL = s_cc[(NCC + 0) * 32 + lane];
                 const R poly = r * ts.a - R(0.5) * r * r;
-                z = (ts.inv_w * poly + dL * (r - poly * ts.inv_w)) + constL;
+                const R t1 = r - poly * ts.inv_w;
+                z = (ts.inv_w * poly + dL * t1) + constL;
                 const R q = (ts.a - r) * ts.inv_w;
                 d = (R(1) - q) * dL + q;
                 dzdr = d; dddr = (dL - R(1)) * ts.inv_w;
+                const R poly0 = ts.a * ts.a - R(0.5) * ts.a * ts.a;
+                cfac = t1 - (ts.a - poly0 * ts.inv_w);
+                qfac = R(1) - q;
               } else if (code == 3) {
                 const R dR = s_cc[(KK * 5 + 3) * 32 + lane], constR = s_cc[(NCC + 1) * 32 + lane];
                 const R poly = R(0.5) * r * r - r * ts.b;
-                z = (ts.inv_w * poly + dR * (r - poly * ts.inv_w)) + constR;
+                const R t1 = r - poly * ts.inv_w;
+                z = (ts.inv_w * poly + dR * t1) + constR;
                 const R q = (r - ts.b) * ts.inv_w;
                 d = (R(1) - q) * dR + q;
                 dzdr = d; dddr = (R(1) - dR) * ts.inv_w;
+                const R poly0 = R(0.5) * ts.b * ts.b - ts.b * ts.b;
+                cfac = t1 - (ts.b - poly0 * ts.inv_w);
+                qfac = R(1) - q;
               } else if (code == 0) {
                 z = s_cc[(NCC + 2) * 32 + lane] - (ts.min_eps - r);
                 d = R(1); dzdr = R(1); dddr = R(0);
+                cfac = cL_of(ts, ts.min_eps);
               } else {
                 z = s_cc[(NCC + 3) * 32 + lane] + (r - ts.max_eps);
                 d = R(1); dzdr = R(1); dddr = R(0);
+                cfac = cR_of(ts, ts.max_eps);
               }
             }
             const R tiny = tiny_of<R>();
@@ -939,20 +952,13 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               gp[96] += g3 * sixth - w4 * R(0.5);
               gp[128] += w4 * sixth;
               if (!core) {
-                if (code == 1) {
-                  const R q = (ts.a - r) * ts.inv_w;
+                const double dv = (double)fma(lz, cfac, ld * qfac);
+                if (code <= 1) {
                   a_gvl += (double)lz;
-                  a_gdl += (double)fma(lz, cL_of(ts, r), ld * (R(1) - q));
-                } else if (code == 3) {
-                  const R q = (r - ts.b) * ts.inv_w;
-                  a_gvr += (double)lz;
-                  a_gdr += (double)fma(lz, cR_of(ts, r), ld * (R(1) - q));
-                } else if (code == 0) {
-                  a_gvl += (double)lz;
-                  a_gdl += (double)(lz * cL_of(ts, ts.min_eps));
+                  a_gdl += dv;
                 } else {
                   a_gvr += (double)lz;
-                  a_gdr += (double)(lz * cR_of(ts, ts.max_eps));
+                  a_gdr += dv;
                 }
               }
             }
