@@ -306,6 +306,9 @@ def _logsumexp(a, **kw):
 
 scipy.special.logsumexp = _logsumexp
 
+nn = types.ModuleType("jax.nn")
+nn.logsumexp = _logsumexp
+
 typing_ = types.ModuleType("jax.typing")
 typing_.ArrayLike = typing.Any
 
@@ -326,6 +329,7 @@ _sys.modules["jax.lax"] = lax
 _sys.modules["jax.tree_util"] = tree_util
 _sys.modules["jax.scipy"] = scipy
 _sys.modules["jax.scipy.special"] = scipy.special
+_sys.modules["jax.nn"] = nn
 _sys.modules["jax.typing"] = typing_
 _sys.modules["jax.random"] = random
 typing = typing_

@@ -5,7 +5,7 @@ jax / tfp / liesel are not installed in this image, so the reference cannot be i
 a package.  This script instead executes the reference's hot-path files unmodified, loaded
 by path from /root/reference/liesel_ptm, over the NumPy stand-ins in tests/golden/jaxshim
 (see its README): bspline/approx.py, bspline/ptm.py, bspline/util.py, dist.py, gam/dist.py,
-constraint.py, penalty.py.  The package `__init__`s are bypassed (they import the liesel
+constraint.py, penalty.py, iwls_proposals.py, predictor.py (static intercept formulas).  The package `__init__`s are bypassed (they import the liesel
 graph machinery); everything evaluated below is the reference's code path for
 `LocScaleTransformationDist(..., batched=False).log_prob` and its building blocks.
 
@@ -68,6 +68,9 @@ def load_reference():
         sys.modules[name] = stub
     mods.iwls = importlib.import_module("liesel_ptm.iwls_proposals")
     del sys.modules["liesel_ptm.logprob"], sys.modules["liesel_ptm.var"]
+    # predictor.py: only the static intercept formulas are called (the classes derive from
+    # inert liesel.model placeholders)
+    mods.predictor = importlib.import_module("liesel_ptm.predictor")
     for m in vars(mods).values():
         assert m.__file__.startswith(REF), m.__file__
     return mods
@@ -310,7 +313,18 @@ def ref_logp(m, out):
         prec[c, 0], chol[c, 0] = A(loc_info.precision(state)), A(loc_info.chol_info(state))
         prec[c, 1], chol[c, 1] = A(scale_info.precision(state)), A(scale_info.chol_info(state))
 
+    # intercept pseudo-parameters (predictor.py:80-100, 126-130): loc_model / log_scale_model
+    # are the predictors without their intercepts; the scale intercept sees the full loc
+    icpt = np.zeros((C, 2))
+    for c in range(C):
+        b_loc, b_scale, _ = unpack(params[c])
+        loc_model = terms[0]["basis"] @ (terms[0]["Z"] @ b_loc)
+        log_scale_model = terms[1]["basis"] @ (terms[1]["Z"] @ b_scale)
+        icpt[c, 0] = float(m.predictor.LocationIntercept.compute_intercept(y, loc_model, log_scale_model))
+        icpt[c, 1] = float(m.predictor.LogScaleIntercept.compute_intercept(y, loc_model, log_scale_model))
+
     np.savez(os.path.join(out, "ref_logp_n257.npz"), y=y, ynan=ynan, precision=prec, chol=chol,
+             intercepts=icpt,
              x_loc=x_loc, x_scale=x_scale,
              knots_loc=terms[0]["knots"], knots_scale=terms[1]["knots"],
              Z_loc=terms[0]["Z"], Z_scale=terms[1]["Z"], K_loc=terms[0]["K"], K_scale=terms[1]["K"],

@@ -136,6 +136,11 @@ def test_oracle_logp_grad_information_match_reference_code():
     for c in range(2):
         ll = om_nan.loglik_terms(st, c)["ll"]
         assert np.array_equal(np.isnan(ll), np.isnan(d["loglik_i_nan"][c])) and np.isnan(ll).sum() == 1
+    # intercept pseudo-parameters: LocationIntercept / LogScaleIntercept.compute_intercept
+    # (predictor.py:80-100, 126-130)
+    for c in range(2):
+        b0, g0 = om.compute_intercepts(st, c)
+        assert abs(b0 - d["intercepts"][c, 0]) < 1e-14 and abs(g0 - d["intercepts"][c, 1]) < 1e-14
     _, P0, L0 = om.loc_precision(st, 0)
     _, P1 = om.scale_precision(st, 1)
     assert rel_err(P0, d["precision"][:, 0]) < 1e-14 and rel_err(L0, d["chol"][:, 0]) < 1e-13
@@ -242,6 +247,10 @@ def test_cuda_logp_grad_information_vs_reference_code_f64():
     assert rel_err(L0.cpu().numpy(), d["chol"][:, 0]) < 1e-9
     assert rel_err(P1.cpu().numpy(), d["precision"][:, 1]) < 1e-11
     assert rel_err(L1.cpu().numpy(), d["chol"][:, 1]) < 1e-9
+    # intercept pseudo-parameters from the fused sufficient statistics (ptm_intercept_stats)
+    b0, g0 = model.compute_intercepts(params)
+    assert np.max(np.abs(b0.cpu().numpy() - d["intercepts"][:, 0])) < 1e-12
+    assert np.max(np.abs(g0.cpu().numpy() - d["intercepts"][:, 1])) < 1e-12
     # per-observation log-densities through the pointwise sweep
     ll = d["loglik_i"]
     mx = ll.max(axis=0)
