@@ -13,7 +13,7 @@ The oracle is therefore pinned against outputs of the REFERENCE'S OWN SOURCE FIL
 executed here over NumPy stand-ins for jax / tfp (tests/golden/jaxshim,
 tests/golden/make_reference_golden.py -> tests/golden/ref_*.npz): bspline/approx.py,
 bspline/ptm.py, bspline/util.py, dist.py, gam/dist.py, constraint.py, penalty.py,
-iwls_proposals.py run unmodified.  tests/test_reference_golden.py: knots, dense bases,
+iwls_proposals.py, predictor.py (intercept formulas) run unmodified.  tests/test_reference_golden.py: knots, dense bases,
 grid tables, theta(delta), h / h' over all five regions are BIT-EQUAL; per-observation
 log-densities agree to 1e-13, the gradient to 1e-14 of its norm against forward mode
 through the reference's code with its declared custom_jvp rules, precision / Cholesky to
