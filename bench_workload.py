@@ -19,6 +19,9 @@ CONFIGS = {
     "c2_n100k_3loc_1scale_64chains": (100_000, 3, 1, 20, 64),
     "c3_n1M_5loc_5scale_nb20_1024chains": (1_000_000, 5, 5, 20, 1024),
     "c4_n1M_10loc_1scale_nb30_256chains": (1_000_000, 10, 1, 30, 256),
+    # c5 (n = 50M over 8 GPUs, 20 smooth terms, 128 chains): the per-GPU slice is 6.25M
+    # observations; built per rank from its own seeded slice (see make_c5_slice)
+    "c5_n50M_10loc_10scale_128chains": (50_000_000, 10, 10, 20, 128),
 }
 
 

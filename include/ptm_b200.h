@@ -94,7 +94,8 @@ typedef struct {
                                   with the restated jnp.linspace formula */
 } PtmProblemDesc;
 
-typedef struct PtmProblem PtmProblem; /* opaque, immutable after create */
+typedef struct PtmProblem PtmProblem; /* opaque, immutable after create (tuning knobs in the
+                                          environment are read once, at create) */
 
 int ptm_problem_create(const PtmProblemDesc* desc, PtmProblem** out);
 int ptm_problem_destroy(PtmProblem* prob);
@@ -110,12 +111,24 @@ int ptm_param_layout(const PtmProblem* prob, int64_t* beta0_off, int64_t* gamma0
 /* Bytes of caller-owned device scratch needed for C chains (any entry point). */
 size_t ptm_workspace_bytes(const PtmProblem* prob, int64_t n_chains);
 
-/* Restrict the observation range this handle evaluates to [obs_begin, obs_end):
- * observation-axis sharding across GPUs.  With add_priors == 0 the
- * per-chain prior terms are left out of logp/grad so that exactly one rank adds
- * them before/after the allreduce.  Default: [0, n), add_priors = 1. */
-int ptm_problem_set_shard(PtmProblem* prob, int64_t obs_begin, int64_t obs_end,
-                          int32_t add_priors);
+/* Observation-axis sharding across GPUs: a NEW handle that evaluates the
+ * observations [obs_begin, obs_end) of `base` only.  Handles are immutable, so the shard is
+ * a create-time property of the view; the view borrows base's device arrays (base must
+ * outlive it; destroy the view with ptm_problem_destroy).  With add_priors == 0 the per-chain
+ * prior terms are left out of logp / grad so that exactly one rank adds them to the
+ * all-reduced sum.  What a view returns is the SHARD-LOCAL, additive part of:
+ *   ptm_logp_* / ptm_logp_grad_* / ptm_logp_grad_block_*   likelihood sums (+ priors if asked)
+ *   ptm_xtwx_*                                             X' W X over the shard
+ *   ptm_intercept_stats_*                                  the five sums
+ *   ptm_pointwise_*                                        records of the shard's observations
+ * ptm_loc_precision_* / ptm_loc_precision_all_* return PTM_ERR_SHAPE on a view (or with
+ * add_priors == 0): penalty, ridge and Cholesky are not additive -- all-reduce ptm_xtwx and
+ * finish on the sum. */
+int ptm_problem_shard_view(const PtmProblem* base, int64_t obs_begin, int64_t obs_end,
+                           int32_t add_priors, PtmProblem** out);
+/* The observation range and prior flag of a handle ([0, n), 1 for a created problem). */
+int ptm_problem_shard(const PtmProblem* prob, int64_t* obs_begin, int64_t* obs_end,
+                      int32_t* add_priors);
 
 /* logp[c] for C chains.  params [C, P] row-major, logp [C]. */
 int ptm_logp_f64(const PtmProblem* prob, const double* params, int64_t n_chains,
@@ -130,6 +143,15 @@ int ptm_logp_grad_f64(const PtmProblem* prob, const double* params, int64_t n_ch
 int ptm_logp_grad_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
                       float* logp, float* grad, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* The same results as ptm_logp_grad_* written into ONE contiguous block [C, 1 + P] row-major:
+ * block[c, 0] = logp[c], block[c, 1:] = grad[c, :].  This is the payload of the
+ * observation-axis all-reduce: the epilogue kernel writes it in place, so the
+ * collective runs on the buffer without a repacking step. */
+int ptm_logp_grad_block_f64(const PtmProblem* prob, const double* params, int64_t n_chains,
+                            double* block, void* workspace, size_t workspace_bytes, void* stream);
+int ptm_logp_grad_block_f32(const PtmProblem* prob, const float* params, int64_t n_chains,
+                            float* block, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Banded design of term `term`: interval[i] = j with knots[j] <= x_i < knots[j+1]
  * (int32, bit-exact with the reference's order-0 indicator) and the four non-zero
@@ -150,10 +172,10 @@ int ptm_transform_f32(const PtmProblem* prob, const float* delta, int64_t n_chai
                       const float* r, int64_t m, float* z, float* dz,
                       int32_t* cell, void* stream);
 
-/* Chain-batched IWLS information of a LOC term: xtwx [C, p, p] = X' diag(w) X and
- * xtr [C, p] = X' (w * resid-free score weights) with w_i = 1/max(sigma_i,
- * sqrt(eps))^2 and X = B_t Z_t (iwls_proposals.py:55-74).  For a SCALE term w == 2.
- * Either output may be NULL. */
+/* Chain-batched IWLS information of a LOC term: xtwx [C, p, p] = X' diag(w) X with
+ * w_i = 1/max(sigma_i, sqrt(eps))^2 and X = B_t Z_t (iwls_proposals.py:55-74).  For a SCALE
+ * term w == 2 (iwls_proposals.py:118-119).  (The score X'r of an IWLS step is the beta_t
+ * block of ptm_logp_grad_*; there is no separate output for it.) */
 int ptm_xtwx_f64(const PtmProblem* prob, int32_t term, const double* params,
                  int64_t n_chains, double* xtwx, void* workspace,
                  size_t workspace_bytes, void* stream);
@@ -190,14 +212,19 @@ int ptm_quadform_f32(const PtmProblem* prob, const float* params, int64_t n_chai
                      float* quad, void* stream);
 
 /* Sufficient statistics of the intercept pseudo-Gibbs updates (predictor.py:80-100,
- * 126-130, 133-175, 239-281), one fused sweep over the handle's observation range:
- *   stats[c, 0] = sum_i exp(-eta_sigma_i)
- *   stats[c, 1] = sum_i r_i            r_i = (y_i - eta_mu_i) exp(-eta_sigma_i)
- *   stats[c, 2] = sum_i r_i^2
- * with both intercepts at their current values.  Then, with n observations,
- *   beta0_new  = beta0  + (stats1 / n) / (stats0 / n)        (LocationIntercept)
- *   gamma0_new = gamma0 + log sqrt(stats2/n - (stats1/n)^2)  (LogScaleIntercept)
- * The sums are additive over observation shards (all-reduce before the formulas). */
+ * 126-130, 133-175, 239-281), one fused sweep over the handle's observation range.
+ * stats is [C, 5] with w_i = exp(-eta_sigma_i), r_i = (y_i - eta_mu_i) w_i, both intercepts
+ * at their current values:
+ *   stats[c, 0] = sum_i w_i      stats[c, 1] = sum_i r_i      stats[c, 2] = sum_i r_i^2
+ *   stats[c, 3] = sum_i w_i^2    stats[c, 4] = sum_i r_i w_i
+ * Then, with n observations and m_k = stats[c, k] / n,
+ *   beta0_new  = beta0 + m_1 / m_0                            (LocationIntercept)
+ *   gamma0_new = gamma0 + log sqrt(var_d),   d = beta0' - beta0,
+ *   var_d = m_2 - 2 d m_4 + d^2 m_3 - (m_1 - d m_0)^2          (LogScaleIntercept)
+ * where beta0' is the location intercept LogScaleIntercept sees: the reference passes it the
+ * full `loc` predictor (predictor.py:604-609), i.e. d = beta0_new - beta0 when the location
+ * intercept was updated first in the same sweep, d = 0 when it is evaluated at the current
+ * state.  The sums are additive over observation shards (all-reduce before the formulas). */
 int ptm_intercept_stats_f64(const PtmProblem* prob, const double* params, int64_t n_chains,
                             double* stats, void* workspace, size_t workspace_bytes, void* stream);
 int ptm_intercept_stats_f32(const PtmProblem* prob, const float* params, int64_t n_chains,

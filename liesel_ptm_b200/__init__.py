@@ -21,6 +21,7 @@ from .spline import (  # noqa: F401
     term,
     trafo_reparam,
 )
+from ._lib import PtmError  # noqa: F401
 from .model import (  # noqa: F401
     FlatLogProb,
     GaussianLocCholInfo,
@@ -32,4 +33,5 @@ __all__ = [
     "LocScalePTM", "FlatLogProb", "GaussianLocCholInfo", "GaussianScaleCholInfo",
     "ps", "term", "PTMKnots", "LogIncKnots", "Penalty", "equidistant_knots",
     "mixed_model", "LinearConstraintEVD", "banded_basis", "approx_grid", "trafo_reparam", "Basis",
+    "PtmError",
 ]

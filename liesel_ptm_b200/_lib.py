@@ -25,7 +25,8 @@ STATUS = {
 # every symbol include/ptm_b200.h declares
 SYMBOLS = [
     "ptm_problem_create", "ptm_problem_destroy", "ptm_num_params", "ptm_param_layout",
-    "ptm_workspace_bytes", "ptm_problem_set_shard",
+    "ptm_workspace_bytes", "ptm_problem_shard_view", "ptm_problem_shard",
+    "ptm_logp_grad_block_f64", "ptm_logp_grad_block_f32",
     "ptm_logp_f64", "ptm_logp_f32", "ptm_logp_grad_f64", "ptm_logp_grad_f32",
     "ptm_basis_f64", "ptm_basis_f32", "ptm_transform_f64", "ptm_transform_f32",
     "ptm_xtwx_f64", "ptm_xtwx_f32", "ptm_loc_precision_f64", "ptm_loc_precision_f32",
@@ -92,14 +93,19 @@ def load() -> C.CDLL:
     lib.ptm_param_layout.restype = C.c_int
     lib.ptm_workspace_bytes.argtypes = [vp, i64]
     lib.ptm_workspace_bytes.restype = sz
-    lib.ptm_problem_set_shard.argtypes = [vp, i64, i64, i32]
-    lib.ptm_problem_set_shard.restype = C.c_int
+    lib.ptm_problem_shard_view.argtypes = [vp, i64, i64, i32, C.POINTER(vp)]
+    lib.ptm_problem_shard_view.restype = C.c_int
+    lib.ptm_problem_shard.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    lib.ptm_problem_shard.restype = C.c_int
     for sfx in ("f64", "f32"):
         f = getattr(lib, f"ptm_logp_{sfx}")
         f.argtypes = [vp, vp, i64, vp, vp, sz, vp]
         f.restype = C.c_int
         f = getattr(lib, f"ptm_logp_grad_{sfx}")
         f.argtypes = [vp, vp, i64, vp, vp, vp, sz, vp]
+        f.restype = C.c_int
+        f = getattr(lib, f"ptm_logp_grad_block_{sfx}")
+        f.argtypes = [vp, vp, i64, vp, vp, sz, vp]
         f.restype = C.c_int
         f = getattr(lib, f"ptm_basis_{sfx}")
         f.argtypes = [vp, i32, vp, vp, vp]

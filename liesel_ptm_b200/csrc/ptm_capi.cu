@@ -70,6 +70,15 @@ struct PtmProblem {
   int twin[ptm::kMaxTerms] = {0};
   int num_sms = 148;
   int device = 0;
+  // tuning knobs, read from the environment ONCE at create (0 / -1 = planner default)
+  struct Tune {
+    int tpw = 0, nu = 0, to = 0, items_per_sm = 0;
+    int xtwx_tc = 3;   // PTM_XTWX_TC: 0 banded, 1 / 2 tensor-core versions, 3 = pick
+    int tc_flush = 0;  // PTM_TC_FLUSH
+  } tune;
+  // shard views share the device arrays of the handle they were made from
+  const PtmProblem* base = nullptr;
+  mutable int views = 0;
   // device buffers (element type by dtype)
   void* d_y = nullptr;
   void* d_X = nullptr;
@@ -155,6 +164,18 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
   // shared designs: every scale term has the same covariate values, knots and basis count as
   // one location term (the usual "same covariates in both predictors" model)
   pr->shared = 0;
+  {
+    auto env_int = [](const char* name, int dflt) {
+      const char* e = getenv(name);
+      return e ? atoi(e) : dflt;
+    };
+    pr->tune.tpw = env_int("PTM_TPW", 0);
+    pr->tune.nu = env_int("PTM_NU", 0);
+    pr->tune.to = env_int("PTM_TO", 0);
+    pr->tune.items_per_sm = env_int("PTM_ITEMS_PER_SM", 0);
+    pr->tune.xtwx_tc = env_int("PTM_XTWX_TC", 3);
+    pr->tune.tc_flush = env_int("PTM_TC_FLUSH", 0);
+  }
   if (pr->T_loc == pr->T_scale && pr->T_loc > 0 && !getenv("PTM_NO_SHARED")) {
     std::vector<int> loc, sc;
     for (int t = 0; t < T; ++t) (d->predictor[t] == PTM_LOC ? loc : sc).push_back(t);
@@ -300,16 +321,13 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   // -> 10 term warps + 6 eval warps = 512 threads at 128 registers, instead of 20 + 8 warps
   // at 72 (where the eval warps spill)
   pl.TPW = T > 12 ? 2 : 1;  // (shared designs keep one term per warp: see k_main)
-  if (const char* e = getenv("PTM_TPW")) pl.TPW = atoi(e) == 2 ? 2 : 1;  // tuning knob
-#if PTM_RESPLIT
-  pl.TPW = 1;
-#endif
+  if (pr->tune.tpw) pl.TPW = pr->tune.tpw == 2 ? 2 : 1;  // tuning knob (PTM_TPW at create)
   pl.NTW = (T + pl.TPW - 1) / pl.TPW;
   if (pl.TPW == 1)
     pl.NU = T <= 12 ? std::min(12, std::max(8, 20 - T)) : std::max(4, std::min(8, 28 - T));
   else  // 16 warps (128 registers per thread) while that leaves at least 4 eval warps
     pl.NU = pl.NTW <= 12 ? std::max(4, 16 - pl.NTW) : 4;
-  if (const char* e = getenv("PTM_NU")) pl.NU = std::max(1, std::min(32 - pl.NTW, atoi(e)));  // tuning knob
+  if (pr->tune.nu) pl.NU = std::max(1, std::min(32 - pl.NTW, pr->tune.nu));  // tuning knob (PTM_NU)
   auto smem_for = [&](int To) {
     size_t b = 0;
     b += (size_t)pr->sum_nb * 32 * sizeof(R);                 // gamma [coef][lane]
@@ -323,7 +341,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
     return b;
   };
   pl.To = 4 * pl.NU;  // four observations per eval warp and tile
-  if (const char* e = getenv("PTM_TO")) pl.To = std::max(8, atoi(e));  // tuning knob
+  if (pr->tune.to) pl.To = std::max(8, pr->tune.to);  // tuning knob (PTM_TO)
   while (pl.To > 8 && smem_for(pl.To) > 227 * 1024) pl.To -= 4;
   // large coefficient tables (many terms x many bases): give up eval warps (their private
   // gradient tables) before giving up
@@ -334,7 +352,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   pl.smem_main = smem_for(pl.To);
   const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
   long long per_sm = 8;  // work items per CTA: amortises the per-item table loads, keeps the tail short
-  if (const char* e = getenv("PTM_ITEMS_PER_SM")) per_sm = std::max(1, atoi(e));  // tuning knob
+  if (pr->tune.items_per_sm) per_sm = std::max(1, pr->tune.items_per_sm);  // tuning knob (PTM_ITEMS_PER_SM)
   const long long target_items = per_sm * pr->num_sms;
   long long M = std::max<long long>(1, target_items / pl.CG);
   const long long max_m = std::max<long long>(1, len / ((long long)pl.To * 16));  // >= 16 tiles per item
@@ -366,12 +384,8 @@ Plan make_plan(const PtmProblem* pr, long long C) {
 template <typename R, int NB, int MODE, int MAXT, int TPW, bool SHARED = false>
 int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
   auto kern = ptm::k_main<R, NB, MODE, MAXT, TPW, SHARED>;
-  PTM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_main));
-#if PTM_RESPLIT
-  kern<<<pl.grid, 32 * ((T + pl.NU + 3) / 4 * 4), pl.smem_main, st>>>(a);
-#else
+  PTM_CUDA(ptm::ensure_smem(kern, pl.smem_main));
   kern<<<pl.grid, 32 * (pl.NTW + pl.NU), pl.smem_main, st>>>(a);
-#endif
   PTM_CUDA(cudaGetLastError());
   return PTM_OK;
 }
@@ -382,22 +396,14 @@ int launch_main_t(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t
 template <typename R, int NB, int MODE>
 int launch_main(const ptm::MainArgs<R>& a, const Plan& pl, int T, cudaStream_t st) {
   // registers are granted per 4 warps: <= 16 warps -> 128/thread, 18 -> 112, 20 -> 96, 24 -> 80, 32 -> 64
-#if PTM_RESPLIT
-  const int threads = 32 * ((T + pl.NU + 3) / 4 * 4);
-#else
   const int threads = 32 * (pl.NTW + pl.NU);
-#endif
   if (pl.TPW == 2) {
-#if !PTM_RESPLIT
     if (a.shared) return launch_main_t<R, NB, MODE, 512, 2, true>(a, pl, T, st);
     if (threads <= 512) return launch_main_t<R, NB, MODE, 512, 2>(a, pl, T, st);
     if (threads <= 640) return launch_main_t<R, NB, MODE, 640, 2>(a, pl, T, st);
     return launch_main_t<R, NB, MODE, 768, 2>(a, pl, T, st);
-#endif
   }
-#if !PTM_RESPLIT
   if (a.shared && threads <= 640) return launch_main_t<R, NB, MODE, 640, 1, true>(a, pl, T, st);
-#endif
   if (threads <= 512) return launch_main_t<R, NB, MODE, 512, 1>(a, pl, T, st);
   if (threads <= 640) return launch_main_t<R, NB, MODE, 640, 1>(a, pl, T, st);
   if (threads <= 768) return launch_main_t<R, NB, MODE, 768, 1>(a, pl, T, st);
@@ -428,7 +434,7 @@ void fill_main_args(const PtmProblem* pr, const Plan& pl, long long C, R* Gamma,
   // the shared-design kernels exist for the CTA sizes the planner picks (<= 640 threads with
   // one term per warp, <= 512 with two); anything else runs the general kernel
   const int cta_threads = 32 * (pl.NTW + pl.NU);
-  ma.shared = pr->shared && !PTM_RESPLIT && cta_threads <= (pl.TPW == 2 ? 512 : 640);
+  ma.shared = pr->shared && cta_threads <= (pl.TPW == 2 ? 512 : 640);
   if (ma.shared) {
     // slots 2k / 2k+1 = location term k and its twin: one term warp, one staged design
     int k = 0;
@@ -462,12 +468,36 @@ void fill_pre_args(const PtmProblem* pr, const R* params, long long C, R* Gamma,
   }
 }
 
+// The handle's device must be the calling thread's current device: the kernels launch on the
+// current device with pointers that live on pr->device.
+int check_device(const PtmProblem* pr) {
+  int dev = -1;
+  PTM_CUDA(cudaGetDevice(&dev));
+  if (dev != pr->device) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "problem lives on device %d but the current device is %d (cudaSetDevice first)",
+             pr->device, dev);
+    return fail(PTM_ERR_CUDA, buf);
+  }
+  return PTM_OK;
+}
+#define PTM_CHECK_DEVICE(pr)                                \
+  do {                                                      \
+    const int rc_dev_ = check_device(pr);                   \
+    if (rc_dev_ != PTM_OK) return rc_dev_;                  \
+  } while (0)
+
+bool is_sharded(const PtmProblem* pr) { return pr->obs_begin != 0 || pr->obs_end != pr->n || !pr->add_priors; }
+
+// ld_logp / ld_grad: element strides of the outputs (1 / P for separate arrays, 1 + P for the
+// packed [C, 1 + P] block of ptm_logp_grad_block_*).
 template <typename R>
 int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* grad, void* ws,
-              size_t ws_bytes, void* stream, R* stats = nullptr) {
+              size_t ws_bytes, void* stream, R* stats = nullptr, long long ld_logp = 1, long long ld_grad = 0) {
   if (!pr || !params || !logp || !ws) return fail(PTM_ERR_NULL, "null argument");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
   if (C < 1) return fail(PTM_ERR_SHAPE, "n_chains must be >= 1");
+  PTM_CHECK_DEVICE(pr);
   const Plan pl = make_plan<R>(pr, C);
   if (ws_bytes < pl.total) return fail(PTM_ERR_WORKSPACE, "workspace too small");
   if (pl.smem_main > 227 * 1024) return fail(PTM_ERR_SHAPE, "shared-memory budget exceeded");
@@ -505,6 +535,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   ptm::PostArgs<R> po;
   memset(&po, 0, sizeof po);
   po.params = params; po.partial = partial; po.logp = logp; po.grad = grad; po.stats = stats;
+  po.ld_logp = ld_logp; po.ld_grad = ld_grad ? ld_grad : pr->P;
   po.Zall = reinterpret_cast<const R*>(pr->d_Zall);
   po.Kall = reinterpret_cast<const R*>(pr->d_Kall);
   po.Zd = reinterpret_cast<const R*>(pr->d_Zd);
@@ -517,10 +548,10 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   po.dz_off = pr->dz_off; po.tau_off = pr->tau_off; po.taud_off = pr->taud_off;
   po.n_obs = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
   po.add_priors = pr->add_priors;
-  const size_t smem_post = ((size_t)ma.NSLOT * 32 + 32) * sizeof(double);
+  const size_t smem_post = ((size_t)ma.NSLOT * 32 + (size_t)std::max(pr->T, 1) * 32) * sizeof(double);
   if (want_grad) {
     auto kp = ptm::k_post<R, true>;
-    PTM_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_post));
+    PTM_CUDA(ptm::ensure_smem(kp, smem_post));
     kp<<<pl.CG, 256, smem_post, st>>>(po);
   } else {
     auto kp = ptm::k_post<R, false>;
@@ -541,6 +572,7 @@ int pointwise_impl(const PtmProblem* pr, const R* params, long long S, R* lppd, 
                    size_t ws_bytes, void* stream) {
   if (!pr || !params || !lppd || !pwaic || !ws) return fail(PTM_ERR_NULL, "null argument");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  PTM_CHECK_DEVICE(pr);
   if (S < 1) return fail(PTM_ERR_SHAPE, "n_samples must be >= 1");
   Plan pl = make_plan<R>(pr, S);
   const size_t need = pl.total + (size_t)pr->n * 4 * sizeof(double);
@@ -584,6 +616,7 @@ template <typename R>
 int basis_impl(const PtmProblem* pr, int term, int32_t* interval, R* values, void* stream) {
   if (!pr || !interval || !values) return fail(PTM_ERR_NULL, "null argument");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  PTM_CHECK_DEVICE(pr);
   if (term < 0 || term >= pr->T) return fail(PTM_ERR_SHAPE, "term index out of range");
   if (pr->n == 0) return PTM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -601,6 +634,7 @@ int transform_impl(const PtmProblem* pr, const R* delta, long long C, const R* r
                    R* dz, int32_t* cell, void* stream) {
   if (!pr || !delta || !r || !z || !dz) return fail(PTM_ERR_NULL, "null argument");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  PTM_CHECK_DEVICE(pr);
   if (C < 1 || m < 0) return fail(PTM_ERR_SHAPE, "bad shape");
   if (m == 0) return PTM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -627,6 +661,7 @@ int predict_impl(const PtmProblem* pr, const R* params, long long S, const R* y_
   if (pr->T > 0 && !x_new) return fail(PTM_ERR_NULL, "x_new is null");
   if (!z && !logpdf && !cdf && !yq) return fail(PTM_ERR_NULL, "no output requested");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  PTM_CHECK_DEVICE(pr);
   if (S < 1 || m < 0) return fail(PTM_ERR_SHAPE, "bad shape");
   if (S > 65535 && pr->T > 12) return fail(PTM_ERR_SHAPE, "at most 65535 samples per call beyond 12 terms");
   if (ws_bytes < predict_ws_bytes(pr, S)) return fail(PTM_ERR_WORKSPACE, "workspace too small (see ptm_predict_workspace_bytes)");
@@ -697,6 +732,7 @@ int inverse_impl(const PtmProblem* pr, const R* delta, long long C, const R* z, 
                  void* stream) {
   if (!pr || !delta || !z || !r) return fail(PTM_ERR_NULL, "null argument");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  PTM_CHECK_DEVICE(pr);
   if (C < 1 || m < 0) return fail(PTM_ERR_SHAPE, "bad shape");
   if (m == 0) return PTM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -708,21 +744,9 @@ int inverse_impl(const PtmProblem* pr, const R* delta, long long C, const R* z, 
 }
 
 static thread_local int g_last_xtwx_route = 0;  // 0 = banded CUDA-core sweep, 1 = tcgen05 sweep
-static bool tc_route_enabled() {
-  const char* e = getenv("PTM_XTWX_TC");
-  return !(e && e[0] == '0');
-}
-// PTM_XTWX_TC: 0 banded sweep, 1 tensor-core contraction with the weights on CUDA cores,
-// 2 scale predictor on the tensor cores too; unset = pick 2 when its Q tiles can be
-// double-buffered, else 1.
-static int tc_version() {
-  const char* e = getenv("PTM_XTWX_TC");
-  return e ? atoi(e) : 3;
-}
-static int tc_flush_tiles() {
-  const char* e = getenv("PTM_TC_FLUSH");
-  return e ? atoi(e) : 0;
-}
+// PtmProblem::tune.xtwx_tc (PTM_XTWX_TC at create): 0 banded sweep, 1 tensor-core contraction
+// with the weights on CUDA cores, 2 scale predictor on the tensor cores too; unset (3) = pick 2
+// when its Q tiles can be double-buffered, else 1.
 
 // Information sweep for the terms in `terms` (all LOC, or one SCALE term): shared
 // prologue (gamma of the scale terms), one banded sweep, one epilogue per term.
@@ -732,6 +756,7 @@ int xtwx_terms(const PtmProblem* pr, const int* terms, int nterms, const R* para
                R* const* out_x, R* const* out_p, R* const* out_l, void* ws, size_t ws_bytes, void* stream) {
   if (!pr || !params || !ws) return fail(PTM_ERR_NULL, "null argument");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  PTM_CHECK_DEVICE(pr);
   if (C < 1) return fail(PTM_ERR_SHAPE, "n_chains must be >= 1");
   if (nterms < 1) return PTM_OK;
   for (int i = 0; i < nterms; ++i)
@@ -740,6 +765,13 @@ int xtwx_terms(const PtmProblem* pr, const int* terms, int nterms, const R* para
   for (int i = 1; i < nterms; ++i)
     if ((pr->pred[terms[i]] == PTM_LOC) != loc) return fail(PTM_ERR_SHAPE, "terms must share a predictor");
   if (!loc && nterms != 1) return fail(PTM_ERR_SHAPE, "one scale term per call");
+  // a shard view holds part of the observations: X'WX is additive over shards, the precision
+  // (penalty, 1e-6 mean(diag) ridge) and its Cholesky factor are not -- all-reduce ptm_xtwx and
+  // finish on the full sum (parallel.finish_precision) instead of getting shard-local factors
+  if (is_sharded(pr) && (out_p || out_l))
+    return fail(PTM_ERR_SHAPE,
+                "precision / Cholesky of an observation-shard view are not additive over shards: "
+                "use ptm_xtwx_* per shard, all-reduce, then add the penalty and factorise");
   const Plan pl = make_plan<R>(pr, C);
   if (ws_bytes < pl.total) return fail(PTM_ERR_WORKSPACE, "workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -795,14 +827,14 @@ int xtwx_terms(const PtmProblem* pr, const int* terms, int nterms, const R* para
     if constexpr (sizeof(R) == 4) {
       // float problems, location terms: tensor-core route (ptm_xtwx_tc.cuh) with as many
       // terms per sweep as TMEM / shared memory take
-      if (loc && tc_route_enabled())
+      if (loc && pr->tune.xtwx_tc != 0)
         for (take = std::min(nterms - done, 8); take >= 1 && rc == -1; --take) {
           select(take);
-          rc = tc_version() >= 2 ? ptm::xtwx_tc2_sweep(xa, xt, pr->num_sms, tc_flush_tiles(), tc_version() == 2, st,
-                                                       &g_launches)
-                                 : -1;
+          rc = pr->tune.xtwx_tc >= 2 ? ptm::xtwx_tc2_sweep(xa, xt, pr->num_sms, pr->tune.tc_flush,
+                                                           pr->tune.xtwx_tc == 2, st, &g_launches)
+                                     : -1;
           if (rc != -1) { g_last_xtwx_route = 2; break; }
-          rc = ptm::xtwx_tc_sweep(xa, xt, pr->num_sms, tc_flush_tiles(), st, &g_launches);
+          rc = ptm::xtwx_tc_sweep(xa, xt, pr->num_sms, pr->tune.tc_flush, st, &g_launches);
           if (rc != -1) { g_last_xtwx_route = 1; break; }
         }
     }
@@ -851,6 +883,7 @@ template <typename R>
 int quadform_impl(const PtmProblem* pr, const R* params, long long C, R* quad, void* stream) {
   if (!pr || !params || !quad) return fail(PTM_ERR_NULL, "null argument");
   if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  PTM_CHECK_DEVICE(pr);
   if (C < 1) return fail(PTM_ERR_SHAPE, "n_chains must be >= 1");
   if (pr->T == 0) return PTM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -863,6 +896,7 @@ int quadform_impl(const PtmProblem* pr, const R* params, long long C, R* quad, v
 }
 
 void free_all(PtmProblem* p) {
+  if (p->base) return;  // a shard view borrows the arrays of its base handle
   cudaFree(p->d_y); cudaFree(p->d_X); cudaFree(p->d_knots); cudaFree(p->d_grid);
   cudaFree(p->d_Zall); cudaFree(p->d_Kall); cudaFree(p->d_Zd); cudaFree(p->d_tc); cudaFree(p->d_tc64); cudaFree(p->d_meta);
 }
@@ -921,12 +955,25 @@ size_t ptm_workspace_bytes(const PtmProblem* p, int64_t C) {
   return p->dtype == PTM_F64 ? make_plan<double>(p, C).total : make_plan<float>(p, C).total;
 }
 
-int ptm_problem_set_shard(PtmProblem* p, int64_t b, int64_t e, int32_t add_priors) {
-  if (!p) return fail(PTM_ERR_NULL, "null problem");
+int ptm_problem_shard_view(const PtmProblem* p, int64_t b, int64_t e, int32_t add_priors, PtmProblem** out) {
+  if (!p || !out) return fail(PTM_ERR_NULL, "null argument");
+  *out = nullptr;
   if (b < 0 || e > p->n || b > e) return fail(PTM_ERR_SHAPE, "shard must satisfy 0 <= begin <= end <= n");
-  p->obs_begin = b;
-  p->obs_end = e;
-  p->add_priors = add_priors ? 1 : 0;
+  PtmProblem* v = new (std::nothrow) PtmProblem(*p);
+  if (!v) return fail(PTM_ERR_CUDA, "out of host memory");
+  v->base = p->base ? p->base : p;
+  v->views = 0;
+  v->obs_begin = b;
+  v->obs_end = e;
+  v->add_priors = add_priors ? 1 : 0;
+  *out = v;
+  return PTM_OK;
+}
+int ptm_problem_shard(const PtmProblem* p, int64_t* obs_begin, int64_t* obs_end, int32_t* add_priors) {
+  if (!p) return fail(PTM_ERR_NULL, "null problem");
+  if (obs_begin) *obs_begin = p->obs_begin;
+  if (obs_end) *obs_end = p->obs_end;
+  if (add_priors) *add_priors = p->add_priors;
   return PTM_OK;
 }
 
@@ -945,6 +992,17 @@ int ptm_logp_grad_f32(const PtmProblem* p, const float* params, int64_t C, float
                       size_t wsb, void* st) {
   if (!grad) return fail(PTM_ERR_NULL, "grad is null");
   return eval_impl<float>(p, params, C, logp, grad, ws, wsb, st);
+}
+
+int ptm_logp_grad_block_f64(const PtmProblem* p, const double* params, int64_t C, double* block, void* ws,
+                            size_t wsb, void* st) {
+  if (!block || !p) return fail(PTM_ERR_NULL, "null argument");
+  return eval_impl<double>(p, params, C, block, block + 1, ws, wsb, st, nullptr, p->P + 1, p->P + 1);
+}
+int ptm_logp_grad_block_f32(const PtmProblem* p, const float* params, int64_t C, float* block, void* ws,
+                            size_t wsb, void* st) {
+  if (!block || !p) return fail(PTM_ERR_NULL, "null argument");
+  return eval_impl<float>(p, params, C, block, block + 1, ws, wsb, st, nullptr, p->P + 1, p->P + 1);
 }
 
 int ptm_basis_f64(const PtmProblem* p, int32_t term, int32_t* interval, double* values, void* st) {

@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include "ptm_math.cuh"
+#include "ptm_launch.cuh"
 #include "ptm_dispatch.cuh"
 
 namespace ptm {
@@ -34,9 +35,13 @@ constexpr int kRegSlots = 9;                 // per-lane scalar accumulators
 enum Slot { SL_Z2 = 0, SL_LS, SL_LOGD, SL_GB0, SL_GG0, SL_GVL, SL_GDL, SL_GVR, SL_GDR };
 // The logp-only sweep has no gradient slots; it reuses three of them for the sums the
 // intercept pseudo-Gibbs updates need (predictor.py:80-100,126-130):
-//   sum_i exp(-eta_sigma_i),  sum_i r_i,  sum_i r_i^2   with r = (y - eta_mu) exp(-eta_sigma)
-enum StatSlot { SL_SEINV = 3, SL_SR = 4, SL_SR2 = 5 };
-constexpr int kLogpSlots = 6;
+//   sum_i w_i,  sum_i r_i,  sum_i r_i^2,  sum_i w_i^2,  sum_i r_i w_i
+// with w = exp(-eta_sigma), r = (y - eta_mu) w.  The last two make the SEQUENTIAL update exact
+// in one sweep: LogScaleIntercept sees the loc predictor with the UPDATED beta0
+// (predictor.py:604-609), and std(r - d w) needs sum w^2 and sum r w for the shift d.
+enum StatSlot { SL_SEINV = 3, SL_SR = 4, SL_SR2 = 5, SL_SW2 = 6, SL_SRW = 7 };
+constexpr int kLogpSlots = 8;
+constexpr int kNumStats = 5;
 
 template <typename R>
 struct MainArgs {
@@ -67,22 +72,6 @@ struct MainArgs {
 #define PTM_TERM_UNROLL 2  // terms of one predictor evaluated per unrolled eval-loop iteration
 #endif
 constexpr int kTermUnroll = PTM_TERM_UNROLL;
-// Experiment (off by default): eval warps first, registers re-split between the roles with
-// setmaxnreg (eval PTM_RESPLIT_EVAL, others PTM_RESPLIT_TERM) and two observations per
-// eval-loop iteration.  Needs NU % 4 == 0 and a CTA padded to whole warpgroups.
-#ifndef PTM_RESPLIT
-#define PTM_RESPLIT 0
-#endif
-#ifndef PTM_RESPLIT_EVAL
-#define PTM_RESPLIT_EVAL 128
-#endif
-#ifndef PTM_RESPLIT_TERM
-#define PTM_RESPLIT_TERM 72
-#endif
-// Experiment: the eval warps carry two observations in lockstep (see the eval loop).
-#ifndef PTM_EVAL_PAIR
-#define PTM_EVAL_PAIR 0
-#endif
 #ifndef PTM_EVAL_UNROLL
 #define PTM_EVAL_UNROLL 1
 #endif
@@ -296,15 +285,12 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   // layout that is used) the two term warps of a pair read the same staged slot for their
   // backward; with TPW = 2 one warp runs both accumulator sets through one switch-lowered
   // dispatch (measured slower: 44.8 vs 42.7 ms at the shared c3 variant, kept for reference).
-  static_assert(!(SHARED && PTM_EVAL_PAIR), "the lockstep-pair experiment has no shared-design gather");
   // TPW = smooth terms per term warp: 1 up to 12 terms; 2 beyond (the CTA then has
   // ceil(T/2) term warps with two accumulator sets each, which leaves room for eval warps
   // at their full register budget)
   static_assert(TPW == 1 || TPW == 2, "one or two terms per term warp");
-  static_assert(!(PTM_RESPLIT && TPW > 1), "the register re-split experiment is single-term only");
   constexpr bool GRAD = MODE == kModeGrad;
   constexpr bool POINT = MODE == kModePoint;
-  constexpr bool kPair = PTM_EVAL_PAIR != 0;  // lockstep pairs in the eval warps (experiment)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -325,18 +311,10 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   double* s_red = reinterpret_cast<double*>(s_g);  // [NU][kRegSlots][32] scalar partials (double),
                    // written after the last tile only: they reuse the dl/deta tiles
 
-#if PTM_RESPLIT
-  const bool is_term = warp >= NU && warp < NU + T;
-  const bool is_pad = warp >= NU + T;
-  const int uw = warp;       // eval warp index when warp < NU
-  const int tq = warp - NU;  // term slot
-#else
   const int NTW = (T + TPW - 1) / TPW;  // term warps
   const bool is_term = warp < NTW;
-  constexpr bool is_pad = false;
   const int uw = warp - NTW;  // eval warp index when !is_term
   const int tq = warp;        // term warp index: owns the staging slots q = tq * TPW + k
-#endif
 
   // term-warp constants (per owned term k)
   int t_nb[TPW], t_pred[TPW], t_term[TPW];
@@ -371,9 +349,6 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
   // The roles run their own work-item loops (no code is shared after the role split, so a
   // register re-split between the roles stays possible); they meet at the CTA barriers.
   if (is_term) {
-#if PTM_RESPLIT
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PTM_RESPLIT_TERM));
-#endif
   for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int cg = item / a.M;
     const int mchunk = item - cg * a.M;
@@ -513,32 +488,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
     cta_bar();
     cta_bar();
   }
-  } else if (is_pad) {
-#if PTM_RESPLIT
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PTM_RESPLIT_TERM));
-#endif
-  for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-    const int cg = item / a.M;
-    const int mchunk = item - cg * a.M;
-    const long long o_begin = a.obs_begin + (long long)mchunk * a.chunk_len;
-    long long o_end = o_begin + a.chunk_len;
-    if (o_end > a.obs_end) o_end = a.obs_end;
-    const long long len = o_end > o_begin ? o_end - o_begin : 0;
-    const int ntiles = (int)((len + To - 1) / To);
-    int chain = cg * 32 + lane;
-    if (chain >= a.C) chain = a.C - 1;
-    double* pout = a.partial + (long long)item * a.NSLOT * 32;
-
-    cta_bar();
-    for (int s = 0; s <= ntiles; ++s) cta_bar();
-    cta_bar();
-    cta_bar();
-    (void)pout; (void)chain;
-  }
   } else {
-#if PTM_RESPLIT
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PTM_RESPLIT_EVAL));
-#endif
   for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int cg = item / a.M;
     const int mchunk = item - cg * a.M;
@@ -585,191 +535,6 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
           const int cnt = (int)((o_end - base) < To ? (o_end - base) : To);
           // (interleaving two observations per warp by unrolling was measured slower: the
           //  extra live values push the eval warps over their 96-register budget)
-          // (off by default: 40.5 vs 41.5 ms at c3 with the register re-split, no gain with two
-          //  terms per warp -- DESIGN.md section 4.2)
-          if constexpr (kPair && !POINT) {
-          // Two observations per eval warp in lockstep (o0 and o0 + NU): every straight-line
-          // stage below carries both, so the scheduler can overlap their dependency chains.
-          for (int o0 = uw; o0 < cnt; o0 += 2 * NU) {
-            const bool vB = o0 + NU < cnt;  // the second slot repeats the first one when absent
-            const int oo[2] = {o0, vB ? o0 + NU : o0};
-            R yv[2], em[2], es[2];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) { yv[k] = a.y[base + oo[k]]; em[k] = beta0; es[k] = gamma0; }
-            {
-              const R* bqA = s_b + (slot * To + oo[0]) * 4;
-              const R* bqB = s_b + (slot * To + oo[1]) * 4;
-              const R* gl = s_gam + lane;
-              const int qstep = 3 * To;
-              int q = 0;
-#pragma unroll kTermUnroll
-              for (; q < a.T_loc; ++q, bqA += qstep * 4, bqB += qstep * 4) {
-                R b0, b1, b2, b3, c0, c1, c2, c3;
-                int joA, joB;
-                load3j(bqA, b0, b1, b2, b3, joA);
-                load3j(bqB, c0, c1, c2, c3, joB);
-                const R* gA = gl + joA;
-                const R* gB = gl + joB;
-                R fA = b0 * gA[0], fB = c0 * gB[0];
-                fA = fma(b1, gA[32], fA); fB = fma(c1, gB[32], fB);
-                fA = fma(b2, gA[64], fA); fB = fma(c2, gB[64], fB);
-                fA = fma(b3, gA[96], fA); fB = fma(c3, gB[96], fB);
-                em[0] += fA; em[1] += fB;
-              }
-#pragma unroll kTermUnroll
-              for (; q < T; ++q, bqA += qstep * 4, bqB += qstep * 4) {
-                R b0, b1, b2, b3, c0, c1, c2, c3;
-                int joA, joB;
-                load3j(bqA, b0, b1, b2, b3, joA);
-                load3j(bqB, c0, c1, c2, c3, joB);
-                const R* gA = gl + joA;
-                const R* gB = gl + joB;
-                R fA = b0 * gA[0], fB = c0 * gB[0];
-                fA = fma(b1, gA[32], fA); fB = fma(c1, gB[32], fB);
-                fA = fma(b2, gA[64], fA); fB = fma(c2, gB[64], fB);
-                fA = fma(b3, gA[96], fA); fB = fma(c3, gB[96], fB);
-                es[0] += fA; es[1] += fB;
-              }
-            }
-            R einv[2], r[2], rc[2];
-            int code[2];
-            CoreEval<R> ev[2];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              einv[k] = fast_exp(-es[k]);
-              r[k] = (yv[k] - em[k]) * einv[k];
-              code[k] = region_code(ts, r[k]);
-              rc[k] = r[k] < ts.a ? ts.a : (r[k] > ts.b ? ts.b : (r[k] == r[k] ? r[k] : ts.a));
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) core_locate_fast(ts, a.grid, rc[k], ev[k]);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const R* cp = s_cc + (ev[k].kk * 5) * 32 + lane;
-              core_eval(ts, cp[0], cp[32], cp[64], cp[96], cp[128], ev[k]);
-            }
-            R z[2], d[2], dzdr[2], dddr[2];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) { z[k] = ev[k].z; d[k] = ev[k].d; dzdr[k] = ev[k].d; dddr[k] = ev[k].d2; }
-            const bool all_core = code[0] == 2 && code[1] == 2;
-            if (!all_core) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                if (code[k] != 2) {
-                  ChainBoundary<R> cb;
-                  make_boundary(ts, s_cc[(KK * 5 + 0) * 32 + lane], s_cc[(KK * 5 + 1) * 32 + lane],
-                                s_cc[(KK * 5 + 2) * 32 + lane], s_cc[(KK * 5 + 3) * 32 + lane], cb);
-                  const R rr = r[k];
-                  if (code[k] == 1) {
-                    const R poly = rr * ts.a - R(0.5) * rr * rr;
-                    z[k] = (ts.inv_w * poly + cb.dL * (rr - poly * ts.inv_w)) + cb.constL;
-                    const R q = (ts.a - rr) * ts.inv_w;
-                    d[k] = (R(1) - q) * cb.dL + q;
-                    dzdr[k] = d[k]; dddr[k] = (cb.dL - R(1)) * ts.inv_w;
-                  } else if (code[k] == 3) {
-                    const R poly = R(0.5) * rr * rr - rr * ts.b;
-                    z[k] = (ts.inv_w * poly + cb.dR * (rr - poly * ts.inv_w)) + cb.constR;
-                    const R q = (rr - ts.b) * ts.inv_w;
-                    d[k] = (R(1) - q) * cb.dR + q;
-                    dzdr[k] = d[k]; dddr[k] = (R(1) - cb.dR) * ts.inv_w;
-                  } else if (code[k] == 0) {
-                    z[k] = cb.ztailL - (ts.min_eps - rr);
-                    d[k] = R(1); dzdr[k] = R(1); dddr[k] = R(0);
-                  } else {
-                    z[k] = cb.ztailR + (rr - ts.max_eps);
-                    d[k] = R(1); dzdr[k] = R(1); dddr[k] = R(0);
-                  }
-                }
-              }
-            }
-            const R tiny = tiny_of<R>();
-            bool above[2];
-            R dcl[2];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const bool val = k == 0 || vB;
-              above[k] = d[k] > tiny;
-              dcl[k] = above[k] ? d[k] : tiny;
-              a_z2 += val ? (double)(z[k] * z[k]) : 0.0;
-              a_ls += val ? (double)es[k] : 0.0;
-              if (MODE == kModeLogp) {
-                a_gb0 += val ? (double)einv[k] : 0.0;
-                a_gg0 += val ? (double)r[k] : 0.0;
-                a_gvl += val ? (double)(r[k] * r[k]) : 0.0;
-              }
-              R mant; int ex;
-              split_mant(dcl[k], mant, ex);
-              a_pm *= val ? mant : R(1);
-              a_pe += val ? ex : 0;
-            }
-            if (GRAD) {
-              R lz[2], ld[2];
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const bool val = k == 0 || vB;
-                lz[k] = val ? -z[k] : R(0);
-                ld[k] = (val && above[k]) ? fast_rcp(dcl[k]) : R(0);
-                const R gr = fma(lz[k], dzdr[k], ld[k] * dddr[k]);
-                const R gmu = -gr * einv[k];
-                const R gls = fma(-gr, r[k], R(-1));
-                if (val) {
-                  gb[oo[k] * 64] = gmu;
-                  gb[oo[k] * 64 + 32] = gls;
-                  a_gb0 += (double)gmu;
-                  a_gg0 += (double)gls;
-                }
-              }
-              R w[2][5];
-#pragma unroll
-              for (int k = 0; k < 2; ++k)
-                core_backward(ts, ev[k], code[k] == 2 ? lz[k] : R(0), code[k] == 2 ? ld[k] : R(0), w[k]);
-              R u0[2], u1[2], u2[2], u3[2], u4[2];
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const bool lastp = ev[k].kk + 1 >= KK;
-                const R w4 = lastp ? R(0) : w[k][4];
-                const R g3 = w[k][3] - w4;
-                u0[k] = (w[k][0] - g3) * sixth + (w[k][2] - w[k][1]) * R(0.5);
-                u1[k] = (R(4) * w[k][0] - w4) * sixth - w[k][2] + g3 * R(0.5);
-                u2[k] = w[k][0] * sixth + (w[k][1] + w[k][2] - g3 + w4) * R(0.5);
-                u3[k] = g3 * sixth - w4 * R(0.5);
-                u4[k] = w4 * sixth;
-              }
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                R* gp = gvp + ev[k].kk * 32;
-                gp[0] += u0[k];
-                gp[32] += u1[k];
-                gp[64] += u2[k];
-                gp[96] += u3[k];
-                gp[128] += u4[k];
-              }
-              if (!all_core) {
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                  if (code[k] != 2 && (k == 0 || vB)) {
-                    const R rr = r[k];
-                    if (code[k] == 1) {
-                      const R q = (ts.a - rr) * ts.inv_w;
-                      a_gvl += (double)lz[k];
-                      a_gdl += (double)fma(lz[k], cL_of(ts, rr), ld[k] * (R(1) - q));
-                    } else if (code[k] == 3) {
-                      const R q = (rr - ts.b) * ts.inv_w;
-                      a_gvr += (double)lz[k];
-                      a_gdr += (double)fma(lz[k], cR_of(ts, rr), ld[k] * (R(1) - q));
-                    } else if (code[k] == 0) {
-                      a_gvl += (double)lz[k];
-                      a_gdl += (double)(lz[k] * cL_of(ts, ts.min_eps));
-                    } else {
-                      a_gvr += (double)lz[k];
-                      a_gdr += (double)(lz[k] * cR_of(ts, ts.max_eps));
-                    }
-                  }
-                }
-              }
-            }
-          }
-          } else
           {
 #pragma unroll kEvalUnroll
           for (int o = uw; o < cnt; o += NU) {
@@ -921,6 +686,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) k_main(const MainArgs<R> a) {
               a_gb0 += (double)einv;
               a_gg0 += (double)r;
               a_gvl += (double)(r * r);
+              a_gdl += (double)(einv * einv);
+              a_gvr += (double)(r * einv);
             }
             {
               R mant; int ex;
@@ -1099,9 +866,10 @@ template <typename R>
 struct PostArgs {
   const R* params;   // [C][P]
   const double* partial;  // [CG*M][NSLOT][32]
-  R* logp;           // [C]
-  R* grad;           // [C][P] or null
-  R* stats;          // [C][3] or null (logp-only sweep): sum exp(-eta_sigma), sum r, sum r^2
+  R* logp;           // logp of chain c at logp[c * ld_logp]
+  R* grad;           // gradient row of chain c at grad + c * ld_grad (P entries), or null
+  long long ld_logp, ld_grad;  // 1 / P for separate arrays; 1 + P for the packed [C][1 + P] block
+  R* stats;          // [C][kNumStats] or null (logp-only sweep): StatSlot sums
   const R* Zall;
   const R* Kall;     // packed K_t [p_t][p_t]
   const R* Zd;
@@ -1122,7 +890,7 @@ __global__ void k_post(const PostArgs<R> a) {
   typedef double D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   D* red = reinterpret_cast<D*>(smem_raw);  // [NSLOT][32]
-  D* s_lp = red + a.NSLOT * 32;             // [32] prior accumulator per chain
+  D* s_lp = red + a.NSLOT * 32;             // [T][32] smooth-term prior per (term, chain)
   const int cg = blockIdx.x;
   const int tid = threadIdx.x;
   const int KK = a.KK;
@@ -1132,7 +900,6 @@ __global__ void k_post(const PostArgs<R> a) {
     for (int m = 0; m < a.M; ++m) v += pp[(long long)m * a.NSLOT * 32];
     red[idx] = v;
   }
-  if (tid < 32) s_lp[tid] = 0.0;
   __syncthreads();
   const D half_log_2pi = 0.91893853320467274178;
 
@@ -1153,11 +920,12 @@ __global__ void k_post(const PostArgs<R> a) {
       quad = fma((D)b[i], kb, quad);
     }
     const D it2 = 1.0 / (tau * tau);
+    // one slot per (term, chain), summed over t in a fixed order below: bit-reproducible
+    s_lp[t * 32 + lane] = -(log(tau) * (D)a.rank[t] + 0.5 * quad * it2);
     if (a.add_priors) {
-      atomicAdd(&s_lp[lane], -(log(tau) * (D)a.rank[t] + 0.5 * quad * it2));
-      if (GRAD) a.grad[(long long)c * a.P + a.tau_off + t] = (R)(-(D)a.rank[t] / tau + quad * it2 / tau);
+      if (GRAD) a.grad[(long long)c * a.ld_grad + a.tau_off + t] = (R)(-(D)a.rank[t] / tau + quad * it2 / tau);
     } else if (GRAD) {
-      a.grad[(long long)c * a.P + a.tau_off + t] = R(0);
+      a.grad[(long long)c * a.ld_grad + a.tau_off + t] = R(0);
     }
   }
   if (GRAD) {
@@ -1181,7 +949,7 @@ __global__ void k_post(const PostArgs<R> a) {
           for (int i = 0; i < p; ++i) kb = fma((D)Kt[k * p + i], (D)b[i], kb);
           v -= kb / (tau * tau);
         }
-        a.grad[(long long)c * a.P + a.boff[t] + k] = (R)v;
+        a.grad[(long long)c * a.ld_grad + a.boff[t] + k] = (R)v;
       }
     }
   }
@@ -1201,17 +969,20 @@ __global__ void k_post(const PostArgs<R> a) {
       D lp = -0.5 * red[SL_Z2 * 32 + lane] + red[SL_LOGD * 32 + lane] - red[SL_LS * 32 + lane] -
              (D)a.n_obs * half_log_2pi;
       if (a.add_priors) {
-        lp += s_lp[lane];
+        for (int t = 0; t < a.T; ++t) lp += s_lp[t * 32 + lane];
         lp += -0.5 * ss / (taud * taud) - (D)(np_ - 1) * (log(taud) + half_log_2pi);
       }
-      a.logp[c] = (R)lp;
+      a.logp[(long long)c * a.ld_logp] = (R)lp;
       if (!GRAD && a.stats != nullptr) {
-        a.stats[c * 3 + 0] = (R)red[SL_SEINV * 32 + lane];
-        a.stats[c * 3 + 1] = (R)red[SL_SR * 32 + lane];
-        a.stats[c * 3 + 2] = (R)red[SL_SR2 * 32 + lane];
+        R* so = a.stats + (long long)c * kNumStats;
+        so[0] = (R)red[SL_SEINV * 32 + lane];
+        so[1] = (R)red[SL_SR * 32 + lane];
+        so[2] = (R)red[SL_SR2 * 32 + lane];
+        so[3] = (R)red[SL_SW2 * 32 + lane];
+        so[4] = (R)red[SL_SRW * 32 + lane];
       }
       if (GRAD) {
-        R* go = a.grad + (long long)c * a.P;
+        R* go = a.grad + (long long)c * a.ld_grad;
         go[0] = (R)red[SL_GB0 * 32 + lane];
         go[1] = (R)red[SL_GG0 * 32 + lane];
         go[a.taud_off] = a.add_priors ? (R)(ss / (taud * taud * taud) - (D)(np_ - 1) / taud) : R(0);

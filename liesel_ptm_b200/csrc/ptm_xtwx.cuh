@@ -321,7 +321,7 @@ int xtwx_sweep(XtwxArgs<R>& a, double* partial, int num_sms, cudaStream_t st, in
   a.M = (int)M;
   a.chunk_len = chunk;
   a.n_items = a.CG * a.M;
-  cudaError_t e = cudaFuncSetAttribute(k_xtwx<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_smem(k_xtwx<R>, smem);
   if (e != cudaSuccess) return (int)e;
   const int warps = (a.NW + NS + 3) / 4 * 4;
   const int grid = std::min(a.n_items, num_sms);

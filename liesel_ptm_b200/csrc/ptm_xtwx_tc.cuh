@@ -701,7 +701,7 @@ inline int xtwx_tc_sweep(XtwxArgs<float>& a, double* partial, int num_sms, int f
   const int grid = std::min(a.n_items, num_sms);
   cudaError_t e = cudaSuccess;
   auto launch = [&](auto kern) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_smem(kern, smem);
     if (e == cudaSuccess) kern<<<grid, 32 * warps, smem, st>>>(g);
   };
   switch (a.nsc) {
@@ -765,7 +765,7 @@ inline int xtwx_tc2_sweep(XtwxArgs<float>& a, double* partial, int num_sms, int 
   a.chunk_len = chunk;
   a.n_items = g.CB * a.M;
   g.a = a;
-  cudaError_t e = cudaFuncSetAttribute(k_xtwx_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_smem(k_xtwx_tc2, smem);
   if (e != cudaSuccess) return (int)e;
   const int warps = (kTcWW + NS + 2 + 3) / 4 * 4;
   const int grid = std::min(a.n_items, num_sms);

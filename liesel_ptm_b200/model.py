@@ -30,6 +30,21 @@ from .spline import Basis, PTMKnots, approx_grid, term, trafo_reparam
 _NP = {torch.float64: np.float64, torch.float32: np.float32}
 
 
+def _on_device(fn):
+    """Run an operator with the model's GPU as the current device (the C ABI launches on the
+    current device and refuses a handle that lives elsewhere)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+
+    return wrapped
+
+
 class _Predictor:
     """``model.loc`` / ``model.scale``: supports ``+=`` with a term (predictor.py:23-60)."""
 
@@ -70,6 +85,10 @@ class LocScalePTM:
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self._handle = None
+        self._view = None    # observation-shard view handle (ptm_problem_shard_view), if any
+        self._owner = True   # this object destroys the problem handle
+        self._parent = None  # shard views keep the owning model alive
+        self.shard = None
         self._ws = None
         self._ws_chains = 0
         self.is_built = False
@@ -183,9 +202,12 @@ class LocScalePTM:
 
     def __del__(self):
         try:
-            if self._handle is not None:
+            if self._view is not None:
+                self._lib.ptm_problem_destroy(self._view)
+                self._view = None
+            if self._handle is not None and self._owner:
                 self._lib.ptm_problem_destroy(self._handle)
-                self._handle = None
+            self._handle = None
         except Exception:
             pass
 
@@ -227,7 +249,7 @@ class LocScalePTM:
     # -- device plumbing -------------------------------------------------------------------
     def _workspace(self, n_chains: int) -> torch.Tensor:
         if self._ws is None or self._ws_chains != n_chains:
-            nbytes = int(self._lib.ptm_workspace_bytes(self._handle, n_chains))
+            nbytes = int(self._lib.ptm_workspace_bytes(self._h, n_chains))
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._ws_chains = n_chains
         return self._ws
@@ -247,12 +269,52 @@ class LocScalePTM:
     def _stream() -> int:
         return torch.cuda.current_stream().cuda_stream
 
+    @property
+    def _h(self):
+        """The handle the operators run on: the shard view when one is set, else the problem."""
+        return self._view if self._view is not None else self._handle
+
+    def _make_view(self, obs_begin: int, obs_end: int, add_priors: bool):
+        if not self.is_built:
+            raise RuntimeError("call build() first")
+        h = C.c_void_p()
+        _lib.check(self._lib.ptm_problem_shard_view(self._handle, obs_begin, obs_end, int(add_priors),
+                                                    C.byref(h)))
+        return h
+
+    def shard_view(self, obs_begin: int, obs_end: int, add_priors: bool = True) -> "LocScalePTM":
+        """Observation-axis sharding: a NEW model object over the same device arrays that
+        evaluates observations [obs_begin, obs_end) only (``ptm_problem_shard_view``).  The
+        model it was made from is untouched; precision / Cholesky entry points raise on a view
+        (they are not additive over shards -- see ``parallel.ObsShardedLogProb.precision``)."""
+        import copy
+
+        h = self._make_view(obs_begin, obs_end, add_priors)
+        v = copy.copy(self)
+        v._view, v._owner, v._parent = h, False, self  # the view keeps the owning model alive
+        v._ws, v._ws_chains = None, 0
+        v.shard = (int(obs_begin), int(obs_end), bool(add_priors))
+        for name in ("_pin_in", "_pin_lp", "_pin_g", "_dev_in", "_dev_lp", "_dev_g"):
+            v.__dict__.pop(name, None)
+        return v
+
     def set_shard(self, obs_begin: int, obs_end: int, add_priors: bool = True) -> None:
-        """Observation-axis sharding: this handle evaluates [obs_begin, obs_end) only."""
-        _lib.check(self._lib.ptm_problem_set_shard(self._handle, obs_begin, obs_end, int(add_priors)))
-        self._ws = None
+        """In-place convenience over ``ptm_problem_shard_view`` (single-process checks): this
+        object's operators run on a view of its problem until the full range is set again.
+        The C handles themselves are immutable."""
+        h = self._make_view(obs_begin, obs_end, add_priors)
+        if self._view is not None:
+            self._lib.ptm_problem_destroy(self._view)
+        full = obs_begin == 0 and obs_end == self.n and add_priors
+        if full:
+            self._lib.ptm_problem_destroy(h)
+            h = None
+        self._view = h
+        self.shard = None if full else (int(obs_begin), int(obs_end), bool(add_priors))
+        self._ws, self._ws_chains = None, 0
 
     # -- the operators -----------------------------------------------------------------------
+    @_on_device
     def log_prob(self, params: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """Model log-density for a batch of chain states [C, P] -> [C]."""
         params = self._check_params(params)
@@ -260,10 +322,11 @@ class LocScalePTM:
         ws = self._workspace(Cn)
         logp = out if out is not None else torch.empty(Cn, dtype=self.dtype, device=self.device)
         f = getattr(self._lib, f"ptm_logp_{self._sfx}")
-        _lib.check(f(self._handle, params.data_ptr(), Cn, logp.data_ptr(), ws.data_ptr(), ws.numel(),
+        _lib.check(f(self._h, params.data_ptr(), Cn, logp.data_ptr(), ws.data_ptr(), ws.numel(),
                      self._stream()))
         return logp
 
+    @_on_device
     def log_prob_and_grad(self, params: torch.Tensor, out_logp: torch.Tensor | None = None,
                           out_grad: torch.Tensor | None = None):
         """value_and_grad of the model log-density: [C, P] -> ([C], [C, P])."""
@@ -273,7 +336,7 @@ class LocScalePTM:
         logp = out_logp if out_logp is not None else torch.empty(Cn, dtype=self.dtype, device=self.device)
         grad = out_grad if out_grad is not None else torch.empty_like(params)
         f = getattr(self._lib, f"ptm_logp_grad_{self._sfx}")
-        _lib.check(f(self._handle, params.data_ptr(), Cn, logp.data_ptr(), grad.data_ptr(), ws.data_ptr(),
+        _lib.check(f(self._h, params.data_ptr(), Cn, logp.data_ptr(), grad.data_ptr(), ws.data_ptr(),
                      ws.numel(), self._stream()))
         return logp, grad
 
@@ -294,6 +357,20 @@ class LocScalePTM:
         torch.cuda.current_stream().synchronize()
         return self._pin_lp.numpy(), self._pin_g.numpy()
 
+    @_on_device
+    def log_prob_and_grad_block(self, params: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """logp and gradient as ONE contiguous [C, 1 + P] block (column 0 = logp), written in
+        place by the epilogue kernel: the payload of the observation-axis all-reduce."""
+        params = self._check_params(params)
+        Cn = params.shape[0]
+        ws = self._workspace(Cn)
+        block = out if out is not None else torch.empty((Cn, 1 + self.num_params), dtype=self.dtype,
+                                                        device=self.device)
+        f = getattr(self._lib, f"ptm_logp_grad_block_{self._sfx}")
+        _lib.check(f(self._h, params.data_ptr(), Cn, block.data_ptr(), ws.data_ptr(), ws.numel(),
+                     self._stream()))
+        return block
+
     def last_launch_count(self) -> int:
         return int(self._lib.ptm_last_launch_count())
 
@@ -310,21 +387,23 @@ class LocScalePTM:
     def shared_designs(self) -> int:
         """Location / scale term pairs on the same covariate and knots that the sweeps stage
         and gather once (0 = general layout)."""
-        return int(self._lib.ptm_problem_shared_designs(self._handle)) if self.is_built else 0
+        return int(self._lib.ptm_problem_shared_designs(self._h)) if self.is_built else 0
 
     def last_kernel_ms(self) -> tuple[float, float, float]:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         _lib.check(self._lib.ptm_last_kernel_ms(C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    @_on_device
     def basis(self, term_index: int):
         """Banded design of a term: (interval [n] int32, values [n, 4])."""
         interval = torch.empty(self.n, dtype=torch.int32, device=self.device)
         values = torch.empty((self.n, 4), dtype=self.dtype, device=self.device)
         f = getattr(self._lib, f"ptm_basis_{self._sfx}")
-        _lib.check(f(self._handle, term_index, interval.data_ptr(), values.data_ptr(), self._stream()))
+        _lib.check(f(self._h, term_index, interval.data_ptr(), values.data_ptr(), self._stream()))
         return interval, values
 
+    @_on_device
     def transform(self, delta: torch.Tensor, r: torch.Tensor):
         """h(r), h'(r) for raw shape coefficients delta [C, nparam] or [nparam]
         (TransformationSpline.dot_and_deriv_n_fullbatch, bspline/util.py:91-103)."""
@@ -341,7 +420,7 @@ class LocScalePTM:
         dz = torch.empty_like(z)
         cell = torch.empty(m, dtype=torch.int32, device=self.device)
         f = getattr(self._lib, f"ptm_transform_{self._sfx}")
-        _lib.check(f(self._handle, d2.data_ptr(), Cn, rv.data_ptr(), m, z.data_ptr(), dz.data_ptr(),
+        _lib.check(f(self._h, d2.data_ptr(), Cn, rv.data_ptr(), m, z.data_ptr(), dz.data_ptr(),
                      cell.data_ptr(), self._stream()))
         self.last_cell = cell
         if squeeze:
@@ -350,6 +429,7 @@ class LocScalePTM:
             z, dz = z[..., 0], dz[..., 0]
         return z, dz
 
+    @_on_device
     def inverse(self, delta: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
         """r with h(r) = z for raw shape coefficients delta [C, nparam] or [nparam]
         (TransformationSpline.dot_inverse_n, bspline/util.py:105-122): exact inverse of the
@@ -365,7 +445,7 @@ class LocScalePTM:
         Cn, m = d2.shape[0], zv.shape[0]
         r = torch.empty((Cn, m), dtype=self.dtype, device=self.device)
         f = getattr(self._lib, f"ptm_inverse_{self._sfx}")
-        _lib.check(f(self._handle, d2.data_ptr(), Cn, zv.data_ptr(), m, r.data_ptr(), self._stream()))
+        _lib.check(f(self._h, d2.data_ptr(), Cn, zv.data_ptr(), m, r.data_ptr(), self._stream()))
         if squeeze:
             r = r[0]
         if was_scalar:
@@ -390,7 +470,8 @@ class LocScalePTM:
                 x = np.asarray(newdata[t.basis.xname], dtype=nd).reshape(-1)
             kn = t.basis.knots
             lo, hi = kn[3], kn[t.basis.nbases]
-            if x.size and not (np.nanmin(x) >= lo and np.nanmax(x) <= hi):
+            # NaN fails the comparison like jnp.min / jnp.max propagate it (approx.py:197-206)
+            if x.size and not (x.min() >= lo and x.max() <= hi):
                 raise ValueError(f"Values of x are not inside the range of interior knots, [{lo}, {hi}]")
             cols.append(x)
         g = self.response if grid is None else np.asarray(grid, dtype=nd).reshape(-1)
@@ -403,6 +484,7 @@ class LocScalePTM:
         return (torch.from_numpy(np.ascontiguousarray(g, dtype=nd)).to(self.device),
                 torch.from_numpy(np.ascontiguousarray(X, dtype=nd)).to(self.device), m)
 
+    @_on_device
     def summarise_dist(self, samples: torch.Tensor, grid=None, newdata=None,
                        which=("z", "prob", "log_prob", "cdf")) -> dict:
         """z, prob, log_prob, cdf over posterior samples [S, P] at ``grid`` (default: the
@@ -411,7 +493,7 @@ class LocScalePTM:
         samples = self._check_params(samples)
         g, X, m = self._newdata(newdata, grid)
         S = samples.shape[0]
-        ws = torch.empty(max(int(self._lib.ptm_predict_workspace_bytes(self._handle, S)), 1),
+        ws = torch.empty(max(int(self._lib.ptm_predict_workspace_bytes(self._h, S)), 1),
                          dtype=torch.uint8, device=self.device)
         want_lp = "log_prob" in which or "prob" in which
         out = {}
@@ -420,7 +502,7 @@ class LocScalePTM:
         cdf = torch.empty((S, m), dtype=self.dtype, device=self.device) if "cdf" in which else None
         f = getattr(self._lib, f"ptm_predict_{self._sfx}")
         ptr = lambda t: 0 if t is None else t.data_ptr()  # noqa: E731
-        _lib.check(f(self._handle, samples.data_ptr(), S, g.data_ptr(), X.data_ptr(), m, ptr(z), ptr(lpdf),
+        _lib.check(f(self._h, samples.data_ptr(), S, g.data_ptr(), X.data_ptr(), m, ptr(z), ptr(lpdf),
                      ptr(cdf), ws.data_ptr(), ws.numel(), self._stream()))
         if z is not None:
             out["z"] = z
@@ -432,6 +514,7 @@ class LocScalePTM:
             out["cdf"] = cdf
         return out
 
+    @_on_device
     def predict_quantile(self, samples: torch.Tensor, u, newdata=None) -> torch.Tensor:
         """Predictive quantiles [S, m] at probabilities ``u`` (scalar or one per row):
         init_dist(samples, newdata=...).quantile(u) (dist.py:203-209)."""
@@ -439,38 +522,41 @@ class LocScalePTM:
         uv = np.asarray(u, dtype=self.np_dtype).reshape(-1)
         g, X, m = self._newdata(newdata, uv)
         S = samples.shape[0]
-        ws = torch.empty(max(int(self._lib.ptm_predict_workspace_bytes(self._handle, S)), 1),
+        ws = torch.empty(max(int(self._lib.ptm_predict_workspace_bytes(self._h, S)), 1),
                          dtype=torch.uint8, device=self.device)
         yq = torch.empty((S, m), dtype=self.dtype, device=self.device)
         f = getattr(self._lib, f"ptm_predict_quantile_{self._sfx}")
-        _lib.check(f(self._handle, samples.data_ptr(), S, g.data_ptr(), X.data_ptr(), m, yq.data_ptr(),
+        _lib.check(f(self._h, samples.data_ptr(), S, g.data_ptr(), X.data_ptr(), m, yq.data_ptr(),
                      ws.data_ptr(), ws.numel(), self._stream()))
         return yq
 
+    @_on_device
     def intercept_stats(self, params: torch.Tensor) -> torch.Tensor:
-        """[C, 3] sufficient statistics of the intercept pseudo-Gibbs updates: sum exp(-eta_sigma),
-        sum r, sum r^2 over this handle's observation range (additive over shards)."""
+        """[C, 5] sufficient statistics of the intercept pseudo-Gibbs updates: sum w, sum r,
+        sum r^2, sum w^2, sum r w (w = exp(-eta_sigma), r = (y - eta_mu) w) over this handle's
+        observation range (additive over shards)."""
         params = self._check_params(params)
         Cn = params.shape[0]
         ws = self._workspace(Cn)
-        out = torch.empty((Cn, 3), dtype=self.dtype, device=self.device)
+        out = torch.empty((Cn, 5), dtype=self.dtype, device=self.device)
         f = getattr(self._lib, f"ptm_intercept_stats_{self._sfx}")
-        _lib.check(f(self._handle, params.data_ptr(), Cn, out.data_ptr(), ws.data_ptr(), ws.numel(),
+        _lib.check(f(self._h, params.data_ptr(), Cn, out.data_ptr(), ws.data_ptr(), ws.numel(),
                      self._stream()))
         return out
 
+    @_on_device
     def pointwise(self, samples: torch.Tensor):
         """Pointwise predictive records over posterior samples [S, P] (draws x chains
         flattened): (lppd_i [n], p_waic_i [n]) -- EvaluatePTM._lppdi / .waic
         (model/evaluate.py:106-133, 177-236) as one fused sweep."""
         samples = self._check_params(samples)
         S = samples.shape[0]
-        nbytes = int(self._lib.ptm_pointwise_workspace_bytes(self._handle, S))
+        nbytes = int(self._lib.ptm_pointwise_workspace_bytes(self._h, S))
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
         lppd = torch.zeros(self.n, dtype=self.dtype, device=self.device)
         pwaic = torch.zeros(self.n, dtype=self.dtype, device=self.device)
         f = getattr(self._lib, f"ptm_pointwise_{self._sfx}")
-        _lib.check(f(self._handle, samples.data_ptr(), S, lppd.data_ptr(), pwaic.data_ptr(), ws.data_ptr(),
+        _lib.check(f(self._h, samples.data_ptr(), S, lppd.data_ptr(), pwaic.data_ptr(), ws.data_ptr(),
                      ws.numel(), self._stream()))
         return lppd, pwaic
 
@@ -485,19 +571,23 @@ class LocScalePTM:
                 "waic_se": float(elpd_i.std(unbiased=False) * n ** 0.5), "waic_p": p,
                 "waic_deviance": -2.0 * (lppd - p), "n_warning": int((p_i > 4).sum())}
 
-    def compute_intercepts(self, params: torch.Tensor, n_obs: int | None = None):
+    def compute_intercepts(self, params: torch.Tensor, sequential: bool = False):
         """LocationIntercept.compute_intercept / LogScaleIntercept.compute_intercept
         (predictor.py:80-100, 126-130) for every chain, from one fused sweep: returns
-        (beta0_new, gamma0_new) where gamma0_new is evaluated at the CURRENT beta0, as the
-        reference's two kernels each see the current state."""
-        st = self.intercept_stats(params)
-        n = float(self.n if n_obs is None else n_obs)
-        L = self.layout
-        m_e, m_r, m_r2 = st[:, 0] / n, st[:, 1] / n, st[:, 2] / n
-        beta0 = params[:, L["beta0"]] + m_r / m_e
-        gamma0 = params[:, L["gamma0"]] + 0.5 * torch.log(m_r2 - m_r * m_r)
-        return beta0, gamma0
+        (beta0_new, gamma0_new).  ``sequential=False``: both evaluated at the current state
+        (the reference's two Calc nodes, each seeing the current beta0).  ``sequential=True``:
+        gamma0_new as LogScaleIntercept sees it AFTER the location intercept was updated in
+        the same sampler sweep (it is wired to the full ``loc`` predictor, predictor.py:604-609)
+        -- exact from the same sums, no second sweep."""
+        if self.shard is not None and (self.shard[0] != 0 or self.shard[1] != self.n):
+            raise RuntimeError("compute_intercepts on an observation-shard view would use partial sums: "
+                               "all-reduce intercept_stats() and call parallel.intercepts_from_stats")
+        from .parallel import intercepts_from_stats
 
+        return intercepts_from_stats(self.intercept_stats(params), params, self.layout, self.n,
+                                     sequential=sequential)
+
+    @_on_device
     def quadform(self, params: torch.Tensor) -> torch.Tensor:
         """beta_t' K_t beta_t for every chain and term, [C, T]: the quadratic form of the
         Gibbs updates of the smoothing variances (gam/kernel.py:29-39, kernel.py:99-111)."""
@@ -505,9 +595,10 @@ class LocScalePTM:
         Cn = params.shape[0]
         out = torch.empty((Cn, len(self.terms)), dtype=self.dtype, device=self.device)
         f = getattr(self._lib, f"ptm_quadform_{self._sfx}")
-        _lib.check(f(self._handle, params.data_ptr(), Cn, out.data_ptr(), self._stream()))
+        _lib.check(f(self._h, params.data_ptr(), Cn, out.data_ptr(), self._stream()))
         return out
 
+    @_on_device
     def xtwx(self, term_index: int, params: torch.Tensor) -> torch.Tensor:
         params = self._check_params(params)
         Cn = params.shape[0]
@@ -515,10 +606,11 @@ class LocScalePTM:
         ws = self._workspace(Cn)
         out = torch.empty((Cn, p, p), dtype=self.dtype, device=self.device)
         f = getattr(self._lib, f"ptm_xtwx_{self._sfx}")
-        _lib.check(f(self._handle, term_index, params.data_ptr(), Cn, out.data_ptr(), ws.data_ptr(),
+        _lib.check(f(self._h, term_index, params.data_ptr(), Cn, out.data_ptr(), ws.data_ptr(),
                      ws.numel(), self._stream()))
         return out
 
+    @_on_device
     def precision(self, term_index: int, params: torch.Tensor, with_chol: bool = True):
         params = self._check_params(params)
         Cn = params.shape[0]
@@ -527,11 +619,12 @@ class LocScalePTM:
         P = torch.empty((Cn, p, p), dtype=self.dtype, device=self.device)
         L = torch.empty_like(P) if with_chol else None
         f = getattr(self._lib, f"ptm_loc_precision_{self._sfx}")
-        _lib.check(f(self._handle, term_index, params.data_ptr(), Cn, P.data_ptr(),
+        _lib.check(f(self._h, term_index, params.data_ptr(), Cn, P.data_ptr(),
                      L.data_ptr() if with_chol else None, ws.data_ptr(), ws.numel(), self._stream()))
         return P, L
 
 
+@_on_device
 def _precision_all(self, params: torch.Tensor, with_chol: bool = True):
     """Precision (and Cholesky factor) of every LOCATION term from one sweep: lists of
     [C, p_t, p_t] tensors in model order."""
@@ -543,7 +636,7 @@ def _precision_all(self, params: torch.Tensor, with_chol: bool = True):
     P = torch.empty(max(total, 1), dtype=self.dtype, device=self.device)
     L = torch.empty_like(P) if with_chol else None
     f = getattr(self._lib, f"ptm_loc_precision_all_{self._sfx}")
-    _lib.check(f(self._handle, params.data_ptr(), Cn, P.data_ptr(), L.data_ptr() if with_chol else None,
+    _lib.check(f(self._h, params.data_ptr(), Cn, P.data_ptr(), L.data_ptr() if with_chol else None,
                  ws.data_ptr(), ws.numel(), self._stream()))
     outP, outL, off = [], [], 0
     for p in ps_:

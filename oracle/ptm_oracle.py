@@ -837,10 +837,12 @@ class PTMModel:
         return out
 
     # --- intercept pseudo-Gibbs values (predictor.py:80-100, 126-130) ------
-    def compute_intercepts(self, st: ChainState, c: int):
+    def compute_intercepts(self, st: ChainState, c: int, sequential: bool = False):
         """LocationIntercept.compute_intercept and LogScaleIntercept.compute_intercept for
         chain c, literally: loc_model / log_scale_model are the predictors WITHOUT their
-        intercepts; the scale intercept sees loc = beta0 + loc_model at the current beta0."""
+        intercepts; the scale intercept sees the full loc predictor (predictor.py:604-609):
+        loc = beta0 + loc_model at the current beta0, or -- ``sequential`` -- at the location
+        intercept this call just computed (the sampler sweep updates beta0 first)."""
         mu, ls = self.predictors(st, c)
         loc_model = mu - st.beta0[c]
         log_scale_model = ls - st.gamma0[c]
@@ -849,7 +851,8 @@ class PTMModel:
         inv_scale_model_mean = np.exp(-log_mean_exp)
         residual_model_mean = np.mean((self.y - loc_model) * np.exp(-log_scale_model))
         beta0 = inv_scale_model_mean * residual_model_mean
-        gamma0 = np.log(np.std((self.y - mu) / np.exp(log_scale_model)))
+        loc = beta0 + loc_model if sequential else mu
+        gamma0 = np.log(np.std((self.y - loc) / np.exp(log_scale_model)))
         return beta0, gamma0
 
     # --- IWLS information (iwls_proposals.py:55-89, 118-144) --------------

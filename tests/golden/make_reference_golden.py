@@ -316,15 +316,20 @@ def ref_logp(m, out):
     # intercept pseudo-parameters (predictor.py:80-100, 126-130): loc_model / log_scale_model
     # are the predictors without their intercepts; the scale intercept sees the full loc
     icpt = np.zeros((C, 2))
+    icpt_seq = np.zeros(C)  # gamma_0 when LogScaleIntercept sees the UPDATED location intercept
     for c in range(C):
         b_loc, b_scale, _ = unpack(params[c])
         loc_model = terms[0]["basis"] @ (terms[0]["Z"] @ b_loc)
         log_scale_model = terms[1]["basis"] @ (terms[1]["Z"] @ b_scale)
         icpt[c, 0] = float(m.predictor.LocationIntercept.compute_intercept(y, loc_model, log_scale_model))
         icpt[c, 1] = float(m.predictor.LogScaleIntercept.compute_intercept(y, loc_model, log_scale_model))
+        # predictor.py:604-609: the scale intercept is wired to the full `loc` predictor, i.e. in
+        # a sampler sweep that updates beta_0 first it sees loc = beta_0(new) + loc_model
+        icpt_seq[c] = float(m.predictor.LogScaleIntercept.compute_intercept(
+            y, icpt[c, 0] + loc_model, log_scale_model))
 
     np.savez(os.path.join(out, "ref_logp_n257.npz"), y=y, ynan=ynan, precision=prec, chol=chol,
-             intercepts=icpt,
+             intercepts=icpt, intercepts_seq=icpt_seq,
              x_loc=x_loc, x_scale=x_scale,
              knots_loc=terms[0]["knots"], knots_scale=terms[1]["knots"],
              Z_loc=terms[0]["Z"], Z_scale=terms[1]["Z"], K_loc=terms[0]["K"], K_scale=terms[1]["K"],

@@ -92,3 +92,38 @@ def oracle_eval(case: Case):
     """logp [C] and packed gradient [C, P] from the NumPy oracle."""
     lp_, g = case.omodel.logp_and_grad(case.state)
     return lp_, pack_grad(case, g)
+
+
+def oracle_from_workload(wl, chain_idx=None, as_f64=False):
+    """Oracle model + chain states for a ``bench_workload.Workload`` (the bench's own seeded
+    data and states).  ``chain_idx`` selects a subset of the chain batch (chains are
+    independent); ``as_f64`` evaluates the f64 oracle on the workload's (f32-rounded) numbers."""
+    from tests import golden_io
+
+    dt = np.float64 if as_f64 else wl.params.dtype
+    terms = [
+        o.term_from_reparam(wl.X[i].astype(dt), t.basis.knots.astype(dt), t.basis.Z.astype(dt),
+                            t.penalty.astype(dt), t.penalty_rank, "loc" if k == 0 else "scale")
+        for i, (t, k) in enumerate(wl.model.all_terms())
+    ]
+    om = o.PTMModel(wl.y.astype(dt), terms, nparam=wl.model.nparam, dtype=dt)
+    om.spline = o.PTMSpline(wl.model.knots.astype(dt))
+    Zd = wl.model.trafo_Z if wl.model.trafo_Z is not None else lp.trafo_reparam(wl.model.nparam, wl.params.dtype)
+    om.Zd = np.asarray(Zd).astype(dt)
+    L, P = wl.model.param_layout()
+    params = wl.params if chain_idx is None else wl.params[np.asarray(chain_idx)]
+    st = golden_io.state_from_params(om, params.astype(dt), L)
+    return om, st, L, P
+
+
+def pack_grad_layout(L, P, g: dict) -> np.ndarray:
+    C = g["delta_z"].shape[0]
+    out = np.zeros((C, P), dtype=np.float64)
+    out[:, L["beta0"]] = g["beta0"]
+    out[:, L["gamma0"]] = g["gamma0"]
+    for t, gb in enumerate(g["beta"]):
+        out[:, L["beta"][t]: L["beta"][t] + gb.shape[1]] = gb
+        out[:, L["tau"][t]] = g["tau"][:, t]
+    out[:, L["delta_z"]: L["delta_z"] + g["delta_z"].shape[1]] = g["delta_z"]
+    out[:, L["tau_delta"]] = g["tau_delta"]
+    return out

@@ -73,12 +73,19 @@ def test_intercept_pseudo_gibbs_values():
     case = build_case(n=3000, n_loc=2, n_scale=1, nbases=12, C=5, beta0=0.3, gamma0=-0.2)
     params = torch.from_numpy(case.params).cuda()
     b0, g0 = case.model.compute_intercepts(params)
+    b0s, g0s = case.model.compute_intercepts(params, sequential=True)
     st = case.model.intercept_stats(params).cpu().numpy()
-    assert st.shape == (5, 3) and np.isfinite(st).all()
+    assert st.shape == (5, 5) and np.isfinite(st).all()
     for c in range(5):
         rb, rg = case.omodel.compute_intercepts(case.state, c)
         assert abs(b0[c].item() - rb) < 1e-11 * max(1.0, abs(rb))
         assert abs(g0[c].item() - rg) < 1e-11 * max(1.0, abs(rg))
+        # the sampler's order: LogScaleIntercept sees the UPDATED location intercept
+        # (predictor.py:604-609) -- exact from the same sweep through sum w^2 and sum r w
+        rb, rg = case.omodel.compute_intercepts(case.state, c, sequential=True)
+        assert abs(b0s[c].item() - rb) < 1e-11 * max(1.0, abs(rb))
+        assert abs(g0s[c].item() - rg) < 1e-11 * max(1.0, abs(rg))
+        assert abs(rg - g0[c].item()) > 1e-6  # the two orders really differ on this case
     # the logp output of the same sweep is untouched
     lp_ref, _ = oracle_eval(case)
     assert rel_err(case.model.log_prob(params).cpu().numpy(), lp_ref) < TOL64
@@ -539,8 +546,13 @@ def test_full_size_properties_c3():
 
 def test_full_size_f32_vs_f64():
     """float32 kernel against the float64 kernel on the f32-rounded inputs at n = 1M.
-    logp meets rel 1e-5; the gradient is limited by the f32 rounding of gamma = Z beta
-    (condition ~ n |Z|^2 / |g|), which any f32 evaluation shares: documented bound 1e-4."""
+    logp meets rel 1e-5.  The gradient meets 1e-5 up to the CONDITIONING of the problem at
+    this size, which the test measures instead of assuming: moving the chain state by at most
+    half a float32 ulp changes the float64 gradient by `kappa` (relative, inf-norm per chain;
+    ~1e-5 here: Hessian ~ n |Z|^2 against |g|), so no float32 evaluation -- the reference's
+    included -- can agree with another one more closely than that.  Bound: max(1e-5, 4 kappa).
+    At n <= 1e5 (test_logp_grad_f32, test_c2_full_config_f32, the reference-run fixture) the
+    plain 1e-5 holds."""
     import bench_workload as bw
     import liesel_ptm_b200 as lp_
 
@@ -564,8 +576,14 @@ def test_full_size_f32_vs_f64():
     lp64, g64 = m64.log_prob_and_grad(p32.double())
     e_lp = ((lp32.double() - lp64).abs() / lp64.abs()).max().item()
     e_g = ((g32.double() - g64).abs().amax(dim=1) / g64.abs().amax(dim=1)).max().item()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    half_ulp = (torch.rand(p32.shape, dtype=torch.float64, device="cuda", generator=gen) - 0.5) * 2.0 ** -23
+    _, g64p = m64.log_prob_and_grad(p32.double() * (1.0 + half_ulp))
+    kappa = ((g64p - g64).abs().amax(dim=1) / g64.abs().amax(dim=1)).max().item()
+    print(f"[f32 vs f64, n=1M] logp {e_lp:.2e}  grad {e_g:.2e}  half-ulp conditioning kappa {kappa:.2e}")
     assert e_lp < 1e-5
-    assert e_g < 1e-4
+    assert e_g < max(1e-5, 4.0 * kappa)
 
 
 def test_iwls_transition_matches_oracle_transcription():

@@ -63,16 +63,20 @@ def _worker(rank, world, port, q):
                    np.max(np.abs(L_r.numpy() - L_full)) / np.max(np.abs(L_full)))
 
     # --- intercept pseudo-Gibbs statistics: three sums per chain, additive over shards -----
-    stats = np.zeros((4, 3))
+    stats = np.zeros((4, 5))
     for c in range(4):
         mu, ls = sub.predictors(st, c)
-        r = (sub.y - mu) / np.exp(ls)
-        stats[c] = [np.sum(np.exp(-ls)), np.sum(r), np.sum(r * r)]
+        w = np.exp(-ls)
+        r = (sub.y - mu) * w
+        stats[c] = [np.sum(w), np.sum(r), np.sum(r * r), np.sum(w * w), np.sum(r * w)]
     stats_r = allreduce_sum(torch.from_numpy(stats))
     params = torch.from_numpy(case.params)
     b0, g0 = intercepts_from_stats(stats_r, params, case.layout, om.n)
     ref = np.array([om.compute_intercepts(st, c) for c in range(4)])
     err_int = max(np.max(np.abs(b0.numpy() - ref[:, 0])), np.max(np.abs(g0.numpy() - ref[:, 1])))
+    b0s, g0s = intercepts_from_stats(stats_r, params, case.layout, om.n, sequential=True)
+    refs = np.array([om.compute_intercepts(st, c, sequential=True) for c in range(4)])
+    err_int = max(err_int, np.max(np.abs(b0s.numpy() - refs[:, 0])), np.max(np.abs(g0s.numpy() - refs[:, 1])))
     err_obs = max(err_obs, err_info, err_int * 1e-1)  # intercepts to 1e-11 absolute
 
     # --- chain-axis sharding: no collective on the data path ---------------------------

@@ -141,6 +141,8 @@ def test_oracle_logp_grad_information_match_reference_code():
     for c in range(2):
         b0, g0 = om.compute_intercepts(st, c)
         assert abs(b0 - d["intercepts"][c, 0]) < 1e-14 and abs(g0 - d["intercepts"][c, 1]) < 1e-14
+        b0, g0 = om.compute_intercepts(st, c, sequential=True)
+        assert abs(b0 - d["intercepts"][c, 0]) < 1e-14 and abs(g0 - d["intercepts_seq"][c]) < 1e-14
     _, P0, L0 = om.loc_precision(st, 0)
     _, P1 = om.scale_precision(st, 1)
     assert rel_err(P0, d["precision"][:, 0]) < 1e-14 and rel_err(L0, d["chol"][:, 0]) < 1e-13
@@ -251,6 +253,11 @@ def test_cuda_logp_grad_information_vs_reference_code_f64():
     b0, g0 = model.compute_intercepts(params)
     assert np.max(np.abs(b0.cpu().numpy() - d["intercepts"][:, 0])) < 1e-12
     assert np.max(np.abs(g0.cpu().numpy() - d["intercepts"][:, 1])) < 1e-12
+    # ... and in the sampler's order, LogScaleIntercept fed the full loc predictor with the
+    # updated location intercept (predictor.py:604-609), from the same single sweep
+    b0, g0 = model.compute_intercepts(params, sequential=True)
+    assert np.max(np.abs(b0.cpu().numpy() - d["intercepts"][:, 0])) < 1e-12
+    assert np.max(np.abs(g0.cpu().numpy() - d["intercepts_seq"])) < 1e-12
     # per-observation log-densities through the pointwise sweep
     ll = d["loglik_i"]
     mx = ll.max(axis=0)
@@ -265,14 +272,32 @@ def test_cuda_logp_grad_information_vs_reference_code_f64():
 
 @pytest.mark.gpu
 def test_cuda_logp_grad_vs_reference_code_f32():
-    """float32 problem against the reference code's float64 values: rel 1e-5."""
+    """float32 problem: rel 1e-5 (north star) against float64 values on the SAME inputs, i.e.
+    the f32-rounded numbers the kernel receives.  The float64 side is the oracle, which the CPU
+    part of this file pins bit-for-bit / to 1e-13 on the reference code's fixture; against the
+    fixture's own float64 values (inputs NOT rounded) the gradient differs by up to ~3e-5 --
+    that is the rounding of y, x, knots, Z to float32, not the kernel -- bounded below too."""
     import torch
+
+    from tests.helpers import pack_grad_layout
 
     d = golden_io.load("ref_logp_n257.npz")
     model = _gpu_model(d, dtype=np.float32)
-    params = torch.from_numpy(_pack(model, d, np.float32)).cuda()
+    p32 = _pack(model, d, np.float32)
+    params = torch.from_numpy(p32).cuda()
     logp, grad = model.log_prob_and_grad(params)
     torch.cuda.synchronize()
     cols = _grad_cols(model, d)
+    d32 = {k: (d[k].astype(np.float32).astype(np.float64) if d[k].dtype == np.float64 and d[k].ndim > 0
+               else d[k]) for k in d.files}
+    om = golden_io.oracle_from_fixture(d32)
+    L, P = model.param_layout()
+    st = golden_io.state_from_params(om, p32.astype(np.float64), L)
+    lp_ref, gd = om.logp_and_grad(st)
+    g_ref = pack_grad_layout(L, P, gd)
+    g = grad.cpu().numpy()
+    assert rel_err(logp.cpu().numpy(), lp_ref) < 1e-5
+    for c in range(g.shape[0]):
+        assert rel_err(g[c], g_ref[c]) < 1e-5
     assert rel_err(logp.cpu().numpy(), d["logp"]) < 1e-5
-    assert rel_err(grad.cpu().numpy()[:, cols], d["grad"]) < 1e-4
+    assert rel_err(g[:, cols], d["grad"]) < 1e-4  # unrounded inputs: input-rounding bound
