@@ -203,6 +203,36 @@ int ptm_loc_precision_all_f32(const PtmProblem* prob, const float* params, int64
                               float* precision, float* chol, void* workspace,
                               size_t workspace_bytes, void* stream);
 
+/* Chain-batched OBSERVED information of one coefficient block,
+ *     info[c] = - jacfwd(grad(log_prob))   restricted to the block       (logprob.py:104-113),
+ * with the reference's post-processing and Cholesky factor.  Replaces FlatLogProb.hessian as
+ * CholInfo / PTMCholInfo / PTMCholInfoFixed / ObservedCholInfoOrIdentity
+ * (iwls_proposals.py:168-184, 227-245, 279-298, 333-364), IWLSKernelFixed.init_state
+ * (iwls_fixed.py:118-143) and kernel.IWLSKernel._chol_info (kernel.py:240-258) use it.
+ *   block: smooth-term index t (coefficients beta_t, d = p_t) or PTM_BLOCK_DELTA_Z (the latent
+ *          transformation coefficients, d = nparam - 1)
+ *   mode 0: info as computed;  chol = cholesky(sym(info))
+ *        1: info = make_pd(info)  [symmetrise, raise the spectrum to >= 1e-6]   (PTMCholInfo(Fixed),
+ *           IWLSKernelFixed.init_state);  chol of that
+ *        2: info = make_pd(info + 1e-6 I)                           (CholInfo);  chol of that
+ *        3: info as computed;  chol = cholesky(info + I)            (kernel.IWLSKernel._chol_info)
+ *        4: info + 1e-6 I;  chol of that, the identity when it has NaNs
+ *           (ObservedCholInfoOrIdentity.chol_info_or_identity)
+ * info, chol: [C, d, d] row-major; chol may be NULL.  A failed factorisation gives NaN like
+ * jnp.linalg.cholesky (modes 0-3).  The second-order terms follow jax's semantics for the
+ * reference's custom_jvp (inner grad: the declared rule; outer jacfwd: the rule body
+ * differentiated as ordinary code, i.e. the true slopes of the lerped tables).
+ * On a shard view only mode 0 without chol is allowed (the likelihood part is additive over
+ * shards).  Workspace: ptm_hessian_workspace_bytes(prob, n_chains, block). */
+#define PTM_BLOCK_DELTA_Z (-1)
+size_t ptm_hessian_workspace_bytes(const PtmProblem* prob, int64_t n_chains, int32_t block);
+int ptm_hessian_block_f64(const PtmProblem* prob, int32_t block, int32_t mode, const double* params,
+                          int64_t n_chains, double* info, double* chol, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int ptm_hessian_block_f32(const PtmProblem* prob, int32_t block, int32_t mode, const float* params,
+                          int64_t n_chains, float* info, float* chol, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* quad[c, t] = beta_t' K_t beta_t for every chain and smooth term: the quadratic form of
  * the Gibbs updates of the smoothing variances (gam/kernel.py:29-39, kernel.py:99-111:
  * b + 0.5 * beta' K beta) and of the prior (gam/dist.py:64-70).  quad is [C, T]. */

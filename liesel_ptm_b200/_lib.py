@@ -32,6 +32,7 @@ SYMBOLS = [
     "ptm_xtwx_f64", "ptm_xtwx_f32", "ptm_loc_precision_f64", "ptm_loc_precision_f32",
     "ptm_quadform_f64", "ptm_quadform_f32", "ptm_intercept_stats_f64", "ptm_intercept_stats_f32",
     "ptm_loc_precision_all_f64", "ptm_loc_precision_all_f32",
+    "ptm_hessian_workspace_bytes", "ptm_hessian_block_f64", "ptm_hessian_block_f32",
     "ptm_pointwise_workspace_bytes", "ptm_pointwise_f64", "ptm_pointwise_f32",
     "ptm_problem_shared_designs", "ptm_predict_workspace_bytes", "ptm_predict_f64", "ptm_predict_f32",
     "ptm_predict_quantile_f64", "ptm_predict_quantile_f32", "ptm_inverse_f64", "ptm_inverse_f32",
@@ -127,6 +128,12 @@ def load() -> C.CDLL:
         f.restype = C.c_int
         f = getattr(lib, f"ptm_loc_precision_{sfx}")
         f.argtypes = [vp, i32, vp, i64, vp, vp, vp, sz, vp]
+        f.restype = C.c_int
+    lib.ptm_hessian_workspace_bytes.argtypes = [vp, i64, i32]
+    lib.ptm_hessian_workspace_bytes.restype = sz
+    for sfx in ("f64", "f32"):
+        f = getattr(lib, f"ptm_hessian_block_{sfx}")
+        f.argtypes = [vp, i32, i32, vp, i64, vp, vp, vp, sz, vp]
         f.restype = C.c_int
     lib.ptm_pointwise_workspace_bytes.argtypes = [vp, i64]
     lib.ptm_pointwise_workspace_bytes.restype = sz

@@ -18,6 +18,7 @@
 #include "ptm_xtwx.cuh"
 #include "ptm_xtwx_tc.cuh"
 #include "ptm_predict.cuh"
+#include "ptm_hessian.cuh"
 
 namespace {
 
@@ -768,7 +769,9 @@ int xtwx_terms(const PtmProblem* pr, const int* terms, int nterms, const R* para
   // a shard view holds part of the observations: X'WX is additive over shards, the precision
   // (penalty, 1e-6 mean(diag) ridge) and its Cholesky factor are not -- all-reduce ptm_xtwx and
   // finish on the full sum (parallel.finish_precision) instead of getting shard-local factors
-  if (is_sharded(pr) && (out_p || out_l))
+  bool wants_factor = false;
+  for (int i = 0; i < nterms; ++i) wants_factor |= (out_p && out_p[i]) || (out_l && out_l[i]);
+  if (is_sharded(pr) && wants_factor)
     return fail(PTM_ERR_SHAPE,
                 "precision / Cholesky of an observation-shard view are not additive over shards: "
                 "use ptm_xtwx_* per shard, all-reduce, then add the penalty and factorise");
@@ -892,6 +895,130 @@ int quadform_impl(const PtmProblem* pr, const R* params, long long C, R* quad, v
       params, (int)C, pr->P, pr->T, reinterpret_cast<const R*>(pr->d_Kall),
       reinterpret_cast<const int*>(pr->d_meta), quad);
   PTM_CUDA(cudaGetLastError());
+  return PTM_OK;
+}
+
+// ---- observed information of one coefficient block (ptm_hessian.cuh) -------------------------
+struct HessPlan {
+  int kind, d, NACC, NW, CG, M, n_items, grid;
+  long long chunk_len;
+  size_t smem, off_gamma, off_cc, off_partial, total;
+};
+
+template <typename R>
+int make_hess_plan(const PtmProblem* pr, int block, long long C, HessPlan& hp) {
+  if (block != PTM_BLOCK_DELTA_Z && (block < 0 || block >= pr->T)) return fail(PTM_ERR_SHAPE, "block: term index or PTM_BLOCK_DELTA_Z");
+  const bool dz = block == PTM_BLOCK_DELTA_Z;
+  hp.kind = dz ? ptm::kHessDeltaZ : ptm::kHessBeta;
+  hp.d = dz ? pr->nparam - 1 : pr->p[block];
+  hp.NACC = ptm::hess_nacc(hp.kind, dz ? 0 : pr->nb[block], pr->KK);
+  const int NCC = pr->KK * 5 + 6, T = pr->T;
+  auto smem_for = [&](int NW) {
+    size_t b = (size_t)NW * hp.NACC * 32 * sizeof(double);
+    b += (size_t)pr->sum_nb * 32 * sizeof(R) + (size_t)(NCC + 4) * 32 * sizeof(R);
+    b += (size_t)T * 4 * ptm::kKnotStride * sizeof(R);
+    b += (size_t)NW * T * 32 * 4 * sizeof(R) + (size_t)NW * 32 * sizeof(R) + 64;
+    return b;
+  };
+  hp.NW = 8;
+  while (hp.NW > 1 && smem_for(hp.NW) > 227 * 1024) --hp.NW;
+  hp.smem = smem_for(hp.NW);
+  if (hp.smem > 227 * 1024) return fail(PTM_ERR_SHAPE, "observed-information sweep does not fit in shared memory");
+  hp.CG = (int)((C + 31) / 32);
+  const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
+  long long M = std::max<long long>(1, (4LL * pr->num_sms + hp.CG - 1) / hp.CG);
+  M = std::min(M, std::max<long long>(1, len / (32LL * hp.NW * 4)));
+  long long chunk = std::max<long long>(32, (len + M - 1) / M);
+  chunk = (chunk + 31) / 32 * 32;
+  M = std::max<long long>(1, (len + chunk - 1) / chunk);
+  hp.M = (int)M; hp.chunk_len = chunk; hp.n_items = hp.CG * hp.M;
+  hp.grid = std::min(hp.n_items, pr->num_sms);
+  size_t off = 0;
+  hp.off_gamma = off; off = align_up(off + (size_t)std::max(T, 1) * ptm::kMaxNbases * C * sizeof(R), 256);
+  hp.off_cc = off;    off = align_up(off + (size_t)NCC * C * sizeof(R), 256);
+  hp.off_partial = off; off = align_up(off + (size_t)hp.n_items * hp.NACC * 32 * sizeof(double), 256);
+  hp.total = off;
+  return PTM_OK;
+}
+
+template <typename R>
+int hessian_impl(const PtmProblem* pr, int block, int mode, const R* params, long long C, R* info, R* chol,
+                 void* ws, size_t ws_bytes, void* stream) {
+  if (!pr || !params || !info || !ws) return fail(PTM_ERR_NULL, "null argument");
+  if (pr->dtype != (sizeof(R) == 8 ? PTM_F64 : PTM_F32)) return fail(PTM_ERR_DTYPE, "dtype mismatch");
+  PTM_CHECK_DEVICE(pr);
+  if (C < 1) return fail(PTM_ERR_SHAPE, "n_chains must be >= 1");
+  if (mode < 0 || mode > 4) return fail(PTM_ERR_SHAPE, "mode must be 0 .. 4");
+  // like the precision: the eigen-shift and the factor are not additive over observation shards
+  if (is_sharded(pr) && (mode != 0 || chol))
+    return fail(PTM_ERR_SHAPE, "observed information of a shard view: mode 0 without Cholesky only (additive), finish on the sum");
+  HessPlan hp;
+  int rc = make_hess_plan<R>(pr, block, C, hp);
+  if (rc != PTM_OK) return rc;
+  if (ws_bytes < hp.total) return fail(PTM_ERR_WORKSPACE, "workspace too small (see ptm_hessian_workspace_bytes)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* wsb = reinterpret_cast<char*>(ws);
+  R* Gamma = reinterpret_cast<R*>(wsb + hp.off_gamma);
+  R* cc = reinterpret_cast<R*>(wsb + hp.off_cc);
+  double* partial = reinterpret_cast<double*>(wsb + hp.off_partial);
+  g_launches = 0;
+  ptm::PreArgs<R> pa;
+  fill_pre_args<R>(pr, params, C, Gamma, cc, pa);
+  ptm::k_pre<R><<<(unsigned)C, 128, pr->P * sizeof(R), st>>>(pa);
+  PTM_CUDA(cudaGetLastError());
+  ++g_launches;
+  ptm::HessArgs<R> ha;
+  memset(&ha, 0, sizeof ha);
+  ha.y = reinterpret_cast<const R*>(pr->d_y);
+  ha.X = reinterpret_cast<const R*>(pr->d_X);
+  ha.knots = reinterpret_cast<const R*>(pr->d_knots);
+  ha.grid = reinterpret_cast<const R*>(pr->d_grid);
+  ha.Gamma = Gamma; ha.cc = cc; ha.partial = partial;
+  ha.n = pr->n; ha.obs_begin = pr->obs_begin; ha.obs_end = pr->obs_end; ha.chunk_len = hp.chunk_len;
+  ha.C = (int)C; ha.CG = hp.CG; ha.M = hp.M; ha.n_items = hp.n_items; ha.KK = pr->KK; ha.T = pr->T;
+  ha.sum_nb = pr->sum_nb; ha.NW = hp.NW; ha.NACC = hp.NACC; ha.kind = hp.kind;
+  ha.bterm = hp.kind == ptm::kHessBeta ? block : 0;
+  for (int t = 0; t < pr->T; ++t) {
+    ha.nb[t] = pr->nb[t]; ha.pred[t] = pr->pred[t] == PTM_LOC ? 0 : 1;
+    ha.goff[t] = pr->goff[t]; ha.inv_dk[t] = (R)pr->inv_dk[t];
+  }
+  ptm::TrafoConst<R> tcr;
+  fill_tc<R>(pr->tc64, tcr);
+  ha.ts = tcr;
+  {
+    auto kern = ptm::k_hess<R>;
+    PTM_CUDA(ptm::ensure_smem(kern, hp.smem));
+    kern<<<hp.grid, 32 * hp.NW, hp.smem, st>>>(ha);
+    PTM_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  ptm::HessPostArgs<R> po;
+  memset(&po, 0, sizeof po);
+  po.params = params; po.partial = partial;
+  po.Zall = reinterpret_cast<const R*>(pr->d_Zall);
+  po.Kall = reinterpret_cast<const R*>(pr->d_Kall);
+  po.Zd = reinterpret_cast<const R*>(pr->d_Zd);
+  po.tc = reinterpret_cast<const ptm::TrafoConst<double>*>(pr->d_tc64);
+  po.hess = info; po.chol = chol;
+  po.C = (int)C; po.P = pr->P; po.M = hp.M; po.NACC = hp.NACC; po.KK = pr->KK; po.mode = mode;
+  po.add_priors = pr->add_priors;
+  po.tau_off = pr->tau_off; po.taud_off = pr->taud_off; po.dz_off = pr->dz_off;
+  if (hp.kind == ptm::kHessBeta) {
+    po.term = block; po.nbt = pr->nb[block]; po.p = pr->p[block]; po.zoff = pr->zoff[block]; po.koff = pr->koff[block];
+    const size_t sm = ((size_t)po.nbt * 4 + (size_t)po.nbt * po.p + 2 * (size_t)po.p * po.p) * sizeof(double);
+    auto kp = ptm::k_hess_post_beta<R>;
+    PTM_CUDA(ptm::ensure_smem(kp, sm));
+    kp<<<(unsigned)C, 128, sm, st>>>(po);
+  } else {
+    const int J = pr->J, np_ = pr->nparam;
+    const size_t sm = ((size_t)hp.NACC + (size_t)J * J + 2 * (size_t)np_ * np_ + (size_t)(J + 1) + J + 3 * (size_t)np_ +
+                       4 * (size_t)(J + 1) + 8) * sizeof(double);
+    auto kp = ptm::k_hess_post_dz<R>;
+    PTM_CUDA(ptm::ensure_smem(kp, sm));
+    kp<<<(unsigned)C, 64, sm, st>>>(po);
+  }
+  PTM_CUDA(cudaGetLastError());
+  ++g_launches;
   return PTM_OK;
 }
 
@@ -1124,6 +1251,21 @@ int ptm_pointwise_f64(const PtmProblem* p, const double* params, int64_t S, doub
 int ptm_pointwise_f32(const PtmProblem* p, const float* params, int64_t S, float* lppd, float* pwaic, void* ws,
                       size_t wsb, void* st) {
   return pointwise_impl<float>(p, params, S, lppd, pwaic, ws, wsb, st);
+}
+
+size_t ptm_hessian_workspace_bytes(const PtmProblem* p, int64_t C, int32_t block) {
+  if (!p || C < 1) return 0;
+  HessPlan hp;
+  const int rc = p->dtype == PTM_F64 ? make_hess_plan<double>(p, block, C, hp) : make_hess_plan<float>(p, block, C, hp);
+  return rc == PTM_OK ? hp.total : 0;
+}
+int ptm_hessian_block_f64(const PtmProblem* p, int32_t block, int32_t mode, const double* params, int64_t C,
+                          double* info, double* chol, void* ws, size_t wsb, void* st) {
+  return hessian_impl<double>(p, block, mode, params, C, info, chol, ws, wsb, st);
+}
+int ptm_hessian_block_f32(const PtmProblem* p, int32_t block, int32_t mode, const float* params, int64_t C,
+                          float* info, float* chol, void* ws, size_t wsb, void* st) {
+  return hessian_impl<float>(p, block, mode, params, C, info, chol, ws, wsb, st);
 }
 
 int ptm_last_launch_count(void) { return g_launches; }

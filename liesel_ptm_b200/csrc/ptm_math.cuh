@@ -461,6 +461,33 @@ PTM_HD void core_eval(const TrafoScal<R>& tc, R c0, R c1, R c2, R c3, R jmp,
   ev.d2 = fma(kap, dD2, R(2) * e1) * (tc.inv_dk * tc.inv_dk);
 }
 
+// core_eval plus the TRUE slopes in r of the three lerps (what an ordinary derivative of the
+// lerp sees: (T[m+1] - T[m]) / step with step = (b-a)/ngrid, i.e. d kappa / d r = inv_h *
+// kap_scale) -- the second-order terms of jacfwd(grad(logp)), see ptm_hessian.cuh.
+template <typename R>
+PTM_HD void core_eval_slopes(const TrafoScal<R>& tc, R c0, R c1, R c2, R c3, R jmp, CoreEval<R>& ev,
+                             R& sH, R& sD, R& sD2) {
+  const R u = ev.u, s = tc.ratio, kap = ev.kappa, mm = ev.mm;
+  const R b2 = fma(u, c3, c2);
+  const R b1 = fma(u, b2, c1);
+  const R P = fma(u, b1, c0);
+  const R d1 = fma(u, c3, b2);
+  const R Pp = fma(u, d1, b1);
+  const R e1 = fma(u, c3, d1);
+  const R mm2 = mm * mm;
+  const R j3 = R(3) * jmp;
+  const R dH = fma(jmp, mm2 * mm, s * fma(s, fma(s, c3, e1), Pp));
+  ev.z = fma(kap, dH, P);
+  const R dD = fma(j3, mm2, s * fma(R(3) * s, c3, R(2) * e1));
+  ev.d = fma(kap, dD, Pp) * tc.inv_dk;
+  const R dD2 = fma(R(2) * j3, mm, R(6) * s * c3);
+  ev.d2 = fma(kap, dD2, R(2) * e1) * (tc.inv_dk * tc.inv_dk);
+  const R dk_dr = tc.inv_h * tc.kap_scale;
+  sH = dH * dk_dr;
+  sD = dD * tc.inv_dk * dk_dr;
+  sD2 = dD2 * (tc.inv_dk * tc.inv_dk) * dk_dr;
+}
+
 // Weights of dl/dz = lz and dl/dd = ld on the five coefficients of the piece.
 template <typename R>
 PTM_HD void core_backward(const TrafoScal<R>& tc, const CoreEval<R>& ev, R lz, R ld,

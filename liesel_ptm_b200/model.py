@@ -624,6 +624,39 @@ class LocScalePTM:
         return P, L
 
 
+HESS_RAW, HESS_MAKE_PD, HESS_JITTER_MAKE_PD, HESS_PLUS_IDENTITY, HESS_OR_IDENTITY = range(5)
+
+
+@_on_device
+def _hessian_block(self, block, params: torch.Tensor, mode: int = HESS_RAW, with_chol: bool = True):
+    """Observed information ``-jacfwd(grad(log_prob))`` of one coefficient block for every
+    chain (``FlatLogProb.hessian``, logprob.py:104-113) with the reference's post-processing
+    ``mode`` (include/ptm_b200.h) and its lower Cholesky factor.  ``block`` = term index or
+    ``"delta_z"``.  Returns (info [C, d, d], chol [C, d, d] | None)."""
+    params = self._check_params(params)
+    Cn = params.shape[0]
+    if block == "delta_z":
+        blk, d = -1, self.nparam - 1
+    else:
+        blk = int(block)
+        if not 0 <= blk < len(self.terms):
+            raise IndexError("block: term index or 'delta_z'")
+        d = self.terms[blk][0].basis.ncoef
+    nbytes = self._lib.ptm_hessian_workspace_bytes(self._h, Cn, blk)
+    if nbytes == 0:
+        raise _lib.PtmError(_lib.PTM_ERR_SHAPE, self._lib.ptm_last_error().decode())
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+    info = torch.empty((Cn, d, d), dtype=self.dtype, device=self.device)
+    chol = torch.empty_like(info) if with_chol else None
+    f = getattr(self._lib, f"ptm_hessian_block_{self._sfx}")
+    _lib.check(f(self._h, blk, int(mode), params.data_ptr(), Cn, info.data_ptr(),
+                 chol.data_ptr() if with_chol else None, ws.data_ptr(), ws.numel(), self._stream()))
+    return info, chol
+
+
+LocScalePTM.hessian_block = _hessian_block
+
+
 @_on_device
 def _precision_all(self, params: torch.Tensor, with_chol: bool = True):
     """Precision (and Cholesky factor) of every LOCATION term from one sweep: lists of
@@ -692,3 +725,78 @@ class GaussianLocCholInfo:
 
 
 GaussianScaleCholInfo = GaussianLocCholInfo  # W == 2 is selected by the term's predictor
+
+
+class _ObservedCholInfo:
+    """Shared body of the reference's observed-information providers: the information of one
+    block is evaluated ONCE at the state given at construction (``__post_init__`` ->
+    ``current_fisher_info``) and ``chol_info(state)`` returns the stored factor."""
+
+    mode = HESS_MAKE_PD
+
+    def __init__(self, model: LocScalePTM, block, params: torch.Tensor) -> None:
+        self.model, self.block = model, block
+        self._fisher_info_unprocessed = model.hessian_block(block, params, HESS_RAW, with_chol=False)[0]
+        self.fisher_info, self.chol_fisher_info = model.hessian_block(block, params, self.mode)
+
+    @classmethod
+    def from_smooth(cls, smooth: term, model: LocScalePTM, params: torch.Tensor):
+        for i, (t, _) in enumerate(model.terms):
+            if t is smooth:
+                return cls(model, i, params)
+        raise ValueError(f"{smooth.name} is not a term of the model")
+
+    @classmethod
+    def from_coef(cls, model: LocScalePTM, params: torch.Tensor):
+        return cls(model, "delta_z", params)
+
+    def current_fisher_info(self, params: torch.Tensor):
+        return (self.model.hessian_block(self.block, params, HESS_RAW, with_chol=False)[0],
+                self.model.hessian_block(self.block, params, self.mode, with_chol=False)[0])
+
+    def chol_info(self, params: torch.Tensor | None = None) -> torch.Tensor:
+        return self.chol_fisher_info
+
+    @property
+    def nan_in_cholesky_of_unprocessed_finfo(self) -> bool:
+        return bool(torch.isnan(torch.linalg.cholesky_ex(self._fisher_info_unprocessed)[0]).any())
+
+
+class PTMCholInfoFixed(_ObservedCholInfo):
+    """iwls_proposals.py:202-256 (make_pd of the observed information of delta_z)."""
+
+
+class CholInfo(_ObservedCholInfo):
+    """iwls_proposals.py:259-312 (``+ 1e-6 I`` then make_pd, smooth-term coefficients)."""
+
+    mode = HESS_JITTER_MAKE_PD
+
+
+class PTMCholInfo(_ObservedCholInfo):
+    """iwls_proposals.py:145-199: fixed make_pd information, rescaled by the CURRENT
+    ``1 / clip(tau_delta, sqrt(eps))^2`` at every call."""
+
+    def precision(self, params: torch.Tensor) -> torch.Tensor:
+        lay, _ = self.model.param_layout()
+        scale = params[:, lay["tau_delta"]]
+        eps = float(np.sqrt(np.finfo(self.model.np_dtype).eps))
+        return self.fisher_info * (1.0 / scale.clamp_min(eps) ** 2)[:, None, None]
+
+    def chol_info(self, params: torch.Tensor) -> torch.Tensor:
+        return torch.linalg.cholesky_ex(self.precision(params))[0]
+
+
+class ObservedCholInfoOrIdentity(_ObservedCholInfo):
+    """iwls_proposals.py:315-372: the factor of ``info + 1e-6 I`` at the CURRENT state, the
+    identity when it has NaNs."""
+
+    mode = HESS_JITTER_MAKE_PD
+
+    def chol_info(self, params: torch.Tensor) -> torch.Tensor:
+        return self.model.hessian_block(self.block, params, HESS_OR_IDENTITY)[1]
+
+
+def iwls_kernel_chol_info(model: LocScalePTM, block, params: torch.Tensor) -> torch.Tensor:
+    """``kernel.IWLSKernel._chol_info`` without a ``chol_info_fn`` (kernel.py:240-258):
+    ``cholesky(-hessian + I)`` at the current state, every transition."""
+    return model.hessian_block(block, params, HESS_PLUS_IDENTITY)[1]

@@ -836,6 +836,143 @@ class PTMModel:
         out += (np.sum(st.delta_z[c] ** 2) / td**3 - (self.nparam - 1) / td) * dst.tau_delta[c]
         return out
 
+    # --- observed information: jacfwd(grad(logp)) of one coefficient block -----------------
+    def hessian_block(self, st: ChainState, c: int, block, rows=None, add_priors: bool = True):
+        """``FlatLogProb.hessian`` (logprob.py:104-113, ``jax.jacfwd(jax.grad(log_prob))``) for
+        chain c and ONE coefficient block, as CholInfo / PTMCholInfo(Fixed) /
+        IWLSKernelFixed.init_state / kernel.IWLSKernel._chol_info use it
+        (iwls_proposals.py:168-184, 227-245, 279-298, 333-364; iwls_fixed.py:118-143;
+        kernel.py:240-258).  ``block`` = term index t (the coefficients beta_t) or "delta_z".
+
+        Derivative semantics of the composition, restated (jax: the inner ``grad`` applies the
+        DECLARED custom_jvp rule approx.py:498-520; the outer ``jacfwd`` differentiates the rule
+        BODY as ordinary code -- including the primal outputs it recomputes -- so second-order
+        terms see the true slopes of the lerped tables): with sH, sD, sD2 the slopes of the
+        lerps of G theta, G' theta, G'' theta in r and d, d2 the lerped G' theta, G'' theta,
+
+            d/dr [dl/dr] = -(sH d + z sD) + [d > tiny] (sD2 / d - sD d2 / d^2)      (core)
+
+        and the ordinary second derivative of the closed forms in the transitions / tails."""
+        dt = self.dtype.type
+        rows = slice(None) if rows is None else rows
+        mu, ls = self.predictors(st, c)
+        mu, ls, y = mu[rows], ls[rows], self.y[rows]
+        s = np.exp(-ls)
+        r = (y - mu) * s
+        sp, ap = self.spline, self.spline.bspline
+        theta = sp.compute_coef(st.delta_z[c] @ self.Zd.T)
+        tiny = np.finfo(self.dtype).tiny
+        tH, tD, tD2 = ap.basis_grid @ theta, ap.basis_deriv_grid @ theta, ap.basis_deriv2_grid @ theta
+        a, b, w = sp.min_knot, sp.max_knot, sp.transition_width
+        code = sp.region_code(r)
+        rc = np.clip(np.where(np.isnan(r), a, r), a, b)
+        _, i0, i1, k = ap.cell(rc)
+        lerp = lambda tab: (dt(1) - k) * tab[i0] + k * tab[i1]  # noqa: E731
+        slope = lambda tab: (tab[i1] - tab[i0]) / ap.step  # noqa: E731
+        z, d = sp.dot_and_deriv_coef(r, theta)
+        d2c = lerp(tD2)
+        (_, ia0, _, _), (_, ib0, _, _) = ap.cell(np.atleast_1d(a)), ap.cell(np.atleast_1d(b))
+        ia, ib = int(ia0[0]), int(ib0[0])
+        vL, dL, vR, dR = tH[ia], tD[ia], tH[ib], tD[ib]
+        above = d > tiny
+        dsafe = np.where(above, d, dt(1))
+        core, lt, rt = code == 2, code == 1, code == 3
+        # first derivative of the log-likelihood in r (declared) and minus its second derivative
+        s1 = np.where(lt, (dL - 1) / w, np.where(rt, (1 - dR) / w, dt(0)))  # dd/dr off the core
+        dzdr = np.where(core, d, np.where(lt | rt, d, dt(1)))
+        dddr = np.where(core, d2c, s1)
+        g_r = -z * dzdr + np.where(above, dddr / dsafe, dt(0))
+        A_core = slope(tH) * d + z * slope(tD) + np.where(
+            above, slope(tD) * d2c / dsafe**2 - slope(tD2) / dsafe, dt(0))
+        A_tr = d * d + z * s1 + np.where(above, (s1 / dsafe) ** 2, dt(0))
+        A = np.where(core, A_core, np.where(lt | rt, A_tr, dt(1)))
+        A = np.where(np.isnan(r), np.nan, A)
+        if block != "delta_z":
+            t = int(block)
+            term = self.terms[t]
+            X = term.design[rows]
+            W = s * s * A if term.predictor == "loc" else r * r * A - r * g_r
+            H = -(X.T @ (X * W[:, None]))
+            if add_priors:
+                H = H - term.K / st.tau[c, t] ** 2
+            return H
+        # delta_z block: rows dz/dtheta, dd/dtheta (core: lerped G, G' rows; off the core through
+        # the boundary values v_L, d_L / v_R, d_R = rows of G, G' at a and b)
+        G, Gd = ap.basis_grid, ap.basis_deriv_grid
+        kk = k[:, None]
+        bz = (dt(1) - kk) * G[i0] + kk * G[i1]
+        bd = (dt(1) - kk) * Gd[i0] + kk * Gd[i1]
+        poly0L, poly0R = a * a - 0.5 * a * a, 0.5 * b * b - b * b
+
+        def cL(x):
+            poly = x * a - 0.5 * x * x
+            return (x - poly / w) - (a - poly0L / w)
+
+        def cR(x):
+            poly = 0.5 * x * x - x * b
+            return (x - poly / w) - (b - poly0R / w)
+
+        left, right = code <= 1, code >= 3
+        rl = np.where(code == 0, sp.min_eps, r)
+        rr = np.where(code == 4, sp.max_eps, r)
+        bz = np.where(left[:, None], G[ia][None, :] + cL(rl)[:, None] * Gd[ia][None, :], bz)
+        bz = np.where(right[:, None], G[ib][None, :] + cR(rr)[:, None] * Gd[ib][None, :], bz)
+        qL = np.where(lt, 1 - (a - r) / w, dt(0))
+        qR = np.where(rt, 1 - (r - b) / w, dt(0))
+        bd = np.where(left[:, None], qL[:, None] * Gd[ia][None, :], bd)
+        bd = np.where(right[:, None], qR[:, None] * Gd[ib][None, :], bd)
+        inv_d = np.where(above, 1 / dsafe, dt(0))
+        bdw = bd * inv_d[:, None]
+        H_theta = -(bz.T @ bz) - bdw.T @ bdw
+        g_theta = (-z) @ bz + inv_d @ bd
+        # coefficient map delta -> theta (ptm.py:155-172, 210-230): first and second derivatives
+        delta = st.delta_z[c] @ self.Zd.T
+        npar = delta.shape[0]
+        wts = log_sfn_weights(npar, self.dtype)
+        sm = wts * np.exp(delta - np.max(delta))
+        sm = sm / sm.sum()
+        e = theta[1:]
+        Bk = sp.coef_map.B[0]
+        J1e = e[:, None] * (np.eye(npar) - sm[None, :])  # de_j / ddelta_l
+        J1 = np.vstack([-(Bk[1:] @ J1e)[None, :], J1e])  # dtheta / ddelta  (J x npar)
+        dsm = sm[:, None] * (np.eye(npar) - sm[None, :])  # dsm_l / ddelta_m
+        g_e = g_theta[1:] - Bk[1:] * g_theta[0]
+        T2 = np.einsum("j,jl,jm->lm", g_e * e, np.eye(npar) - sm[None, :], np.eye(npar) - sm[None, :])
+        T2 = T2 - (g_e @ e) * dsm
+        H_delta = J1.T @ H_theta @ J1 + T2
+        H = self.Zd.T @ H_delta @ self.Zd
+        if add_priors:
+            H = H - np.eye(npar - 1) / st.tau_delta[c] ** 2
+        return H
+
+    @staticmethod
+    def observed_info_chol(H, mode: int):
+        """Post-processing of info = -H as the reference applies it before factorising:
+        mode 0 raw; 1 make_pd (symmetrise, raise the spectrum to >= 1e-6: iwls_proposals.py:
+        175-181, 236-242, iwls_fixed.py:129-136); 2 ``+ 1e-6 I`` then make_pd (CholInfo 291-301,
+        ObservedCholInfoOrIdentity 345-355); 3 ``cholesky(-H + I)`` (kernel.py:255-257).
+        Returns (info_processed, lower Cholesky factor)."""
+        info = -np.asarray(H, dtype=np.float64)
+        eye = np.eye(info.shape[0])
+
+        def make_pd(Am, jitter=1e-6):
+            Am = 0.5 * (Am + Am.T)
+            w_min = np.linalg.eigvalsh(Am).min()
+            return Am + max(0.0, jitter - w_min) * eye
+
+        if mode == 1:
+            info = make_pd(info)
+        elif mode == 2:
+            info = make_pd(info + 1e-6 * eye)
+        elif mode == 3:
+            info = info + eye
+        sym = 0.5 * (info + info.T)  # jnp.linalg.cholesky symmetrises its input
+        try:
+            L = np.linalg.cholesky(sym)
+        except np.linalg.LinAlgError:
+            L = np.full_like(sym, np.nan)
+        return info, L
+
     # --- intercept pseudo-Gibbs values (predictor.py:80-100, 126-130) ------
     def compute_intercepts(self, st: ChainState, c: int, sequential: bool = False):
         """LocationIntercept.compute_intercept and LogScaleIntercept.compute_intercept for

@@ -201,8 +201,9 @@ def _tree_stack(items):
     if first is None:
         return None
     if any(_isdual(v) for v in items):
-        from ._dual import Dual, P, T
-        return Dual(_np.stack([_np.asarray(P(v)) for v in items]), _np.stack([_np.asarray(T(v)) for v in items]))
+        from ._dual import Dual, P, T, lvl
+        L = max(lvl(v) for v in items)
+        return Dual(_tree_stack([P(v, L) for v in items]), _tree_stack([T(v, L) for v in items]), L)
     return _np.stack([_np.asarray(v) for v in items]).view(Array)
 
 
@@ -244,13 +245,17 @@ class custom_jvp:
 
     def __call__(self, *a, **k):
         if any(_isdual(v) for v in a):
-            from ._dual import Dual, P, T
-            prim = tuple(_wrap(_np.asarray(P(v))) for v in a)
-            tang = tuple(_wrap(_np.asarray(T(v))) for v in a)
+            # the rule runs on the primals / tangents of the HIGHEST level present; they may
+            # carry lower-level tangents, which then see the rule body as ordinary code
+            from ._dual import Dual, P, T, lvl
+            L = max(lvl(v) for v in a)
+            as_arr = lambda x: x if _isdual(x) else _wrap(_np.asarray(x))  # noqa: E731
+            prim = tuple(as_arr(P(v, L)) for v in a)
+            tang = tuple(as_arr(T(v, L)) for v in a)
             out_p, out_t = self.jvp(prim, tang)
             if isinstance(out_p, (tuple, list)):
-                return type(out_p)(Dual(p_, t_) for p_, t_ in zip(out_p, out_t))
-            return Dual(out_p, out_t)
+                return type(out_p)(Dual(p_, t_, L) for p_, t_ in zip(out_p, out_t))
+            return Dual(out_p, out_t, L)
         return self.fn(*a, **k)
 
 

@@ -1,21 +1,41 @@
-"""Single-direction forward-mode values for the NumPy stand-in (test infrastructure).
+"""Forward-mode values for the NumPy stand-in (test infrastructure), nestable.
 
-`Dual(p, t)` carries a primal array and one tangent of the same shape through the
+`Dual(p, t, level)` carries a primal array and one tangent of the same shape through the
 reference's code; NumPy ufuncs / functions are intercepted with `__array_ufunc__` /
 `__array_function__`.  `custom_jvp` functions apply their DECLARED rule (that is the point:
 the reference's gradient is defined by approx.py:498-520, not by the derivative of its
 lerp).  Tangent conventions follow jax: comparisons and `searchsorted` see the primal,
 `where` selects tangents, `maximum(x, c)` passes the tangent where x > c (half at ties).
+
+Nesting (second derivatives, `jacfwd(grad(f))` of logprob.py:104-113): every Dual has a
+`level`; the components of a level-L Dual may themselves be Duals of a LOWER level, and a
+value of a lower level is a constant for level L (no perturbation confusion).  The innermost
+derivative (jax's `grad`, whose JVP trace is created last) gets the HIGHEST level.  When a
+`custom_jvp` function meets level-L arguments its rule runs on the level-L primals and
+tangents -- which may carry lower-level tangents -- so the rule body, INCLUDING the primal
+outputs it recomputes, is differentiated by the outer levels as ordinary code.  That is what
+jax does (`JVPTrace.process_custom_jvp_call` uses the rule's own primal outputs).
 """
 import numpy as np
 
 
-def P(x):
-    return x.p if isinstance(x, Dual) else x
+def lvl(x):
+    return x.level if isinstance(x, Dual) else 0
 
 
-def T(x):
-    if isinstance(x, Dual):
+def _top(*xs):
+    return max(lvl(x) for x in xs)
+
+
+def P(x, level=None):
+    """Primal of x at `level` (default: x's own level); lower-level values are constants."""
+    L = lvl(x) if level is None else level
+    return x.p if (L > 0 and lvl(x) == L) else x
+
+
+def T(x, level=None):
+    L = lvl(x) if level is None else level
+    if L > 0 and lvl(x) == L:
         return x.t
     return np.zeros(np.shape(x), dtype=np.float64)
 
@@ -25,102 +45,134 @@ def clamp(idx, shape):
     return _clamp_index(idx, shape)
 
 
+def _arr(x):
+    return x if isinstance(x, Dual) else np.asarray(x, dtype=np.float64)
+
+
 class Dual:
     __array_priority__ = 1000.0
     _is_dual = True
 
-    def __init__(self, p, t):
-        self.p = np.asarray(p, dtype=np.float64)
-        self.t = np.broadcast_to(np.asarray(t, dtype=np.float64), self.p.shape).copy()
+    def __init__(self, p, t, level=1):
+        self.level = level
+        self.p = _arr(p)
+        assert lvl(self.p) < level and lvl(t) < level, "components must be of a lower level"
+        t = _arr(t)
+        if np.shape(t) != np.shape(self.p):
+            if isinstance(t, Dual) or isinstance(self.p, Dual):
+                t = t + 0.0 * self.p  # broadcast through the (lower-level) arithmetic
+            else:
+                t = np.broadcast_to(t, self.p.shape)
+        self.t = t if isinstance(t, Dual) else np.array(t, dtype=np.float64, copy=True)
 
     # ---- array-ish surface
-    shape = property(lambda s: s.p.shape)
-    ndim = property(lambda s: s.p.ndim)
-    dtype = property(lambda s: s.p.dtype)
-    size = property(lambda s: s.p.size)
-    T = property(lambda s: Dual(s.p.T, s.t.T))
+    shape = property(lambda s: np.shape(s.p))
+    ndim = property(lambda s: np.ndim(s.p))
+    dtype = property(lambda s: np.dtype(np.float64))
+    size = property(lambda s: np.size(s.p))
+    T = property(lambda s: Dual(s.p.T, s.t.T, s.level))
 
     def __len__(self):
         return len(self.p)
 
     def __repr__(self):
-        return f"Dual({self.p!r}, {self.t!r})"
+        return f"Dual[{self.level}]({self.p!r}, {self.t!r})"
+
+    def __float__(self):
+        return float(self.p)
 
     def __getitem__(self, idx):
-        idx = clamp(idx, self.p.shape)
-        return Dual(self.p[idx], self.t[idx])
+        idx = clamp(idx, np.shape(self.p))
+        return Dual(self.p[idx], self.t[idx], self.level)
 
     @property
     def at(self):
         return _At(self)
 
     def squeeze(self, axis=None):
-        return Dual(self.p.squeeze(axis), self.t.squeeze(axis))
+        return Dual(self.p.squeeze(axis), self.t.squeeze(axis), self.level)
 
     def sum(self, axis=None, keepdims=False):
-        return Dual(self.p.sum(axis=axis, keepdims=keepdims), self.t.sum(axis=axis, keepdims=keepdims))
+        return Dual(self.p.sum(axis=axis, keepdims=keepdims), self.t.sum(axis=axis, keepdims=keepdims),
+                    self.level)
 
     def reshape(self, *s):
-        return Dual(self.p.reshape(*s), self.t.reshape(*s))
+        return Dual(self.p.reshape(*s), self.t.reshape(*s), self.level)
 
     def astype(self, _dt):
         return self
 
-    # ---- arithmetic
+    def copy(self):
+        return Dual(self.p.copy(), self.t.copy(), self.level)
+
+    # ---- arithmetic (at the higher of the two levels; the other operand is a constant there)
     def __neg__(self):
-        return Dual(-self.p, -self.t)
+        return Dual(-self.p, -self.t, self.level)
 
     def __pos__(self):
         return self
 
     def __add__(self, o):
-        return Dual(self.p + P(o), self.t + T(o))
+        L = _top(self, o)
+        return Dual(P(self, L) + P(o, L), T(self, L) + T(o, L), L)
 
     __radd__ = __add__
 
     def __sub__(self, o):
-        return Dual(self.p - P(o), self.t - T(o))
+        L = _top(self, o)
+        return Dual(P(self, L) - P(o, L), T(self, L) - T(o, L), L)
 
     def __rsub__(self, o):
-        return Dual(P(o) - self.p, T(o) - self.t)
+        L = _top(self, o)
+        return Dual(P(o, L) - P(self, L), T(o, L) - T(self, L), L)
 
     def __mul__(self, o):
-        return Dual(self.p * P(o), self.t * P(o) + self.p * T(o))
+        L = _top(self, o)
+        a, b = P(self, L), P(o, L)
+        return Dual(a * b, T(self, L) * b + a * T(o, L), L)
 
     __rmul__ = __mul__
 
     def __truediv__(self, o):
-        q = self.p / P(o)
-        return Dual(q, (self.t - q * T(o)) / P(o))
+        L = _top(self, o)
+        a, b = P(self, L), P(o, L)
+        q = a / b
+        return Dual(q, (T(self, L) - q * T(o, L)) / b, L)
 
     def __rtruediv__(self, o):
-        q = P(o) / self.p
-        return Dual(q, (T(o) - q * self.t) / self.p)
+        L = _top(self, o)
+        a, b = P(o, L), P(self, L)
+        q = a / b
+        return Dual(q, (T(o, L) - q * T(self, L)) / b, L)
 
     def __pow__(self, e):
         assert not isinstance(e, Dual)
-        return Dual(self.p ** e, e * self.p ** (e - 1) * self.t)
+        return Dual(self.p ** e, e * self.p ** (e - 1) * self.t, self.level)
 
     def __matmul__(self, o):
-        return Dual(self.p @ P(o), self.t @ P(o) + self.p @ T(o))
+        L = _top(self, o)
+        a, b = P(self, L), P(o, L)
+        return Dual(a @ b, T(self, L) @ b + a @ T(o, L), L)
 
     def __rmatmul__(self, o):
-        return Dual(P(o) @ self.p, T(o) @ self.p + P(o) @ self.t)
+        L = _top(self, o)
+        a, b = P(o, L), P(self, L)
+        return Dual(a @ b, T(o, L) @ b + a @ T(self, L), L)
 
     def __lt__(self, o):
-        return self.p < P(o)
+        return _prim(self) < _prim(o)
 
     def __le__(self, o):
-        return self.p <= P(o)
+        return _prim(self) <= _prim(o)
 
     def __gt__(self, o):
-        return self.p > P(o)
+        return _prim(self) > _prim(o)
 
     def __ge__(self, o):
-        return self.p >= P(o)
+        return _prim(self) >= _prim(o)
 
     def __eq__(self, o):
-        return self.p == P(o)
+        return _prim(self) == _prim(o)
 
     __hash__ = None
 
@@ -142,6 +194,13 @@ class Dual:
         raise NotImplementedError(f"Dual: function {func.__name__}")
 
 
+def _prim(x):
+    """The plain NumPy primal underneath every level (what comparisons / indices see)."""
+    while isinstance(x, Dual):
+        x = x.p
+    return x
+
+
 class _At:
     def __init__(self, d):
         self.d = d
@@ -152,24 +211,42 @@ class _At:
         class _S:
             @staticmethod
             def set(v):
-                p, t = d.p.copy(), d.t.copy()
-                p[idx] = P(v)
-                t[idx] = T(v)
-                return Dual(p, t)
+                L = _top(d, v)
+                return Dual(_set(P(d, L), idx, P(v, L)), _set(T(d, L), idx, T(v, L)), L)
 
         return _S
 
 
+def _set(base, idx, val):
+    """base with base[idx] = val, where either may be a (lower-level) Dual."""
+    if isinstance(base, Dual) or isinstance(val, Dual):
+        return _lift(base, max(lvl(base), lvl(val))).at[idx].set(val)
+    out = np.array(base, dtype=np.float64, copy=True)
+    out[idx] = val
+    return out
+
+
+def _lift(x, level):
+    """x as a Dual of `level` (zero tangent) when it is of a lower level."""
+    if level <= 0 or lvl(x) >= level:
+        return x
+    return Dual(x, np.zeros(np.shape(x)), level)
+
+
 def _maximum(a, b):
-    pa, pb = P(a), P(b)
-    w = np.where(pa > pb, 1.0, np.where(pa == pb, 0.5, 0.0))
-    return Dual(np.maximum(pa, pb), w * T(a) + (1.0 - w) * T(b))
+    L = _top(a, b)
+    pa, pb = P(a, L), P(b, L)
+    ra, rb = _prim(pa), _prim(pb)
+    w = np.where(ra > rb, 1.0, np.where(ra == rb, 0.5, 0.0))
+    return Dual(np.maximum(pa, pb), w * T(a, L) + (1.0 - w) * T(b, L), L)
 
 
 def _minimum(a, b):
-    pa, pb = P(a), P(b)
-    w = np.where(pa < pb, 1.0, np.where(pa == pb, 0.5, 0.0))
-    return Dual(np.minimum(pa, pb), w * T(a) + (1.0 - w) * T(b))
+    L = _top(a, b)
+    pa, pb = P(a, L), P(b, L)
+    ra, rb = _prim(pa), _prim(pb)
+    w = np.where(ra < rb, 1.0, np.where(ra == rb, 0.5, 0.0))
+    return Dual(np.minimum(pa, pb), w * T(a, L) + (1.0 - w) * T(b, L), L)
 
 
 def _d(x):
@@ -177,31 +254,33 @@ def _d(x):
 
 
 _UFUNCS = {
-    np.add: lambda a, b: _d(a) + b,
-    np.subtract: lambda a, b: _d(a) - b,
-    np.multiply: lambda a, b: _d(a) * b,
-    np.true_divide: lambda a, b: _d(a) / b,
+    np.add: lambda a, b: _d(a) + b if isinstance(a, Dual) else b + a,
+    np.subtract: lambda a, b: a - b if isinstance(a, Dual) else b.__rsub__(a),
+    np.multiply: lambda a, b: a * b if isinstance(a, Dual) else b * a,
+    np.true_divide: lambda a, b: a / b if isinstance(a, Dual) else b.__rtruediv__(a),
     np.negative: lambda a: -a,
-    np.matmul: lambda a, b: _d(a) @ b,
-    np.exp: lambda a: Dual(np.exp(a.p), np.exp(a.p) * a.t),
-    np.log: lambda a: Dual(np.log(a.p), a.t / a.p),
-    np.sqrt: lambda a: Dual(np.sqrt(a.p), 0.5 * a.t / np.sqrt(a.p)),
+    np.matmul: lambda a, b: a @ b if isinstance(a, Dual) else b.__rmatmul__(a),
+    np.exp: lambda a: Dual(np.exp(a.p), np.exp(a.p) * a.t, a.level),
+    np.log: lambda a: Dual(np.log(a.p), a.t / a.p, a.level),
+    np.sqrt: lambda a: Dual(np.sqrt(a.p), 0.5 * a.t / np.sqrt(a.p), a.level),
     np.square: lambda a: a * a,
     np.power: lambda a, e: a ** e,
-    np.isnan: lambda a: np.isnan(a.p),
-    np.isfinite: lambda a: np.isfinite(a.p),
-    np.less: lambda a, b: P(a) < P(b),
-    np.less_equal: lambda a, b: P(a) <= P(b),
-    np.greater: lambda a, b: P(a) > P(b),
-    np.greater_equal: lambda a, b: P(a) >= P(b),
-    np.equal: lambda a, b: P(a) == P(b),
+    np.isnan: lambda a: np.isnan(_prim(a)),
+    np.isfinite: lambda a: np.isfinite(_prim(a)),
+    np.less: lambda a, b: _prim(a) < _prim(b),
+    np.less_equal: lambda a, b: _prim(a) <= _prim(b),
+    np.greater: lambda a, b: _prim(a) > _prim(b),
+    np.greater_equal: lambda a, b: _prim(a) >= _prim(b),
+    np.equal: lambda a, b: _prim(a) == _prim(b),
     np.maximum: _maximum,
     np.minimum: _minimum,
 }
 
 
 def _where(c, a, b):
-    return Dual(np.where(c, P(a), P(b)), np.where(c, T(a), T(b)))
+    L = _top(a, b)
+    c = _prim(c)
+    return Dual(np.where(c, P(a, L), P(b, L)), np.where(c, T(a, L), T(b, L)), L)
 
 
 def _clip(x, a_min=None, a_max=None, **kw):
@@ -215,20 +294,23 @@ def _clip(x, a_min=None, a_max=None, **kw):
 
 
 def _dot(a, b):
-    return Dual(np.dot(P(a), P(b)), np.dot(T(a), P(b)) + np.dot(P(a), T(b)))
+    L = _top(a, b)
+    pa, pb = P(a, L), P(b, L)
+    return Dual(np.dot(pa, pb), np.dot(T(a, L), pb) + np.dot(pa, T(b, L)), L)
 
 
 def _searchsorted(a, v, side="left", sorter=None):
-    return np.searchsorted(P(a), P(v), side=side)
+    return np.searchsorted(_prim(a), _prim(v), side=side)
 
 
 def _einsum(sub, *ops, **kw):
-    prim = [P(o) for o in ops]
+    L = _top(*ops)
+    prim = [P(o, L) for o in ops]
     out_t = 0.0
     for k, o in enumerate(ops):
-        if isinstance(o, Dual):
+        if lvl(o) == L:
             out_t = out_t + np.einsum(sub, *[o.t if j == k else prim[j] for j in range(len(ops))])
-    return Dual(np.einsum(sub, *prim), out_t)
+    return Dual(np.einsum(sub, *prim), out_t, L)
 
 
 _FUNCS = {
@@ -237,12 +319,12 @@ _FUNCS = {
     np.clip: _clip,
     np.dot: _dot,
     np.searchsorted: _searchsorted,
-    np.shape: lambda a: a.p.shape,
-    np.ndim: lambda a: a.p.ndim,
-    np.size: lambda a: a.p.size,
-    np.isnan: lambda a: np.isnan(a.p),
-    np.zeros_like: lambda a, **k: np.zeros_like(a.p),
-    np.ones_like: lambda a, **k: np.ones_like(a.p),
+    np.shape: lambda a: np.shape(a.p),
+    np.ndim: lambda a: np.ndim(a.p),
+    np.size: lambda a: np.size(a.p),
+    np.isnan: lambda a: np.isnan(_prim(a)),
+    np.zeros_like: lambda a, **k: np.zeros_like(_prim(a)),
+    np.ones_like: lambda a, **k: np.ones_like(_prim(a)),
 }
 
 _LINEAR = {np.concatenate, np.stack, np.sum, np.mean, np.diff, np.reshape, np.expand_dims,
@@ -250,21 +332,31 @@ _LINEAR = {np.concatenate, np.stack, np.sum, np.mean, np.diff, np.reshape, np.ex
            np.ravel, np.take}
 
 
+def _levels_in(x):
+    if isinstance(x, Dual):
+        return x.level
+    if isinstance(x, (tuple, list)):
+        return max([_levels_in(v) for v in x] or [0])
+    return 0
+
+
 def _map(x, f):
     if isinstance(x, Dual):
         return f(x)
-    if isinstance(x, (tuple, list)) and any(isinstance(v, Dual) for v in x):
+    if isinstance(x, (tuple, list)) and _levels_in(x) > 0:
         return type(x)(f(v) for v in x)
     return x
 
 
 def _linear(func, args, kwargs):
-    """Structure-only / linear functions: apply to primals and to tangents."""
-    pa = [_map(a, P) for a in args]
-    ta = [_map(a, T) for a in args]
-    return Dual(func(*pa, **kwargs), func(*ta, **kwargs))
+    """Structure-only / linear functions: apply to primals and to tangents (of the top level;
+    lower levels are handled by the recursive call on the components)."""
+    L = max(_levels_in(a) for a in args)
+    pa = [_map(a, lambda v: P(v, L)) for a in args]
+    ta = [_map(a, lambda v: T(v, L)) for a in args]
+    return Dual(func(*pa, **kwargs), func(*ta, **kwargs), L)
 
 
 def logsumexp(a):
-    m = np.max(P(a))
+    m = np.max(_prim(a))
     return np.log(np.sum(np.exp(a - m))) + m

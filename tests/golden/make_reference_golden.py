@@ -262,6 +262,50 @@ def ref_logp(m, out):
             g[k] = float(tot.t)
         return g
 
+    n_h = 96  # observations of the Hessian fixture (includes the tail / transition rows 0..5)
+
+    def total_dual(dv, c, yy, rows):
+        """The model log-density (likelihood of `rows` + priors) on a Dual parameter vector."""
+        from tensorflow_probability.substrates.jax import distributions as tfd
+
+        b_loc, b_scale, dz = dv[:p], dv[p:2 * p], dv[2 * p:]
+        mu = terms[0]["basis"][rows] @ (terms[0]["Z"] @ b_loc)
+        sigma = np.exp(terms[1]["basis"][rows] @ (terms[1]["Z"] @ b_scale))
+        delta = Z_delta @ dz
+        dist = m.dist.LocScaleTransformationDist(
+            coef=delta, loc=mu, scale=sigma, bspline=sp, batched=False)
+        tot = np.sum(dist.log_prob(jnp.asarray(yy[rows])))
+        for t, b in enumerate((b_loc, b_scale)):
+            d = m.gamdist.MultivariateNormalSingular(
+                loc=0.0, scale=tau[c, t], penalty=terms[t]["K"], penalty_rank=terms[t]["rank"])
+            tot = tot + d.log_prob(b)
+        return tot + np.sum(tfd.Normal(loc=0.0, scale=tau_d[c]).log_prob(dz))
+
+    def hessian_block(v, c, yy, lo, hi, full=False):
+        """FlatLogProb.hessian for ONE coefficient block v[lo:hi] (logprob.py:104-113:
+        `jacfwd(grad(log_prob))`): entry [i, j] = d/dv_j of (dlogp/dv_i).  grad is the inner
+        derivative (highest Dual level, declared custom_jvp rule), jacfwd the outer one, which
+        sees the rule body as ordinary code -- see jaxshim/jax/_dual.py.  The upper triangle
+        is computed and mirrored unless `full` (one block is done in full to record that the
+        jacfwd(grad) matrix is symmetric here)."""
+        from jax._dual import Dual
+
+        d = hi - lo
+        H = np.zeros((d, d))
+        rows = slice(0, n_h)
+        for i in range(d):
+            ei = np.zeros(P)
+            ei[lo + i] = 1.0
+            for j in range(d if full else i + 1):
+                ej = np.zeros(P)
+                ej[lo + j] = 1.0
+                dv = Dual(Dual(v, ej, 1), ei, 2)
+                tot = total_dual(dv, c, yy, rows)
+                H[i, j] = float(tot.t.t)
+                if not full:
+                    H[j, i] = H[i, j]
+        return H
+
     params = np.zeros((C, P))
     ll_i = np.zeros((C, n))
     ll_i_nan = np.zeros((C, n))
@@ -287,6 +331,33 @@ def ref_logp(m, out):
                 return (logp(v + e, c, y) - logp(v - e, c, y)) / (2 * h)
             h = 1e-3
             grad_fd[c, k] = (4.0 * f(h / 2) - f(h)) / 3.0
+    # Observed information (-Hessian) of the three coefficient blocks of chain 0 over the
+    # first n_h observations + priors: what CholInfo / PTMCholInfoFixed / IWLSKernelFixed
+    # .init_state / kernel.IWLSKernel._chol_info factorise (iwls_proposals.py:168-184,
+    # 227-245, 279-298; iwls_fixed.py:118-143; kernel.py:240-258)
+    hess_loc = hessian_block(params[0], 0, y, 0, p, full=True)
+    hess_scale = hessian_block(params[0], 0, y, p, 2 * p)
+    hess_dz = hessian_block(params[0], 0, y, 2 * p, P)
+
+    if os.environ.get("PTM_GOLDEN_CHECK_HESS"):
+        # self-check (off by default): the nested-Dual Hessian against central differences of
+        # the first-order forward-mode gradient on the same rows (the gradient is piecewise
+        # smooth: agreement ~1e-7 unless a row crosses a grid cell within the step)
+        from jax._dual import Dual
+
+        def grad_i(v, i):
+            e = np.zeros(P)
+            e[i] = 1.0
+            return float(total_dual(Dual(v, e), 0, y, slice(0, n_h)).t)
+
+        hcd = 1e-6
+        for (blk, lo) in ((hess_loc, 0), (hess_scale, p), (hess_dz, 2 * p)):
+            for (i, j) in ((0, 0), (1, 3), (4, 2), (7, 7)):
+                ej = np.zeros(P)
+                ej[lo + j] = hcd
+                fd = (grad_i(params[0] + ej, lo + i) - grad_i(params[0] - ej, lo + i)) / (2 * hcd)
+                print(f"hess check block@{lo} [{i},{j}]: nested {blk[i, j]:.10e}  fd {fd:.10e}")
+
     # IWLS information through GaussianLocCholInfo / GaussianScaleCholInfo
     # (iwls_proposals.py:55-89, 118-144) with a dict-backed model interface
     class DictModel:
@@ -330,6 +401,7 @@ def ref_logp(m, out):
 
     np.savez(os.path.join(out, "ref_logp_n257.npz"), y=y, ynan=ynan, precision=prec, chol=chol,
              intercepts=icpt, intercepts_seq=icpt_seq,
+             hess_n=n_h, hess_loc=hess_loc, hess_scale=hess_scale, hess_dz=hess_dz,
              x_loc=x_loc, x_scale=x_scale,
              knots_loc=terms[0]["knots"], knots_scale=terms[1]["knots"],
              Z_loc=terms[0]["Z"], Z_scale=terms[1]["Z"], K_loc=terms[0]["K"], K_scale=terms[1]["K"],

@@ -16,8 +16,14 @@ def load(name):
     return np.load(os.path.join(GOLDEN, name))
 
 
-def model_from_fixture(d, dtype=np.float64, device="cuda:0"):
-    """Product model built from the fixture's reparameterisation DATA (Z, K, knots)."""
+def model_from_fixture(d, dtype=np.float64, device="cuda:0", n_rows=None):
+    """Product model built from the fixture's reparameterisation DATA (Z, K, knots);
+    ``n_rows`` keeps the first observations only."""
+    if n_rows is not None:
+        d = dict(d)
+        d["y"] = d["y"][:n_rows]
+        for t in range(int(d["n_terms"])):
+            d[f"x{t}"] = d[f"x{t}"][:n_rows]
     model = lp.LocScalePTM.new_ptm(d["y"].astype(dtype), nparam=int(d["nparam"]),
                                    to_float32=(np.dtype(dtype) == np.float32), device=device)
     for t in range(int(d["n_terms"])):

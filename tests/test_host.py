@@ -4,6 +4,7 @@ the C-ABI library as a shared object (symbols, argument validation that needs no
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -193,3 +194,43 @@ def test_generated_dispatch_header_is_current():
     with open(os.path.join(root, "liesel_ptm_b200", "csrc", "ptm_dispatch.cuh")) as f:
         assert f.read() == out
 
+
+
+# ---- the JAX side of the boundary: committed, type-checked, not executable here ----
+def test_xla_ffi_translation_unit_type_checks_and_matches_fused_py(tmp_path):
+    """csrc/ptm_xla_ffi.cc compiles against a stand-in of the XLA FFI header (jax is absent
+    from this image) and links against libptm_b200.so; the handler symbols it exports are the
+    ones integration/fused.py registers; fused.py byte-compiles."""
+    import importlib.util
+    import py_compile
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available: the XLA FFI translation unit is NOT type-checked")
+    _lib.load()
+    src = os.path.join(ROOT, "liesel_ptm_b200", "csrc", "ptm_xla_ffi.cc")
+    out = str(tmp_path / "libptm_xla_ffi_stub.so")
+    cuda_inc = "/usr/local/cuda/include"
+    cmd = ["g++", "-std=c++17", "-Wall", "-Werror", "-shared", "-fPIC", "-DPTM_FFI_STUB",
+           "-I" + os.path.join(ROOT, "tests", "ffi_stub"), "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"),
+           src, "-L" + os.path.join(ROOT, "liesel_ptm_b200"), "-lptm_b200", "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    syms = subprocess.run(["nm", "-D", "--defined-only", out], capture_output=True, text=True).stdout
+    exported = sorted(ln.split()[-1] for ln in syms.splitlines() if " T Ptm" in ln)
+    fused_path = os.path.join(ROOT, "integration", "fused.py")
+    py_compile.compile(fused_path, doraise=True)
+    spec = importlib.util.spec_from_file_location("ptm_fused", fused_path)
+    fused = importlib.util.module_from_spec(spec)
+    sys.modules["ptm_fused"] = fused  # dataclasses look the module up
+    spec.loader.exec_module(fused)  # top level imports only numpy / ctypes
+    assert sorted(fused.all_target_symbols()) == exported
+    # every entry point the handlers call is declared in the header
+    names = _header_functions()
+    for name in fused.FFI_TARGETS:
+        assert f"{name}_f64" in names and f"{name}_f32" in names, name
+    # without the stub macro and without jax the TU compiles to nothing (guarded)
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + cuda_inc,
+                        "-I" + os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -143,6 +143,13 @@ def test_oracle_logp_grad_information_match_reference_code():
         assert abs(b0 - d["intercepts"][c, 0]) < 1e-14 and abs(g0 - d["intercepts"][c, 1]) < 1e-14
         b0, g0 = om.compute_intercepts(st, c, sequential=True)
         assert abs(b0 - d["intercepts"][c, 0]) < 1e-14 and abs(g0 - d["intercepts_seq"][c]) < 1e-14
+    # observed information: jacfwd(grad(logp)) of each coefficient block through the
+    # reference's code on nested forward-mode values (logprob.py:104-113; iwls_proposals.py:
+    # 168-184, 227-245, 279-298; kernel.py:240-258), first hess_n observations + priors
+    rows = slice(0, int(d["hess_n"]))
+    assert np.max(np.abs(d["hess_loc"] - d["hess_loc"].T)) < 1e-12 * np.max(np.abs(d["hess_loc"]))
+    for blk, key in ((0, "hess_loc"), (1, "hess_scale"), ("delta_z", "hess_dz")):
+        assert rel_err(om.hessian_block(st, 0, blk, rows=rows), d[key]) < 1e-13, key
     _, P0, L0 = om.loc_precision(st, 0)
     _, P1 = om.scale_precision(st, 1)
     assert rel_err(P0, d["precision"][:, 0]) < 1e-14 and rel_err(L0, d["chol"][:, 0]) < 1e-13
