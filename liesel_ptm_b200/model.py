@@ -759,7 +759,8 @@ class _ObservedCholInfo:
 
     @property
     def nan_in_cholesky_of_unprocessed_finfo(self) -> bool:
-        return bool(torch.isnan(torch.linalg.cholesky_ex(self._fisher_info_unprocessed)[0]).any())
+        # jnp.linalg.cholesky gives NaN where torch reports a failed pivot
+        return bool((torch.linalg.cholesky_ex(self._fisher_info_unprocessed).info != 0).any())
 
 
 class PTMCholInfoFixed(_ObservedCholInfo):
@@ -783,7 +784,8 @@ class PTMCholInfo(_ObservedCholInfo):
         return self.fisher_info * (1.0 / scale.clamp_min(eps) ** 2)[:, None, None]
 
     def chol_info(self, params: torch.Tensor) -> torch.Tensor:
-        return torch.linalg.cholesky_ex(self.precision(params))[0]
+        L, info = torch.linalg.cholesky_ex(self.precision(params))
+        return torch.where((info != 0)[:, None, None], torch.full_like(L, float("nan")), L)
 
 
 class ObservedCholInfoOrIdentity(_ObservedCholInfo):
