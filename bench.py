@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--n", type=int, default=0, help="override the number of observations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-n", type=int, default=100_000)
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements under `extra`")
     return ap.parse_args()
 
 
@@ -120,27 +121,40 @@ def cpu_oracle_throughput(config: str, dtype, sample_n: int, steps: int, warmup:
                 ms_per_step=sec * 1e3, steps=steps)
 
 
+def _config_dict(name, n, C, world, n_loc, n_scale, nbases, P):
+    return {
+        "workload": name, "n": n, "chains_per_gpu": C, "chains_total": C * world,
+        "terms": f"{n_loc} loc + {n_scale} scale P-splines, nbases {nbases}, nparam 20",
+        "params_per_chain": P, "parallelism": f"chain-sharded x{world}, no collective",
+    }
+
+
 def run_reference(args):
+    """The reference's algorithm for the path on the host cores.  The reference itself cannot
+    be installed here, so this is the oracle port; every step is a bounded
+    sample of the workload (first --cpu-sample-n observations x one chain per core), the
+    driver's --steps / --warmup are honoured as given."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     dtype = np.float64
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     cb = cpu_oracle_throughput(args.config, dtype, args.cpu_sample_n, steps, warm)
     import bench_workload as bw
 
     n, n_loc, n_scale, nbases, C = bw.CONFIGS[args.config]
+    P = 2 + (n_loc + n_scale) * (nbases - 1) + 19 + (n_loc + n_scale) + 1
+    cfg = _config_dict(args.config, n, args.chains or C, max(args.gpus, 1), n_loc, n_scale, nbases, P)
+    cfg["reference_sample"] = cb["sample"]
+    cfg["note"] = ("reference arm = CPU restatement (oracle) of the reference algorithm on the host cores; "
+                   "the reference itself (jax 0.8.2 / liesel 0.4.3 / Python 3.13) cannot be installed in "
+                   "this image; throughput is per obs*chain evaluation, so the bounded sample extrapolates "
+                   "linearly to the configuration")
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": args.config, "n": n, "chains_per_gpu": args.chains or C,
-                   "terms": f"{n_loc} loc + {n_scale} scale P-splines, nbases {nbases}, nparam 20",
-                   "note": "reference arm = CPU restatement (oracle) of the reference algorithm; the "
-                           "reference itself (jax 0.8.2 / liesel 0.4.3 / Python 3.13) cannot be "
-                           "installed in this image"},
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -299,13 +313,34 @@ def run_ours(args):
     e2e_ms = float(t.item())
     finite = bool(np.isfinite(lp_h).all() and np.isfinite(g_h).all())
 
-    if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak = float(json.load(open(peaks_path))["hbm_gbs"])
-            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # secondary measurements of the same run (bench_extra.py); the headline numbers above are
+    # complete before any of this starts
+    extra = {}
+    if not args.no_extra and args.config == DEFAULT_CONFIG and not args.n and not args.chains:
+        import bench_extra as bx
+        import liesel_ptm_b200 as lp_mod
+
+        del model, params, grad, logp
+        wl.model = None
+        torch.cuda.empty_cache()
+        reps = max(3, min(K, 10))
+        if world == 1:
+            if args.dtype == "f64":
+                bx._guard(extra, "c3_f32", lambda: bx.f32_c3(torch, bw, dev, peak, reps))
+            bx._guard(extra, "c4_information", lambda: bx.c4_information(torch, bw, dev, 5))
+            bx._guard(extra, "ess", lambda: bx.ess(torch, bw, dev))
         else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+            bx._guard(extra, "c3_strong_scaling", lambda: bx.strong_scaling_c3(torch, dist, bw, dev, rank, world, dtype, reps))
+            bx._guard(extra, "c5_obs_sharded", lambda: bx.c5_obs_sharded(torch, dist, bw, lp_mod, dev, rank, world, dtype, 5))
+
+    if rank == 0:
         ms_per_step = total_ms / K
         value = n * C * world / (ms_per_step * 1e-3)
         achieved = n * C * wl.bytes_alg / (main_ms * 1e-3) / 1e9
@@ -321,16 +356,16 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {
-                "workload": wl.name, "n": n, "chains_per_gpu": C, "chains_total": C * world,
-                "terms": f"{wl.n_loc} loc + {wl.n_scale} scale P-splines, nbases {wl.nbases}, nparam 20",
-                "params_per_chain": int(wl.params.shape[1]), "parallelism": f"chain-sharded x{world}, no collective",
-                "l2": "flushed between timed steps (256 MiB write); inputs are 88 MB < L2",
-                "finite_outputs": finite,
-            },
+            "config": dict(
+                _config_dict(wl.name, n, C, world, wl.n_loc, wl.n_scale, wl.nbases, int(wl.params.shape[1])),
+                l2="flushed between timed steps (256 MiB write); inputs are 88 MB < L2",
+                finite_outputs=finite),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "ptm::k_main",
+                "traffic": traffic,
+                "traffic_source": "static: ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel on "
+                                  "this workload, profiles/r1_traffic.json (not re-measured in this run)",
+                "peak_source": peak_src, "kernel": "ptm::k_main",
                 "kernel_ms": main_ms, "pre_ms": pre_ms, "post_ms": post_ms,
                 "bytes_alg_per_eval": wl.bytes_alg,
                 "note": "algorithmic bytes = w*(1+T_x) per obs-chain eval; the kernel re-uses every "
@@ -349,6 +384,8 @@ def run_ours(args):
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
