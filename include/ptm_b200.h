@@ -325,6 +325,13 @@ int ptm_pointwise_f32(const PtmProblem* prob, const float* params, int64_t n_sam
 /* Number of kernels the last logp / logp_grad call on this thread launched. */
 int ptm_last_launch_count(void);
 
+/* Route the last logp / logp_grad sweep on this thread took: 0 = CUDA-core sweep (k_main);
+ * 1 = tcgen05 sweep (float problems whose coefficient count fits tensor memory, sum of
+ * nbases <= 224: eta = Gamma B' and the coefficient gradients G' B on the tensor cores with
+ * the 3xTF32 split, ptm_main_tc.cuh).  PTM_MAIN_TC=0 in the environment at create time forces
+ * the CUDA-core sweep. */
+int ptm_last_main_route(void);
+
 /* Route the last information sweep (ptm_xtwx / ptm_loc_precision / ptm_loc_precision_all)
  * on this thread took: 0 = banded CUDA-core sweep; 2 = tcgen05 tensor-core sweep (float
  * problems, location terms, when the terms fit TMEM / shared memory) with the scale

@@ -36,7 +36,7 @@ SYMBOLS = [
     "ptm_pointwise_workspace_bytes", "ptm_pointwise_f64", "ptm_pointwise_f32",
     "ptm_problem_shared_designs", "ptm_predict_workspace_bytes", "ptm_predict_f64", "ptm_predict_f32",
     "ptm_predict_quantile_f64", "ptm_predict_quantile_f32", "ptm_inverse_f64", "ptm_inverse_f32",
-    "ptm_last_launch_count", "ptm_last_xtwx_route", "ptm_profile_enable", "ptm_last_kernel_ms", "ptm_last_error",
+    "ptm_last_launch_count", "ptm_last_main_route", "ptm_last_xtwx_route", "ptm_profile_enable", "ptm_last_kernel_ms", "ptm_last_error",
     "ptm_version",
 ]
 
@@ -157,6 +157,7 @@ def load() -> C.CDLL:
         f.restype = C.c_int
     lib.ptm_last_launch_count.restype = C.c_int
     lib.ptm_last_xtwx_route.restype = C.c_int
+    lib.ptm_last_main_route.restype = C.c_int
     lib.ptm_profile_enable.argtypes = [C.c_int]
     lib.ptm_profile_enable.restype = C.c_int
     lib.ptm_last_kernel_ms.argtypes = [C.POINTER(C.c_float)] * 3

@@ -19,6 +19,7 @@
 #include "ptm_xtwx_tc.cuh"
 #include "ptm_predict.cuh"
 #include "ptm_hessian.cuh"
+#include "ptm_main_tc.cuh"
 
 namespace {
 
@@ -46,7 +47,12 @@ struct Plan {
   int TPW, NTW;  // smooth terms per term warp, term warps
   long long chunk_len;
   size_t smem_main;
-  size_t off_gamma, off_cc, off_partial, off_xt, off_scratch, total;
+  size_t off_gamma, off_cc, off_partial, off_xt, off_scratch, off_G, total;
+  // tensor-core route of the float sweep (ptm_main_tc.cuh): its own chunking of the observations
+  bool tc = false;
+  int tc_NT = 0, tc_NSW = 0, tc_M = 0, tc_CB = 0;
+  long long tc_chunk = 0;
+  size_t tc_smem_fwd = 0, tc_smem_bwd = 0;
 };
 
 }  // namespace
@@ -76,6 +82,8 @@ struct PtmProblem {
     int tpw = 0, nu = 0, to = 0, items_per_sm = 0;
     int xtwx_tc = 3;   // PTM_XTWX_TC: 0 banded, 1 / 2 tensor-core versions, 3 = pick
     int tc_flush = 0;  // PTM_TC_FLUSH
+    int main_tc = 1;   // PTM_MAIN_TC: 0 = CUDA-core sweep only, 1 = tensor-core sweep when the model fits
+    int mtc_items = 0; // PTM_MTC_ITEMS: work items per CTA of the tensor-core sweep (0 = default)
   } tune;
   // shard views share the device arrays of the handle they were made from
   const PtmProblem* base = nullptr;
@@ -176,6 +184,8 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
     pr->tune.items_per_sm = env_int("PTM_ITEMS_PER_SM", 0);
     pr->tune.xtwx_tc = env_int("PTM_XTWX_TC", 3);
     pr->tune.tc_flush = env_int("PTM_TC_FLUSH", 0);
+    pr->tune.main_tc = env_int("PTM_MAIN_TC", 1);
+    pr->tune.mtc_items = env_int("PTM_MTC_ITEMS", 0);
   }
   if (pr->T_loc == pr->T_scale && pr->T_loc > 0 && !getenv("PTM_NO_SHARED")) {
     std::vector<int> loc, sc;
@@ -372,12 +382,49 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   pl.chunk_len = chunk;
   pl.n_items = pl.CG * pl.M;
   pl.grid = std::min(pl.n_items, pr->num_sms);
+  // float problems whose coefficient count fits tensor memory: eta and the coefficient
+  // gradients on tcgen05 (ptm_main_tc.cuh)
+  size_t g_bytes = 0;
+  long long n_part_items = pl.n_items;
+  if (sizeof(R) == 4 && pr->tune.main_tc && T >= 1 && T <= 24) {
+    int K8[2] = {0, 0}, K16[2] = {0, 0};
+    for (int t = 0; t < T; ++t) {
+      const int q = pr->pred[t] == PTM_LOC ? 0 : 1;
+      K8[q] += (pr->nb[t] + 3) & ~3;
+      K16[q] += (pr->nb[t] + 3) & ~3;
+    }
+    for (int q = 0; q < 2; ++q) { K8[q] = (K8[q] + 7) & ~7; K16[q] = (K16[q] + 15) & ~15; }
+    const int Kt = K8[0] + K8[1];
+    const int avail = (512 - 2 * Kt) / 2;
+    const int NT = avail >= 64 ? 64 : (avail >= 48 ? 48 : (avail >= 32 ? 32 : 0));
+    const int NSW = std::min(T, 6);
+    if (Kt <= ptm::kMtcMaxK && NT > 0 && K16[0] + K16[1] <= 256 && len > 0) {
+      pl.tc_smem_fwd = (size_t)2 * NT * Kt * 4 + (size_t)(NCC + 4) * 128 * 4 + (size_t)ptm::kMtcEvalWarps * NGV * 32 * 4 +
+                       (size_t)T * 4 * ptm::kKnotStride * 4 + (size_t)ptm::kMtcEvalWarps * ptm::kRegSlots * 32 * 8 + 128;
+      pl.tc_smem_bwd = (size_t)2 * 2 * (K16[0] + K16[1]) * ptm::kGtcKT * 4 + (size_t)T * 4 * ptm::kKnotStride * 4 + 128;
+      if (pl.tc_smem_fwd <= 227 * 1024 - 64 && pl.tc_smem_bwd <= 227 * 1024 - 64) {
+        pl.tc = true;
+        pl.tc_NT = NT; pl.tc_NSW = NSW;
+        pl.tc_CB = (int)((C + 127) / 128);
+        const long long items_per_sm = pr->tune.mtc_items > 0 ? pr->tune.mtc_items : 4;
+        long long Mt = std::max<long long>(1, items_per_sm * pr->num_sms / pl.tc_CB);
+        Mt = std::min(Mt, std::max<long long>(1, len / (8LL * 192)));
+        long long ch = (len + Mt - 1) / Mt;
+        ch = std::max<long long>(192, (ch + 191) / 192 * 192);  // whole forward (32/48/64) and backward (32) tiles
+        Mt = std::max<long long>(1, (len + ch - 1) / ch);
+        pl.tc_M = (int)Mt; pl.tc_chunk = ch;
+        n_part_items = std::max<long long>(n_part_items, (long long)pl.CG * Mt);
+        g_bytes = (size_t)len * 2 * (size_t)pl.tc_CB * 128 * 4;
+      }
+    }
+  }
   size_t off = 0;
   pl.off_gamma = off; off = align_up(off + (size_t)std::max(T, 1) * ptm::kMaxNbases * C * sizeof(R), 256);
   pl.off_cc = off;    off = align_up(off + (size_t)NCC * C * sizeof(R), 256);
-  pl.off_partial = off; off = align_up(off + (size_t)pl.n_items * pl.NSLOT * 32 * sizeof(double), 256);
+  pl.off_partial = off; off = align_up(off + (size_t)n_part_items * pl.NSLOT * 32 * sizeof(double), 256);
   pl.off_xt = off;    off = align_up(off + ptm::xtwx_workspace_bytes<R>(std::max(pr->sum_nb, 1), C), 256);
   pl.off_scratch = off; off = align_up(off + (size_t)C * sizeof(R), 256);
+  pl.off_G = off;     off = align_up(off + g_bytes, 256);
   pl.total = off;
   return pl;
 }
@@ -490,6 +537,71 @@ int check_device(const PtmProblem* pr) {
 
 bool is_sharded(const PtmProblem* pr) { return pr->obs_begin != 0 || pr->obs_end != pr->n || !pr->add_priors; }
 
+// Tensor-core route of the float sweep: k_main_tc (+ k_grad_tc when the gradient is wanted).
+// Returns PTM_OK or an error; the caller has checked pl.tc.
+int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gamma, float* cc, double* partial,
+                   float* G, bool want_grad, cudaStream_t st) {
+  static thread_local ptm::MainTcArgs g;  // 3 KB of launch arguments: keep it off the stack hot path
+  memset(&g, 0, sizeof g);
+  Plan plc = pl;
+  plc.M = pl.tc_M; plc.chunk_len = pl.tc_chunk; plc.n_items = pl.tc_CB * pl.tc_M;
+  fill_main_args<float>(pr, plc, C, Gamma, cc, partial, g.a);
+  g.a.shared = 0;
+  if (!want_grad) g.a.NSLOT = ptm::kLogpSlots;
+  g.G = G; g.CB = pl.tc_CB; g.Cpad = pl.tc_CB * 128; g.NT = pl.tc_NT; g.NSW = pl.tc_NSW;
+  g.mode = want_grad ? ptm::kModeGrad : ptm::kModeLogp;
+  g.flush = pr->tune.tc_flush > 0 ? pr->tune.tc_flush : 32;
+  const int NGV = pr->KK + 4;
+  memset(g.kterm, 255, sizeof g.kterm);
+  for (size_t i = 0; i < sizeof g.dslot / sizeof g.dslot[0]; ++i) g.dslot[i] = -1;
+  int k = 0, n = 0;
+  for (int q = 0; q < 2; ++q) {
+    g.kbase[q] = k; g.nbase[q] = n;
+    for (int t = 0; t < pr->T; ++t) {
+      if ((pr->pred[t] == PTM_LOC ? 0 : 1) != q) continue;
+      g.kcol[t] = k; g.ncol[t] = n;
+      for (int j = 0; j < pr->nb[t]; ++j) {
+        g.kterm[k + j] = (unsigned char)t; g.kj[k + j] = (unsigned char)j;
+        g.dslot[n + j] = (short)(ptm::kRegSlots + NGV + pr->goff[t] + j);
+      }
+      k += (pr->nb[t] + 3) & ~3; n += (pr->nb[t] + 3) & ~3;
+    }
+    k = (k + 7) & ~7; n = (n + 15) & ~15;
+    g.Kq[q] = k - g.kbase[q]; g.Nq[q] = n - g.nbase[q];
+  }
+  g.Kt = k;
+  const int threads = 32 * ((ptm::kMtcEvalWarps + pl.tc_NSW + 1 + 3) / 4 * 4);
+  const int grid = std::min(plc.n_items, pr->num_sms);
+#define PTM_MTC_LAUNCH(NTV)                                                            \
+  do {                                                                                 \
+    if (want_grad) {                                                                   \
+      auto kern = ptm::k_main_tc<NTV, true>;                                           \
+      PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_fwd));                                \
+      kern<<<grid, threads, pl.tc_smem_fwd, st>>>(g);                                  \
+    } else {                                                                           \
+      auto kern = ptm::k_main_tc<NTV, false>;                                          \
+      PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_fwd));                                \
+      kern<<<grid, threads, pl.tc_smem_fwd, st>>>(g);                                  \
+    }                                                                                  \
+  } while (0)
+  if (pl.tc_NT == 64) PTM_MTC_LAUNCH(64);
+  else if (pl.tc_NT == 48) PTM_MTC_LAUNCH(48);
+  else PTM_MTC_LAUNCH(32);
+#undef PTM_MTC_LAUNCH
+  PTM_CUDA(cudaGetLastError());
+  ++g_launches;
+  if (want_grad) {
+    auto kern = ptm::k_grad_tc;
+    PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_bwd));
+    kern<<<grid, threads, pl.tc_smem_bwd, st>>>(g);
+    PTM_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  return PTM_OK;
+}
+
+static thread_local int g_last_main_route = 0;  // 0 = CUDA-core sweep (k_main), 1 = tcgen05 sweep
+
 // ld_logp / ld_grad: element strides of the outputs (1 / P for separate arrays, 1 + P for the
 // packed [C, 1 + P] block of ptm_logp_grad_block_*).
 template <typename R>
@@ -523,14 +635,28 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   fill_main_args<R>(pr, pl, C, Gamma, cc, partial, ma);
   if (!want_grad) ma.NSLOT = ptm::kLogpSlots;
   int rc;
-  if (pr->max_nb <= 20)
-    rc = want_grad ? launch_main<R, 20, ptm::kModeGrad>(ma, pl, pr->T, st)
-                   : launch_main<R, 20, ptm::kModeLogp>(ma, pl, pr->T, st);
-  else
-    rc = want_grad ? launch_main<R, 32, ptm::kModeGrad>(ma, pl, pr->T, st)
-                   : launch_main<R, 32, ptm::kModeLogp>(ma, pl, pr->T, st);
-  if (rc != PTM_OK) return rc;
-  ++g_launches;
+  int post_M = pl.M;
+  bool took_tc = false;
+  if constexpr (sizeof(R) == 4) {
+    if (pl.tc) {
+      rc = launch_main_tc(pr, pl, C, reinterpret_cast<float*>(Gamma), reinterpret_cast<float*>(cc), partial,
+                          reinterpret_cast<float*>(wsb + pl.off_G), want_grad, st);
+      if (rc != PTM_OK) return rc;
+      post_M = pl.tc_M;
+      took_tc = true;
+    }
+  }
+  g_last_main_route = took_tc ? 1 : 0;
+  if (!took_tc) {
+    if (pr->max_nb <= 20)
+      rc = want_grad ? launch_main<R, 20, ptm::kModeGrad>(ma, pl, pr->T, st)
+                     : launch_main<R, 20, ptm::kModeLogp>(ma, pl, pr->T, st);
+    else
+      rc = want_grad ? launch_main<R, 32, ptm::kModeGrad>(ma, pl, pr->T, st)
+                     : launch_main<R, 32, ptm::kModeLogp>(ma, pl, pr->T, st);
+    if (rc != PTM_OK) return rc;
+    ++g_launches;
+  }
   if (g_profile) PTM_CUDA(cudaEventRecord(g_ev[2], st));
 
   ptm::PostArgs<R> po;
@@ -541,7 +667,7 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   po.Kall = reinterpret_cast<const R*>(pr->d_Kall);
   po.Zd = reinterpret_cast<const R*>(pr->d_Zd);
   po.tc = reinterpret_cast<const ptm::TrafoConst<double>*>(pr->d_tc64);
-  po.C = (int)C; po.P = pr->P; po.T = pr->T; po.M = pl.M; po.NSLOT = ma.NSLOT; po.KK = pr->KK;
+  po.C = (int)C; po.P = pr->P; po.T = pr->T; po.M = post_M; po.NSLOT = ma.NSLOT; po.KK = pr->KK;
   for (int t = 0; t < pr->T; ++t) {
     po.nb[t] = pr->nb[t]; po.p[t] = pr->p[t]; po.zoff[t] = pr->zoff[t]; po.koff[t] = pr->koff[t];
     po.boff[t] = pr->boff[t]; po.goff[t] = pr->goff[t]; po.rank[t] = pr->rank[t];
@@ -1269,6 +1395,7 @@ int ptm_hessian_block_f32(const PtmProblem* p, int32_t block, int32_t mode, cons
 }
 
 int ptm_last_launch_count(void) { return g_launches; }
+int ptm_last_main_route(void) { return g_last_main_route; }
 int ptm_last_xtwx_route(void) { return g_last_xtwx_route; }
 
 int ptm_profile_enable(int on) {

@@ -1,0 +1,684 @@
+// ptm_main_tc.cuh -- tensor-core route of the fused logp(+gradient) sweep for FLOAT problems.
+//
+// The two contractions of the sweep have a chain-independent operand (dist.py:718-740 over
+// gam/var.py:157-162 and its transpose in reverse mode):
+//
+//   forward   eta_q[chain, obs]  = sum_k Gamma[chain, k] * B[obs, k]      q = mu, sigma
+//   backward  dGamma[chain, k]  += sum_obs G_q[chain, obs] * B[obs, k]    G_q = dl/deta_q
+//
+// with k = (smooth term, B-spline coefficient) and B the banded design expanded to its dense
+// row (4 non-zeros per term and observation).  Both run on tcgen05.mma kind::tf32 with the
+// 3xTF32 split (hi*hi + hi*lo + lo*hi, hi = cvt.rna.tf32, lo = x - hi), M = 128 chains:
+//
+//   k_main_tc  (forward + point-wise part):  A = Gamma hi / lo in TENSOR MEMORY (written once per
+//       work item with tcgen05.st, lane = chain), B = the expanded design tile [NT obs x K] in
+//       shared memory (core-matrix layout, written by the stager warps: only the four entries
+//       per term and observation change from tile to tile), D = eta_mu, eta_sigma [128 x NT]
+//       in TMEM.  16 eval warps (4 per chain quarter) read their eta values with tcgen05.ld,
+//       release the accumulators, and run the point-wise part of k_main (transformation,
+//       log-Jacobian, declared derivatives, gradient w.r.t. the B-spline coefficients of h);
+//       dl/deta goes to HBM as G[obs][q][chain] (8 bytes per evaluation).
+//   k_grad_tc  (backward):  A = G hi / lo in TMEM (loader warps: coalesced read, split,
+//       tcgen05.st), B = the expanded design transposed [K coefs x 32 obs] in shared memory,
+//       D = dGamma [128 chains x K] in TMEM, promoted to the double partials of k_post every
+//       `flush` tiles.
+//
+// TMEM budget (512 columns): 2 K (Gamma hi, lo) + 2 NT (eta)  and  2 K16 + 256 (G tiles), so the
+// route takes models with K = sum of bases <= 224 (c3: 5 + 5 terms x 20 -> 208, NT = 48); larger
+// models use the CUDA-core sweep (k_main).  tools/micro/umma_ts.cu is the known-answer test of
+// the TMEM-operand MMA form used here.
+#pragma once
+#include <cstdint>
+
+#include "ptm_kernels.cuh"
+#include "ptm_xtwx_tc.cuh"
+
+namespace ptm {
+
+constexpr int kMtcEvalWarps = 16;  // 4 chain quarters x 4 observation groups
+constexpr int kMtcMaxK = 224;
+constexpr int kGtcKT = 32;         // observations per backward K tile
+
+struct MainTcArgs {
+  MainArgs<float> a;
+  float* G;            // [len][2][Cpad] dl/deta_mu, dl/deta_sigma (chain fastest)
+  int CB, Cpad;        // chain blocks of 128
+  int Kt;              // forward K extent (both predictor blocks, each padded to 8)
+  int Kq[2], kbase[2]; // forward K extent / first column of the mu and sigma blocks
+  int NT;              // observations per forward tile (48 or 64)
+  int NSW;             // stager warps
+  int kcol[kMaxTerms]; // first forward K column of each term
+  unsigned char kterm[kMtcMaxK], kj[kMtcMaxK];  // forward K column -> (term, coefficient); 255 = padding
+  // backward
+  int Nq[2], nbase[2]; // D columns / first D column of the predictor blocks (padded to 16)
+  int ncol[kMaxTerms]; // first D column of each term
+  short dslot[2 * kMtcMaxK + 32];  // D column -> partial slot (-1 = padding)
+  int flush;           // backward tiles between promotions to double
+  int mode;            // kModeLogp / kModeGrad
+};
+
+__device__ __forceinline__ void mtc_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d), "r"(a_tmem), "l"(db),
+      "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t mtc_desc(uint32_t addr, int sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void mtc_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mtc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mtc_st8(uint32_t addr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void mtc_ld4(uint32_t addr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// forward + point-wise part
+// ---------------------------------------------------------------------------------------
+template <int NT, bool GRAD>
+__global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
+  const MainArgs<float>& a = g.a;
+  constexpr int OPW = NT / 4;  // observations per eval warp and tile
+  extern __shared__ __align__(128) unsigned char smem_mtc[];
+  __shared__ __align__(8) uint64_t s_bar[3];  // [0] eta ready (MMA commit), [1] eta consumed, [2] B tile filled
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = a.T, KK = a.KK, Kt = g.Kt, NSW = g.NSW;
+  const int NCC = KK * 5 + 6, NGV = KK + 4;
+  const int sbo = (Kt >> 2) * 128, bbytes = NT * Kt * 4;
+  unsigned char* s_B = smem_mtc;                                            // [hi, lo][NT x Kt]
+  float* s_cc = reinterpret_cast<float*>(s_B + 2 * bbytes);                 // [NCC + 4][128]
+  float* s_gv = s_cc + (NCC + 4) * 128;                                     // [16][NGV][32]
+  float* s_kn = s_gv + (GRAD ? kMtcEvalWarps * NGV * 32 : 0);               // [T][4][kKnotStride]
+  double* s_red = reinterpret_cast<double*>(s_kn + T * 4 * kKnotStride + ((T * 4 * kKnotStride) & 1));  // [16][kRegSlots][32]
+
+  const bool is_eval = warp < kMtcEvalWarps;
+  const int sidx = warp - kMtcEvalWarps;
+  const bool is_stager = sidx >= 0 && sidx < NSW;
+  const bool is_mma = sidx == NSW;
+  const int q4 = warp & 3, sub = (warp >> 2) & 3;
+
+  for (int t = warp; t < T; t += blockDim.x >> 5) {
+    float* kn = s_kn + t * 4 * kKnotStride;
+    const float* gk = a.knots + t * kKnotStride;
+    const int nbt = a.nb[t];
+    for (int i = lane; i < nbt + 4; i += 32) {
+      kn[i] = gk[i];
+      kn[kKnotStride + i] = i + 1 < nbt + 4 ? 1.f / (gk[i + 1] - gk[i]) : 0.f;
+      kn[2 * kKnotStride + i] = i + 2 < nbt + 4 ? 1.f / (gk[i + 2] - gk[i]) : 0.f;
+      kn[3 * kKnotStride + i] = i + 3 < nbt + 4 ? 1.f / (gk[i + 3] - gk[i]) : 0.f;
+    }
+  }
+  // the design tile starts as zeros; afterwards only the entries a tile wrote are cleared
+  for (int i = tid; i < (2 * bbytes) >> 4; i += blockDim.x) reinterpret_cast<float4*>(s_B)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[1])), "r"(kMtcEvalWarps));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[2])), "r"(NSW));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  const uint32_t barE = smem_u32(&s_bar[0]), barC = smem_u32(&s_bar[1]), barB = smem_u32(&s_bar[2]);
+  const uint32_t etaCol = (uint32_t)(2 * Kt);
+  const TrafoScal<float> ts = a.ts;
+  uint32_t tg = 0;  // tiles this CTA has gone through (phase parity of all three barriers)
+
+  // stager state: K column each (owned term, pass) wrote last, -1 = nothing to clear
+  int prev_k[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) prev_k[i][0] = prev_k[i][1] = -1;
+
+  for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const int cb = item / a.M, mchunk = item - cb * a.M;
+    const long long o_begin = a.obs_begin + (long long)mchunk * a.chunk_len;
+    long long o_end = o_begin + a.chunk_len;
+    if (o_end > a.obs_end) o_end = a.obs_end;
+    const long long len = o_end > o_begin ? o_end - o_begin : 0;
+    const int ntiles = (int)((len + NT - 1) / NT);
+    int chain = cb * 128 + q4 * 32 + lane;
+    if (chain >= a.C) chain = a.C - 1;
+    const int cg = cb * 4 + q4;
+
+    float beta0 = 0.f, gamma0 = 0.f;
+    if (is_eval) {
+      // Gamma hi / lo of the 128 chains -> TMEM (thread = chain, 8 columns per store)
+      for (int c0 = sub * 8; c0 < Kt; c0 += 32) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = c0 + j;
+          const int t = g.kterm[k];
+          const float v = t != 255 ? a.Gamma[((long long)t * kMaxNbases + g.kj[k]) * a.C + chain] : 0.f;
+          const float vh = tf32_round(v);
+          hi[j] = __float_as_uint(vh);
+          lo[j] = __float_as_uint(v - vh);
+        }
+        const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0;
+        mtc_st8(addr, hi);
+        mtc_st8(addr + (uint32_t)Kt, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      for (int s = sub; s < NCC; s += 4) s_cc[s * 128 + q4 * 32 + lane] = a.cc[(long long)s * a.C + chain];
+      if (sub == 0) {
+        ChainBoundary<float> cbd;
+        make_boundary(ts, a.cc[(long long)(KK * 5 + 0) * a.C + chain], a.cc[(long long)(KK * 5 + 1) * a.C + chain],
+                      a.cc[(long long)(KK * 5 + 2) * a.C + chain], a.cc[(long long)(KK * 5 + 3) * a.C + chain], cbd);
+        s_cc[(NCC + 0) * 128 + q4 * 32 + lane] = cbd.constL;
+        s_cc[(NCC + 1) * 128 + q4 * 32 + lane] = cbd.constR;
+        s_cc[(NCC + 2) * 128 + q4 * 32 + lane] = cbd.ztailL;
+        s_cc[(NCC + 3) * 128 + q4 * 32 + lane] = cbd.ztailR;
+      }
+      beta0 = a.cc[(long long)(KK * 5 + 4) * a.C + chain];
+      gamma0 = a.cc[(long long)(KK * 5 + 5) * a.C + chain];
+      if (GRAD) {
+        float* gvp = s_gv + (warp * NGV) * 32 + lane;
+        for (int s = 0; s < NGV; ++s) gvp[s * 32] = 0.f;
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    if (is_stager) {
+      // ---- design tile: clear what the previous tile wrote, write this tile's four entries
+      //      per (term, observation), hi and lo halves
+      for (int s = 0; s < ntiles; ++s, ++tg) {
+        if (tg > 0) tc_wait(barE, (tg - 1) & 1);  // the MMAs that read the tile have completed
+        const long long base = o_begin + (long long)s * NT;
+        int ti = 0;
+        for (int t = sidx; t < T; t += NSW, ++ti) {
+          const float* kn = s_kn + t * 4 * kKnotStride;
+          const float* xt = a.X + (long long)t * a.n;
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const int o = p * 32 + lane;
+            if (o >= NT) continue;
+            unsigned char* rowp = s_B + (o >> 3) * sbo + (o & 7) * 16;
+            const int pk = prev_k[ti][p];
+            if (pk >= 0) {
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                const int k = pk + m;
+                float* e = reinterpret_cast<float*>(rowp + (k >> 2) * 128 + (k & 3) * 4);
+                e[0] = 0.f;
+                *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(e) + bbytes) = 0.f;
+              }
+            }
+            const long long gi = base + o;
+            int nk = -1;
+            if (gi < o_end) {
+              float bb[4];
+              const int jj = basis_window_fast(xt[gi], kn, kn + kKnotStride, kn + 2 * kKnotStride, kn + 3 * kKnotStride,
+                                               a.nb[t], a.inv_dk[t], bb);
+              nk = g.kcol[t] + jj;
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                const int k = nk + m;
+                const float vh = tf32_round(bb[m]);
+                float* e = reinterpret_cast<float*>(rowp + (k >> 2) * 128 + (k & 3) * 4);
+                e[0] = vh;
+                *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(e) + bbytes) = bb[m] - vh;
+              }
+            }
+            prev_k[ti][p] = nk;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mtc_arrive(barB);
+      }
+    } else if (is_mma) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | (8u << 24);
+      for (int s = 0; s < ntiles; ++s, ++tg) {
+        if (lane == 0) {
+          tc_wait(barB, tg & 1);                      // design tile written
+          if (tg > 0) tc_wait(barC, (tg - 1) & 1);    // eval warps have read the previous eta
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t d = tmem + etaCol + (uint32_t)(q * NT);
+            const int nks = g.Kq[q] >> 3;
+            for (int ks = 0; ks < nks; ++ks) {
+              const int k0 = g.kbase[q] + ks * 8;
+              const uint32_t a_hi = tmem + (uint32_t)k0, a_lo = a_hi + (uint32_t)Kt;
+              const uint32_t baddr = smem_u32(s_B) + (uint32_t)((k0 >> 2) * 128);
+              const uint64_t b_hi = mtc_desc(baddr, sbo), b_lo = mtc_desc(baddr + (uint32_t)bbytes, sbo);
+              mtc_mma_ts(d, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+              mtc_mma_ts(d, a_hi, b_lo, idesc, 1u);
+              mtc_mma_ts(d, a_lo, b_hi, idesc, 1u);
+            }
+          }
+          mtc_commit(barE);
+        }
+        __syncwarp();
+      }
+    } else if (is_eval) {
+      // =========================== eval warp ==========================================
+      float* gvp = s_gv + (warp * NGV) * 32 + lane;
+      const float* ccl = s_cc + q4 * 32 + lane;
+      double a_z2 = 0, a_ls = 0, a_gb0 = 0, a_gg0 = 0, a_gvl = 0, a_gdl = 0, a_gvr = 0, a_gdr = 0;
+      double a_logd = 0;
+      const float sixth = 1.f / 6.f;
+      const bool hasq0 = g.Kq[0] > 0, hasq1 = g.Kq[1] > 0;
+      float* Gp = g.G + (long long)cb * 128 + q4 * 32 + lane;
+      for (int s = 0; s < ntiles; ++s, ++tg) {
+        const long long base = o_begin + (long long)s * NT + sub * OPW;
+        tc_wait(barE, tg & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t em_u[OPW], es_u[OPW];
+        const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + etaCol + (uint32_t)(sub * OPW);
+#pragma unroll
+        for (int c = 0; c < OPW; c += 4) {
+          uint32_t v[4], w[4];
+          mtc_ld4(addr + c, v);
+          mtc_ld4(addr + NT + c, w);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { em_u[c + j] = v[j]; es_u[c + j] = w[j]; }
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mtc_arrive(barC);
+        float t_z2 = 0.f, t_ls = 0.f, t_gb0 = 0.f, t_gg0 = 0.f, t_pm = 1.f;
+        int t_pe = 0;
+#pragma unroll
+        for (int i = 0; i < OPW; ++i) {
+          const long long gi = base + i;
+          if (gi < o_end) {
+            const float yv = a.y[gi];
+            const float em = beta0 + (hasq0 ? __uint_as_float(em_u[i]) : 0.f);
+            const float es = gamma0 + (hasq1 ? __uint_as_float(es_u[i]) : 0.f);
+            const float einv = fast_exp(-es);
+            const float r = (yv - em) * einv;
+            const int code = region_code(ts, r);
+            const bool core = code == 2;
+            const float rc = r < ts.a ? ts.a : (r > ts.b ? ts.b : (r == r ? r : ts.a));
+            CoreEval<float> ev;
+            core_locate_fast(ts, a.grid, rc, ev);
+            const float* cp = ccl + (ev.kk * 5) * 128;
+            core_eval(ts, cp[0], cp[128], cp[256], cp[384], cp[512], ev);
+            float z = ev.z, d = ev.d, dzdr = ev.d, dddr = ev.d2;
+            float cfac = 0.f, qfac = 0.f;
+            if (!core) {
+              if (code == 1) {
+                const float dL = ccl[(KK * 5 + 1) * 128], constL = ccl[(NCC + 0) * 128];
+                const float poly = r * ts.a - 0.5f * r * r;
+                const float t1 = r - poly * ts.inv_w;
+                z = (ts.inv_w * poly + dL * t1) + constL;
+                const float q = (ts.a - r) * ts.inv_w;
+                d = (1.f - q) * dL + q;
+                dzdr = d; dddr = (dL - 1.f) * ts.inv_w;
+                const float poly0 = ts.a * ts.a - 0.5f * ts.a * ts.a;
+                cfac = t1 - (ts.a - poly0 * ts.inv_w);
+                qfac = 1.f - q;
+              } else if (code == 3) {
+                const float dR = ccl[(KK * 5 + 3) * 128], constR = ccl[(NCC + 1) * 128];
+                const float poly = 0.5f * r * r - r * ts.b;
+                const float t1 = r - poly * ts.inv_w;
+                z = (ts.inv_w * poly + dR * t1) + constR;
+                const float q = (r - ts.b) * ts.inv_w;
+                d = (1.f - q) * dR + q;
+                dzdr = d; dddr = (1.f - dR) * ts.inv_w;
+                const float poly0 = 0.5f * ts.b * ts.b - ts.b * ts.b;
+                cfac = t1 - (ts.b - poly0 * ts.inv_w);
+                qfac = 1.f - q;
+              } else if (code == 0) {
+                z = ccl[(NCC + 2) * 128] - (ts.min_eps - r);
+                d = 1.f; dzdr = 1.f; dddr = 0.f;
+                cfac = cL_of(ts, ts.min_eps);
+              } else {
+                z = ccl[(NCC + 3) * 128] + (r - ts.max_eps);
+                d = 1.f; dzdr = 1.f; dddr = 0.f;
+                cfac = cR_of(ts, ts.max_eps);
+              }
+            }
+            const float tiny = tiny_of<float>();
+            const bool above = d > tiny;
+            const float dcl = above ? d : tiny;
+            t_z2 = fmaf(z, z, t_z2);
+            t_ls += es;
+            {
+              float mant; int ex;
+              split_mant(dcl, mant, ex);
+              t_pm *= mant;
+              t_pe += ex;
+            }
+            if (!GRAD) {  // intercept statistics ride along with the logp-only sweep
+              a_gb0 += (double)einv;
+              a_gg0 += (double)r;
+              a_gvl += (double)(r * r);
+              a_gdl += (double)(einv * einv);
+              a_gvr += (double)(r * einv);
+            } else {
+              const float lz = -z;
+              const float ld = above ? fast_rcp(dcl) : 0.f;
+              const float gr = fmaf(lz, dzdr, ld * dddr);
+              const float gmu = -gr * einv;
+              const float gls = fmaf(-gr, r, -1.f);
+              float* gp2 = Gp + (gi - a.obs_begin) * 2 * g.Cpad;
+              gp2[0] = gmu;
+              gp2[g.Cpad] = gls;
+              t_gb0 += gmu;
+              t_gg0 += gls;
+              float w[5];
+              core_backward(ts, ev, core ? lz : 0.f, core ? ld : 0.f, w);
+              const bool lastp = ev.kk + 1 >= KK;
+              const float w4 = lastp ? 0.f : w[4];
+              const float g3 = w[3] - w4;
+              float* gp = gvp + ev.kk * 32;
+              gp[0] += (w[0] - g3) * sixth + (w[2] - w[1]) * 0.5f;
+              gp[32] += (4.f * w[0] - w4) * sixth - w[2] + g3 * 0.5f;
+              gp[64] += w[0] * sixth + (w[1] + w[2] - g3 + w4) * 0.5f;
+              gp[96] += g3 * sixth - w4 * 0.5f;
+              gp[128] += w4 * sixth;
+              if (!core) {
+                const double dv = (double)fmaf(lz, cfac, ld * qfac);
+                if (code <= 1) { a_gvl += (double)lz; a_gdl += dv; }
+                else { a_gvr += (double)lz; a_gdr += dv; }
+              }
+            }
+          }
+        }
+        // per-tile float sums -> double (a tile is at most 16 observations per warp)
+        a_z2 += (double)t_z2;
+        a_ls += (double)t_ls;
+        if (GRAD) { a_gb0 += (double)t_gb0; a_gg0 += (double)t_gg0; }
+        a_logd += (double)logf(t_pm) + (double)t_pe * 0.69314718055994530942;
+      }
+      double* rp = s_red + (warp * kRegSlots) * 32 + lane;
+      rp[SL_Z2 * 32] = a_z2;
+      rp[SL_LS * 32] = a_ls;
+      rp[SL_LOGD * 32] = a_logd;
+      rp[SL_GB0 * 32] = a_gb0;
+      rp[SL_GG0 * 32] = a_gg0;
+      rp[SL_GVL * 32] = a_gvl;
+      rp[SL_GDL * 32] = a_gdl;
+      rp[SL_GVR * 32] = a_gvr;
+      rp[SL_GDR * 32] = a_gdr;
+      named_bar(1, kMtcEvalWarps * 32);
+      // sum over the four eval warps of a chain quarter -> this (chain group, chunk)'s partial
+      if (cg < a.CG) {
+        double* pout = a.partial + ((long long)(cg * a.M + mchunk) * a.NSLOT) * 32;
+        const int nreg = GRAD ? kRegSlots : kLogpSlots;
+        for (int idx = sub * 32 + lane; idx < nreg * 32; idx += 128) {
+          double v = 0.0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) v += s_red[((w * 4 + q4) * kRegSlots) * 32 + idx];
+          pout[idx] = v;
+        }
+        if (GRAD)
+          for (int idx = sub * 32 + lane; idx < NGV * 32; idx += 128) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) v += (double)s_gv[((w * 4 + q4) * NGV) * 32 + idx];
+            pout[kRegSlots * 32 + idx] = v;
+          }
+      }
+      named_bar(1, kMtcEvalWarps * 32);
+    } else {
+      tg += (uint32_t)ntiles;  // idle warps keep the tile count in step
+    }
+    // every warp leaves the item with the same tile count
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+// ---------------------------------------------------------------------------------------
+// backward: dGamma[chain, k] += sum_obs G_q[chain, obs] B[obs, k]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(768, 1) k_grad_tc(const MainTcArgs g) {
+  const MainArgs<float>& a = g.a;
+  extern __shared__ __align__(128) unsigned char smem_gtc[];
+  __shared__ __align__(8) uint64_t s_bar[6];  // [0,1] A tile written, [2,3] B tile written, [4,5] MMAs done
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = a.T, NSW = g.NSW;
+  const int Ntot = g.Nq[0] + g.Nq[1];
+  const int halfb = Ntot * kGtcKT * 4;   // bytes of one half (hi or lo) of a B buffer, both predictor blocks
+  const int bufb = 2 * halfb;
+  unsigned char* s_B = smem_gtc;                                   // [2 buffers][hi, lo][Ntot x 32]
+  float* s_kn = reinterpret_cast<float*>(s_B + 2 * bufb);          // [T][4][kKnotStride]
+  constexpr int sboB = (kGtcKT / 4) * 128;
+
+  const bool is_load = warp < kMtcEvalWarps;
+  const int sidx = warp - kMtcEvalWarps;
+  const bool is_stager = sidx >= 0 && sidx < NSW;
+  const bool is_mma = sidx == NSW;
+  const int q4 = warp & 3, sub = (warp >> 2) & 3;
+
+  for (int t = warp; t < T; t += blockDim.x >> 5) {
+    float* kn = s_kn + t * 4 * kKnotStride;
+    const float* gk = a.knots + t * kKnotStride;
+    const int nbt = a.nb[t];
+    for (int i = lane; i < nbt + 4; i += 32) {
+      kn[i] = gk[i];
+      kn[kKnotStride + i] = i + 1 < nbt + 4 ? 1.f / (gk[i + 1] - gk[i]) : 0.f;
+      kn[2 * kKnotStride + i] = i + 2 < nbt + 4 ? 1.f / (gk[i + 2] - gk[i]) : 0.f;
+      kn[3 * kKnotStride + i] = i + 3 < nbt + 4 ? 1.f / (gk[i + 3] - gk[i]) : 0.f;
+    }
+  }
+  for (int i = tid; i < (2 * bufb) >> 4; i += blockDim.x) reinterpret_cast<float4*>(s_B)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[0 + b])), "r"(kMtcEvalWarps));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[2 + b])), "r"(NSW));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[4 + b])));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  const uint32_t barA = smem_u32(&s_bar[0]), barBf = smem_u32(&s_bar[2]), barM = smem_u32(&s_bar[4]);
+  const uint32_t colA = 256;  // A tiles: [256 + b * 128 + q * 64 + {0: hi, 32: lo}], D in [0, Ntot)
+  uint32_t tg = 0;            // K tiles this CTA has gone through (buffer = tg & 1, use count = tg >> 1)
+
+  int prev_r[4][2];           // stager: D row each (owned term, buffer) wrote last for this lane's observation
+#pragma unroll
+  for (int i = 0; i < 4; ++i) prev_r[i][0] = prev_r[i][1] = -1;
+
+  for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const int cb = item / a.M, mchunk = item - cb * a.M;
+    const long long o_begin = a.obs_begin + (long long)mchunk * a.chunk_len;
+    long long o_end = o_begin + a.chunk_len;
+    if (o_end > a.obs_end) o_end = a.obs_end;
+    const long long len = o_end > o_begin ? o_end - o_begin : 0;
+    const int ntiles = (int)((len + kGtcKT - 1) / kGtcKT);
+    const int cg = cb * 4 + q4;
+
+    auto flush_acc = [&](bool first) {
+      // loader warps: TMEM accumulators -> double partials of k_post
+      if (cg < a.CG) {
+        double* pout = a.partial + ((long long)(cg * a.M + mchunk) * a.NSLOT) * 32 + lane;
+        for (int c0 = sub * 8; c0 < Ntot; c0 += 32) {
+          uint32_t v[8];
+          const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(addr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int slot = g.dslot[c0 + j];
+            if (slot >= 0) {
+              double* pp = pout + (long long)slot * 32;
+              const double x = (double)__uint_as_float(v[j]);
+              *pp = first ? x : *pp + x;
+            }
+          }
+        }
+      }
+    };
+
+    if (is_load) {
+      const float* Gp = g.G + (long long)cb * 128 + q4 * 32 + lane;
+      int since = 0;
+      bool first = true;
+      for (int s = 0; s < ntiles; ++s, ++tg) {
+        const int b = tg & 1;
+        const uint32_t use = tg >> 1;
+        if (use > 0) tc_wait(barM + 8 * b, (use - 1) & 1);  // the MMAs that read A buffer b have completed
+        const long long base = o_begin + (long long)s * kGtcKT + sub * 8;
+        uint32_t hi[2][8], lo[2][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const long long gi = base + j;
+          float v0 = 0.f, v1 = 0.f;
+          if (gi < o_end) {
+            const float* p = Gp + (gi - a.obs_begin) * 2 * g.Cpad;
+            v0 = p[0];
+            v1 = p[g.Cpad];
+          }
+          const float h0 = tf32_round(v0), h1 = tf32_round(v1);
+          hi[0][j] = __float_as_uint(h0); lo[0][j] = __float_as_uint(v0 - h0);
+          hi[1][j] = __float_as_uint(h1); lo[1][j] = __float_as_uint(v1 - h1);
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + colA + (uint32_t)(b * 128 + sub * 8);
+        mtc_st8(addr, hi[0]);
+        mtc_st8(addr + 32, lo[0]);
+        mtc_st8(addr + 64, hi[1]);
+        mtc_st8(addr + 96, lo[1]);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mtc_arrive(barA + 8 * b);
+        ++since;
+        if (since == g.flush || s == ntiles - 1) {
+          // every MMA issued so far: wait for the commit of THIS tile
+          tc_wait(barM + 8 * b, use & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          flush_acc(first);
+          // (the next tile's MMAs overwrite D only after ALL loader warps have arrived on its
+          //  A-tile barrier, i.e. after every warp has finished these reads: no extra barrier)
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          since = 0;
+          first = false;
+        }
+      }
+      if (ntiles == 0 && cg < a.CG) {
+        double* pout = a.partial + ((long long)(cg * a.M + mchunk) * a.NSLOT) * 32 + lane;
+        for (int c0 = sub; c0 < Ntot; c0 += 4) {
+          const int slot = g.dslot[c0];
+          if (slot >= 0) pout[(long long)slot * 32] = 0.0;
+        }
+      }
+    } else if (is_stager) {
+      for (int s = 0; s < ntiles; ++s, ++tg) {
+        const int b = tg & 1;
+        const uint32_t use = tg >> 1;
+        if (use > 0) tc_wait(barM + 8 * b, (use - 1) & 1);
+        const long long gi = o_begin + (long long)s * kGtcKT + lane;  // lane = observation of the K tile
+        unsigned char* colp = s_B + b * bufb + (lane >> 2) * 128 + (lane & 3) * 4;
+        int ti = 0;
+        for (int t = sidx; t < T; t += NSW, ++ti) {
+          const float* kn = s_kn + t * 4 * kKnotStride;
+          const int pr = prev_r[ti][b];
+          if (pr >= 0) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int r = pr + m;
+              unsigned char* e = colp + (r >> 3) * sboB + (r & 7) * 16;
+              *reinterpret_cast<float*>(e) = 0.f;
+              *reinterpret_cast<float*>(e + halfb) = 0.f;
+            }
+          }
+          int nr = -1;
+          if (gi < o_end) {
+            float bb[4];
+            const int jj = basis_window_fast(a.X[(long long)t * a.n + gi], kn, kn + kKnotStride, kn + 2 * kKnotStride,
+                                             kn + 3 * kKnotStride, a.nb[t], a.inv_dk[t], bb);
+            nr = g.ncol[t] + jj;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int r = nr + m;
+              const float vh = tf32_round(bb[m]);
+              unsigned char* e = colp + (r >> 3) * sboB + (r & 7) * 16;
+              *reinterpret_cast<float*>(e) = vh;
+              *reinterpret_cast<float*>(e + halfb) = bb[m] - vh;
+            }
+          }
+          prev_r[ti][b] = nr;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mtc_arrive(barBf + 8 * b);
+      }
+    } else if (is_mma) {
+      int since = 0;
+      for (int s = 0; s < ntiles; ++s, ++tg) {
+        const int b = tg & 1;
+        const uint32_t use = tg >> 1;
+        if (lane == 0) {
+          tc_wait(barA + 8 * b, use & 1);
+          tc_wait(barBf + 8 * b, use & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (g.Nq[q] == 0) continue;
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.Nq[q] >> 3) << 17) | (8u << 24);
+            const uint32_t d = tmem + (uint32_t)g.nbase[q];
+            const uint32_t a0 = tmem + colA + (uint32_t)(b * 128 + q * 64);
+            const uint32_t bq = smem_u32(s_B) + (uint32_t)(b * bufb + (g.nbase[q] >> 3) * sboB);
+#pragma unroll
+            for (int ks = 0; ks < kGtcKT / 8; ++ks) {
+              const uint64_t b_hi = mtc_desc(bq + ks * 256, sboB), b_lo = mtc_desc(bq + halfb + ks * 256, sboB);
+              mtc_mma_ts(d, a0 + ks * 8, b_hi, idesc, (since > 0 || ks > 0) ? 1u : 0u);
+              mtc_mma_ts(d, a0 + ks * 8, b_lo, idesc, 1u);
+              mtc_mma_ts(d, a0 + 32 + ks * 8, b_hi, idesc, 1u);
+            }
+          }
+          mtc_commit(barM + 8 * b);
+        }
+        __syncwarp();
+        ++since;
+        if (since == g.flush) since = 0;
+      }
+    } else {
+      tg += (uint32_t)ntiles;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+}  // namespace ptm

@@ -378,6 +378,10 @@ class LocScalePTM:
         """Measurement hook: record CUDA events around the three kernels of each call."""
         _lib.check(self._lib.ptm_profile_enable(int(on)))
 
+    def last_main_route(self) -> str:
+        """Route of the last logp / logp+grad sweep: "cuda-core" (k_main) or "tcgen05"."""
+        return ["cuda-core", "tcgen05"][int(self._lib.ptm_last_main_route())]
+
     def last_xtwx_route(self) -> str:
         """Route of the last information sweep: "banded" (CUDA cores), "tcgen05-w" (tensor-core
         contraction, weights on CUDA cores) or "tcgen05" (scale predictor on the tensor cores too)."""
