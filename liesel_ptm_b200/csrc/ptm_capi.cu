@@ -396,13 +396,18 @@ Plan make_plan(const PtmProblem* pr, long long C) {
     for (int q = 0; q < 2; ++q) { K8[q] = (K8[q] + 7) & ~7; K16[q] = (K16[q] + 15) & ~15; }
     const int Kt = K8[0] + K8[1];
     const int avail = (512 - 2 * Kt) / 2;
-    const int NT = avail >= 64 ? 64 : (avail >= 48 ? 48 : (avail >= 32 ? 32 : 0));
+    int NT = avail >= 64 ? 64 : (avail >= 48 ? 48 : (avail >= 32 ? 32 : 0));
     const int NSW = std::min(T, 6);
+    auto fwd_smem = [&](int nt) {
+      return (size_t)2 * nt * Kt * 4 + (size_t)(NCC + 4) * 128 * 4 + (size_t)ptm::kMtcEvalWarps * NGV * 32 * 4 +
+             (size_t)T * 4 * ptm::kKnotStride * 4 + (size_t)ptm::kMtcEvalWarps * ptm::kRegSlots * 32 * 8 +
+             (size_t)ptm::kMtcEvalWarps * (2 * (nt / 4) * 32 + 32) * 4 + 128;
+    };
+    while (NT > 32 && fwd_smem(NT) > 227 * 1024 - 1280) NT -= 16;
     if (Kt <= ptm::kMtcMaxK && NT > 0 && K16[0] + K16[1] <= 256 && len > 0) {
-      pl.tc_smem_fwd = (size_t)2 * NT * Kt * 4 + (size_t)(NCC + 4) * 128 * 4 + (size_t)ptm::kMtcEvalWarps * NGV * 32 * 4 +
-                       (size_t)T * 4 * ptm::kKnotStride * 4 + (size_t)ptm::kMtcEvalWarps * ptm::kRegSlots * 32 * 8 + 128;
+      pl.tc_smem_fwd = fwd_smem(NT);
       pl.tc_smem_bwd = (size_t)2 * 2 * (K16[0] + K16[1]) * ptm::kGtcKT * 4 + (size_t)T * 4 * ptm::kKnotStride * 4 + 128;
-      if (pl.tc_smem_fwd <= 227 * 1024 - 64 && pl.tc_smem_bwd <= 227 * 1024 - 64) {
+      if (pl.tc_smem_fwd <= 227 * 1024 - 1280 && pl.tc_smem_bwd <= 227 * 1024 - 1280) {
         pl.tc = true;
         pl.tc_NT = NT; pl.tc_NSW = NSW;
         pl.tc_CB = (int)((C + 127) / 128);
@@ -550,7 +555,8 @@ int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gam
   if (!want_grad) g.a.NSLOT = ptm::kLogpSlots;
   g.G = G; g.CB = pl.tc_CB; g.Cpad = pl.tc_CB * 128; g.NT = pl.tc_NT; g.NSW = pl.tc_NSW;
   g.mode = want_grad ? ptm::kModeGrad : ptm::kModeLogp;
-  g.flush = pr->tune.tc_flush > 0 ? pr->tune.tc_flush : 32;
+  g.flush = pr->tune.tc_flush > 0 ? pr->tune.tc_flush : 64;
+  g.NSWb = std::min(pr->T, 11);
   const int NGV = pr->KK + 4;
   memset(g.kterm, 255, sizeof g.kterm);
   for (size_t i = 0; i < sizeof g.dslot / sizeof g.dslot[0]; ++i) g.dslot[i] = -1;
@@ -593,7 +599,8 @@ int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gam
   if (want_grad) {
     auto kern = ptm::k_grad_tc;
     PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_bwd));
-    kern<<<grid, threads, pl.tc_smem_bwd, st>>>(g);
+    const int threads_b = 32 * ((ptm::kMtcEvalWarps + g.NSWb + 1 + 3) / 4 * 4);
+    kern<<<grid, threads_b, pl.tc_smem_bwd, st>>>(g);
     PTM_CUDA(cudaGetLastError());
     ++g_launches;
   }

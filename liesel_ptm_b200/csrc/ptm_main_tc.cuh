@@ -46,7 +46,8 @@ struct MainTcArgs {
   int Kt;              // forward K extent (both predictor blocks, each padded to 8)
   int Kq[2], kbase[2]; // forward K extent / first column of the mu and sigma blocks
   int NT;              // observations per forward tile (48 or 64)
-  int NSW;             // stager warps
+  int NSW;             // stager warps of the forward kernel
+  int NSWb;            // stager warps of the backward kernel
   int kcol[kMaxTerms]; // first forward K column of each term
   unsigned char kterm[kMtcMaxK], kj[kMtcMaxK];  // forward K column -> (term, coefficient); 255 = padding
   // backward
@@ -84,6 +85,38 @@ __device__ __forceinline__ void mtc_ld4(uint32_t addr, uint32_t (&v)[4]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                : "r"(addr));
 }
+// Wait on an mbarrier phase with a back-off between polls: a spinning warp would take issue
+// slots from the eval warps of its scheduler (bounded like tc_wait: a protocol bug traps).
+__device__ __forceinline__ void mtc_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int it = 0; it < (1 << 22); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(2000u)
+        : "memory");
+    if (done) return;
+    __nanosleep(200);
+  }
+  __trap();
+}
+// exp / reciprocal / log of the float point-wise part: one MUFU each (ex2.approx, rcp.approx,
+// lg2.approx: <= 2 ulp; the float parity bar is 1e-5)
+__device__ __forceinline__ float mtc_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float mtc_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mtc_log(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * 0.69314718055994530942f;
+}
 __device__ __forceinline__ void named_bar(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -107,6 +140,7 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
   float* s_gv = s_cc + (NCC + 4) * 128;                                     // [16][NGV][32]
   float* s_kn = s_gv + (GRAD ? kMtcEvalWarps * NGV * 32 : 0);               // [T][4][kKnotStride]
   double* s_red = reinterpret_cast<double*>(s_kn + T * 4 * kKnotStride + ((T * 4 * kKnotStride) & 1));  // [16][kRegSlots][32]
+  float* s_eta = reinterpret_cast<float*>(s_red + kMtcEvalWarps * kRegSlots * 32);  // [16][2 OPW][32] eta + [OPW] y per eval warp
 
   const bool is_eval = warp < kMtcEvalWarps;
   const int sidx = warp - kMtcEvalWarps;
@@ -207,7 +241,7 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
       // ---- design tile: clear what the previous tile wrote, write this tile's four entries
       //      per (term, observation), hi and lo halves
       for (int s = 0; s < ntiles; ++s, ++tg) {
-        if (tg > 0) tc_wait(barE, (tg - 1) & 1);  // the MMAs that read the tile have completed
+        if (tg > 0) mtc_wait(barE, (tg - 1) & 1);  // the MMAs that read the tile have completed
         const long long base = o_begin + (long long)s * NT;
         int ti = 0;
         for (int t = sidx; t < T; t += NSW, ++ti) {
@@ -255,8 +289,8 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | (8u << 24);
       for (int s = 0; s < ntiles; ++s, ++tg) {
         if (lane == 0) {
-          tc_wait(barB, tg & 1);                      // design tile written
-          if (tg > 0) tc_wait(barC, (tg - 1) & 1);    // eval warps have read the previous eta
+          mtc_wait(barB, tg & 1);                      // design tile written
+          if (tg > 0) mtc_wait(barC, (tg - 1) & 1);    // eval warps have read the previous eta
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
@@ -287,32 +321,39 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
       float* Gp = g.G + (long long)cb * 128 + q4 * 32 + lane;
       for (int s = 0; s < ntiles; ++s, ++tg) {
         const long long base = o_begin + (long long)s * NT + sub * OPW;
-        tc_wait(barE, tg & 1);
+        // this warp's responses of the tile: one coalesced load, in flight while eta is waited for
+        float yreg = 0.f;
+        if (lane < OPW && base + lane < o_end) yreg = a.y[base + lane];
+        mtc_wait(barE, tg & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t em_u[OPW], es_u[OPW];
         const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + etaCol + (uint32_t)(sub * OPW);
+        float* eb = s_eta + warp * (2 * OPW * 32 + 32);
 #pragma unroll
         for (int c = 0; c < OPW; c += 4) {
           uint32_t v[4], w[4];
           mtc_ld4(addr + c, v);
           mtc_ld4(addr + NT + c, w);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { em_u[c + j] = v[j]; es_u[c + j] = w[j]; }
+          for (int j = 0; j < 4; ++j) {
+            eb[(c + j) * 32 + lane] = __uint_as_float(v[j]);
+            eb[(OPW + c + j) * 32 + lane] = __uint_as_float(w[j]);
+          }
         }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (lane < OPW) eb[2 * OPW * 32 + lane] = yreg;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mtc_arrive(barC);
-        float t_z2 = 0.f, t_ls = 0.f, t_gb0 = 0.f, t_gg0 = 0.f, t_pm = 1.f;
-        int t_pe = 0;
-#pragma unroll
-        for (int i = 0; i < OPW; ++i) {
+        float t_z2 = 0.f, t_ls = 0.f, t_gb0 = 0.f, t_gg0 = 0.f, t_ld = 0.f;
+        const int cnt = (int)((o_end - base) < OPW ? (o_end - base) : OPW);
+#pragma unroll 2
+        for (int i = 0; i < cnt; ++i) {
           const long long gi = base + i;
-          if (gi < o_end) {
-            const float yv = a.y[gi];
-            const float em = beta0 + (hasq0 ? __uint_as_float(em_u[i]) : 0.f);
-            const float es = gamma0 + (hasq1 ? __uint_as_float(es_u[i]) : 0.f);
-            const float einv = fast_exp(-es);
+          {
+            const float yv = eb[2 * OPW * 32 + i];
+            const float em = beta0 + (hasq0 ? eb[i * 32 + lane] : 0.f);
+            const float es = gamma0 + (hasq1 ? eb[(OPW + i) * 32 + lane] : 0.f);
+            const float einv = mtc_exp(-es);
             const float r = (yv - em) * einv;
             const int code = region_code(ts, r);
             const bool core = code == 2;
@@ -361,12 +402,7 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
             const float dcl = above ? d : tiny;
             t_z2 = fmaf(z, z, t_z2);
             t_ls += es;
-            {
-              float mant; int ex;
-              split_mant(dcl, mant, ex);
-              t_pm *= mant;
-              t_pe += ex;
-            }
+            t_ld += mtc_log(dcl);
             if (!GRAD) {  // intercept statistics ride along with the logp-only sweep
               a_gb0 += (double)einv;
               a_gg0 += (double)r;
@@ -375,7 +411,7 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
               a_gvr += (double)(r * einv);
             } else {
               const float lz = -z;
-              const float ld = above ? fast_rcp(dcl) : 0.f;
+              const float ld = above ? mtc_rcp(dcl) : 0.f;
               const float gr = fmaf(lz, dzdr, ld * dddr);
               const float gmu = -gr * einv;
               const float gls = fmaf(-gr, r, -1.f);
@@ -407,7 +443,7 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
         a_z2 += (double)t_z2;
         a_ls += (double)t_ls;
         if (GRAD) { a_gb0 += (double)t_gb0; a_gg0 += (double)t_gg0; }
-        a_logd += (double)logf(t_pm) + (double)t_pe * 0.69314718055994530942;
+        a_logd += (double)t_ld;
       }
       double* rp = s_red + (warp * kRegSlots) * 32 + lane;
       rp[SL_Z2 * 32] = a_z2;
@@ -455,13 +491,13 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
 // ---------------------------------------------------------------------------------------
 // backward: dGamma[chain, k] += sum_obs G_q[chain, obs] B[obs, k]
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(768, 1) k_grad_tc(const MainTcArgs g) {
+__global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
   const MainArgs<float>& a = g.a;
   extern __shared__ __align__(128) unsigned char smem_gtc[];
   __shared__ __align__(8) uint64_t s_bar[6];  // [0,1] A tile written, [2,3] B tile written, [4,5] MMAs done
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int T = a.T, NSW = g.NSW;
+  const int T = a.T, NSW = g.NSWb;
   const int Ntot = g.Nq[0] + g.Nq[1];
   const int halfb = Ntot * kGtcKT * 4;   // bytes of one half (hi or lo) of a B buffer, both predictor blocks
   const int bufb = 2 * halfb;
@@ -549,25 +585,35 @@ __global__ void __launch_bounds__(768, 1) k_grad_tc(const MainTcArgs g) {
       const float* Gp = g.G + (long long)cb * 128 + q4 * 32 + lane;
       int since = 0;
       bool first = true;
-      for (int s = 0; s < ntiles; ++s, ++tg) {
-        const int b = tg & 1;
-        const uint32_t use = tg >> 1;
-        if (use > 0) tc_wait(barM + 8 * b, (use - 1) & 1);  // the MMAs that read A buffer b have completed
+      // this warp's 8 observations x 2 predictors of a K tile; the next tile's values are
+      // requested before the current ones are handed to the tensor cores
+      float v0[8], v1[8];
+      auto fetch = [&](int s) {
         const long long base = o_begin + (long long)s * kGtcKT + sub * 8;
-        uint32_t hi[2][8], lo[2][8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const long long gi = base + j;
-          float v0 = 0.f, v1 = 0.f;
+          v0[j] = 0.f; v1[j] = 0.f;
           if (gi < o_end) {
             const float* p = Gp + (gi - a.obs_begin) * 2 * g.Cpad;
-            v0 = p[0];
-            v1 = p[g.Cpad];
+            v0[j] = __ldcs(p);
+            v1[j] = __ldcs(p + g.Cpad);
           }
-          const float h0 = tf32_round(v0), h1 = tf32_round(v1);
-          hi[0][j] = __float_as_uint(h0); lo[0][j] = __float_as_uint(v0 - h0);
-          hi[1][j] = __float_as_uint(h1); lo[1][j] = __float_as_uint(v1 - h1);
         }
+      };
+      if (ntiles > 0) fetch(0);
+      for (int s = 0; s < ntiles; ++s, ++tg) {
+        const int b = tg & 1;
+        const uint32_t use = tg >> 1;
+        uint32_t hi[2][8], lo[2][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float h0 = tf32_round(v0[j]), h1 = tf32_round(v1[j]);
+          hi[0][j] = __float_as_uint(h0); lo[0][j] = __float_as_uint(v0[j] - h0);
+          hi[1][j] = __float_as_uint(h1); lo[1][j] = __float_as_uint(v1[j] - h1);
+        }
+        if (s + 1 < ntiles) fetch(s + 1);
+        if (use > 0) mtc_wait(barM + 8 * b, (use - 1) & 1);  // the MMAs that read A buffer b have completed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + colA + (uint32_t)(b * 128 + sub * 8);
         mtc_st8(addr, hi[0]);
@@ -581,7 +627,7 @@ __global__ void __launch_bounds__(768, 1) k_grad_tc(const MainTcArgs g) {
         ++since;
         if (since == g.flush || s == ntiles - 1) {
           // every MMA issued so far: wait for the commit of THIS tile
-          tc_wait(barM + 8 * b, use & 1);
+          mtc_wait(barM + 8 * b, use & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           flush_acc(first);
           // (the next tile's MMAs overwrite D only after ALL loader warps have arrived on its
@@ -599,14 +645,33 @@ __global__ void __launch_bounds__(768, 1) k_grad_tc(const MainTcArgs g) {
         }
       }
     } else if (is_stager) {
+      // covariate values of the next K tile are requested one tile ahead (lane = observation)
+      float xn[4] = {0.f, 0.f, 0.f, 0.f};
+      auto fetch_x = [&](int s) {
+        const long long gi = o_begin + (long long)s * kGtcKT + lane;
+        int ti = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = sidx + i * NSW;
+          if (t < T && gi < o_end) xn[ti] = a.X[(long long)t * a.n + gi];
+          ++ti;
+        }
+      };
+      if (ntiles > 0) fetch_x(0);
       for (int s = 0; s < ntiles; ++s, ++tg) {
         const int b = tg & 1;
         const uint32_t use = tg >> 1;
-        if (use > 0) tc_wait(barM + 8 * b, (use - 1) & 1);
+        float xc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xc[i] = xn[i];
+        if (s + 1 < ntiles) fetch_x(s + 1);
+        if (use > 0) mtc_wait(barM + 8 * b, (use - 1) & 1);
         const long long gi = o_begin + (long long)s * kGtcKT + lane;  // lane = observation of the K tile
         unsigned char* colp = s_B + b * bufb + (lane >> 2) * 128 + (lane & 3) * 4;
-        int ti = 0;
-        for (int t = sidx; t < T; t += NSW, ++ti) {
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti) {
+          const int t = sidx + ti * NSW;
+          if (t >= T) break;
           const float* kn = s_kn + t * 4 * kKnotStride;
           const int pr = prev_r[ti][b];
           if (pr >= 0) {
@@ -621,7 +686,7 @@ __global__ void __launch_bounds__(768, 1) k_grad_tc(const MainTcArgs g) {
           int nr = -1;
           if (gi < o_end) {
             float bb[4];
-            const int jj = basis_window_fast(a.X[(long long)t * a.n + gi], kn, kn + kKnotStride, kn + 2 * kKnotStride,
+            const int jj = basis_window_fast(xc[ti], kn, kn + kKnotStride, kn + 2 * kKnotStride,
                                              kn + 3 * kKnotStride, a.nb[t], a.inv_dk[t], bb);
             nr = g.ncol[t] + jj;
 #pragma unroll
@@ -645,8 +710,8 @@ __global__ void __launch_bounds__(768, 1) k_grad_tc(const MainTcArgs g) {
         const int b = tg & 1;
         const uint32_t use = tg >> 1;
         if (lane == 0) {
-          tc_wait(barA + 8 * b, use & 1);
-          tc_wait(barBf + 8 * b, use & 1);
+          mtc_wait(barA + 8 * b, use & 1);
+          mtc_wait(barBf + 8 * b, use & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
