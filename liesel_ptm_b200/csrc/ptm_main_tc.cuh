@@ -103,9 +103,15 @@ __device__ __forceinline__ void mtc_wait(uint32_t bar, uint32_t parity) {
 // exp / reciprocal / log of the float point-wise part: one MUFU each (ex2.approx, rcp.approx,
 // lg2.approx: <= 2 ulp; the float parity bar is 1e-5)
 __device__ __forceinline__ float mtc_exp(float x) {
+  // exp(x) = 2^t (1 + e ln 2): t = fl(x log2 e), e = the exactly recovered rounding error of
+  // that product plus the low word of log2 e -- the argument of the approximate ex2 is then
+  // exact to ~2^-31 instead of |x| 2^-24, which removes the systematic part of the error
+  const float t = x * 1.4426950216293335f;
+  float e = fmaf(x, 1.4426950216293335f, -t);
+  e = fmaf(x, 1.9259629911266175e-8f, e);
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
-  return y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t));
+  return fmaf(y, e * 0.69314718055994530942f, y);
 }
 __device__ __forceinline__ float mtc_rcp(float x) {
   float y;
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
           const float v = t != 255 ? a.Gamma[((long long)t * kMaxNbases + g.kj[k]) * a.C + chain] : 0.f;
           const float vh = tf32_round(v);
           hi[j] = __float_as_uint(vh);
-          lo[j] = __float_as_uint(v - vh);
+          lo[j] = __float_as_uint(tf32_round(v - vh));
         }
         const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0;
         mtc_st8(addr, hi);
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
                 const float vh = tf32_round(bb[m]);
                 float* e = reinterpret_cast<float*>(rowp + (k >> 2) * 128 + (k & 3) * 4);
                 e[0] = vh;
-                *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(e) + bbytes) = bb[m] - vh;
+                *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(e) + bbytes) = tf32_round(bb[m] - vh);
               }
             }
             prev_k[ti][p] = nk;
@@ -561,20 +567,35 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
       // loader warps: TMEM accumulators -> double partials of k_post
       if (cg < a.CG) {
         double* pout = a.partial + ((long long)(cg * a.M + mchunk) * a.NSLOT) * 32 + lane;
-        for (int c0 = sub * 8; c0 < Ntot; c0 += 32) {
-          uint32_t v[8];
-          const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0;
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                       : "r"(addr));
+        // this warp's columns sub * 8 + 32 i: up to four 8-column loads in flight per wait
+        for (int c0 = sub * 8; c0 < Ntot; c0 += 128) {
+          uint32_t v[4][8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            // (columns past Ntot belong to the A tiles: read and ignored, dslot = -1 there)
+            const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c0 + 32 * u);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]), "=r"(v[u][4]), "=r"(v[u][5]),
+                           "=r"(v[u][6]), "=r"(v[u][7])
+                         : "r"(addr));
+          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int slot = g.dslot[c0 + j];
-            if (slot >= 0) {
-              double* pp = pout + (long long)slot * 32;
-              const double x = (double)__uint_as_float(v[j]);
-              *pp = first ? x : *pp + x;
+          for (int u = 0; u < 4; ++u) {
+            {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int slot = g.dslot[c0 + 32 * u + j];
+                if (slot >= 0) {
+                  double* pp = pout + (long long)slot * 32;
+                  const double x = (double)__uint_as_float(v[u][j]);
+                  // single writer per address: a plain store first, then fire-and-forget
+                  // reductions (no load-add-store round trip; same-thread same-address order
+                  // is program order)
+                  if (first) *pp = x;
+                  else asm volatile("red.global.add.f64 [%0], %1;" ::"l"(pp), "d"(x) : "memory");
+                }
+              }
             }
           }
         }
@@ -609,8 +630,8 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float h0 = tf32_round(v0[j]), h1 = tf32_round(v1[j]);
-          hi[0][j] = __float_as_uint(h0); lo[0][j] = __float_as_uint(v0[j] - h0);
-          hi[1][j] = __float_as_uint(h1); lo[1][j] = __float_as_uint(v1[j] - h1);
+          hi[0][j] = __float_as_uint(h0); lo[0][j] = __float_as_uint(tf32_round(v0[j] - h0));
+          hi[1][j] = __float_as_uint(h1); lo[1][j] = __float_as_uint(tf32_round(v1[j] - h1));
         }
         if (s + 1 < ntiles) fetch(s + 1);
         if (use > 0) mtc_wait(barM + 8 * b, (use - 1) & 1);  // the MMAs that read A buffer b have completed
@@ -695,7 +716,7 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
               const float vh = tf32_round(bb[m]);
               unsigned char* e = colp + (r >> 3) * sboB + (r & 7) * 16;
               *reinterpret_cast<float*>(e) = vh;
-              *reinterpret_cast<float*>(e + halfb) = bb[m] - vh;
+              *reinterpret_cast<float*>(e + halfb) = tf32_round(bb[m] - vh);
             }
           }
           prev_r[ti][b] = nr;

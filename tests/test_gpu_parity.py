@@ -442,8 +442,10 @@ def test_xtwx_f32_tensor_core_clipped_and_nan_weights(monkeypatch):
     params[3, case.layout["gamma0"]] = np.nan
     P_tc, _ = case.model.precision(0, torch.from_numpy(params).cuda(), with_chol=False)
     assert case.model.last_xtwx_route().startswith("tcgen05")
-    monkeypatch.setenv("PTM_XTWX_TC", "0")
-    P_b, _ = case.model.precision(0, torch.from_numpy(params).cuda(), with_chol=False)
+    monkeypatch.setenv("PTM_XTWX_TC", "0")  # read at create: a second model for the banded route
+    banded = build_case(n=2500, n_loc=1, n_scale=1, nbases=12, nparam=20, C=5, dtype=np.float32).model
+    P_b, _ = banded.precision(0, torch.from_numpy(params).cuda(), with_chol=False)
+    assert banded.last_xtwx_route() == "banded"
     P_tc, P_b = P_tc.cpu().numpy(), P_b.cpu().numpy()
     assert np.isnan(P_tc[3]).all() and np.isnan(P_b[3]).all()
     assert np.isfinite(P_tc[[0, 1, 2, 4]]).all()
@@ -463,36 +465,42 @@ def test_xtwx_f32_tensor_core_and_banded_routes(n, C, monkeypatch):
     accumulators promoted to double) and the banded CUDA-core route against the f64 oracle
     on the f32-rounded inputs, rel 2e-5 (north star: 1e-5 f32; the weights 1/sigma^2 carry
     the f32 rounding of eta_sigma, |eta| * 6e-8 * 2)."""
-    case = build_case(n=n, n_loc=2, n_scale=2, nbases=12, nparam=20, C=C, dtype=np.float32)
+    # the tuning knobs are read ONCE, when the problem is created: one model per setting
+    shape = dict(n=n, n_loc=2, n_scale=2, nbases=12, nparam=20, C=C, dtype=np.float32)
+
+    def model_with(**env):
+        for k in ("PTM_XTWX_TC", "PTM_TC_FLUSH"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        return build_case(**shape)
+
+    case = model_with()
     om, st = _f64_oracle_of(case)
     params = torch.from_numpy(case.params).cuda()
     refs = [om.loc_precision(st, t) for t in range(2)]
-    monkeypatch.setenv("PTM_XTWX_TC", "2")  # scale predictor on the tensor cores as well
-    for flush in ("3", None):  # promote every 3 tiles / default cadence
-        if flush:
-            monkeypatch.setenv("PTM_TC_FLUSH", flush)
-        else:
-            monkeypatch.delenv("PTM_TC_FLUSH", raising=False)
-        Ps, Ls = case.model.precision_all(params)
-        assert case.model.last_xtwx_route() == "tcgen05"
+    for env in (dict(PTM_XTWX_TC="2", PTM_TC_FLUSH="3"), dict(PTM_XTWX_TC="2")):  # eta on the tensor cores too
+        m = model_with(**env).model
+        Ps, Ls = m.precision_all(params)
+        assert m.last_xtwx_route() == "tcgen05"
         for t in range(2):
             assert rel_err(Ps[t].cpu().numpy(), refs[t][1]) < 2e-5
             assert rel_err(Ls[t].cpu().numpy(), refs[t][2]) < 2e-4
-    x_tc = case.model.xtwx(0, params).cpu().numpy()
-    assert case.model.last_xtwx_route() == "tcgen05"
-    assert rel_err(x_tc, refs[0][0]) < 2e-5
-    monkeypatch.setenv("PTM_XTWX_TC", "1")  # weights on CUDA cores, contraction on tensor cores
-    x_tw = case.model.xtwx(0, params).cpu().numpy()
-    assert case.model.last_xtwx_route() == "tcgen05-w"
+        x_tc = m.xtwx(0, params).cpu().numpy()
+        assert m.last_xtwx_route() == "tcgen05"
+        assert rel_err(x_tc, refs[0][0]) < 2e-5
+    m = model_with(PTM_XTWX_TC="1").model  # weights on CUDA cores, contraction on tensor cores
+    x_tw = m.xtwx(0, params).cpu().numpy()
+    assert m.last_xtwx_route() == "tcgen05-w"
     assert rel_err(x_tw, refs[0][0]) < 2e-5
-    monkeypatch.setenv("PTM_XTWX_TC", "0")
-    x_b = case.model.xtwx(0, params).cpu().numpy()
-    assert case.model.last_xtwx_route() == "banded"
+    m = model_with(PTM_XTWX_TC="0").model
+    x_b = m.xtwx(0, params).cpu().numpy()
+    assert m.last_xtwx_route() == "banded"
     assert rel_err(x_b, refs[0][0]) < 2e-5
     # scale terms (W == 2) always take the banded route
-    monkeypatch.delenv("PTM_XTWX_TC")
-    P, _ = case.model.precision(2, params)
-    assert case.model.last_xtwx_route() == "banded"
+    m = model_with().model
+    P, _ = m.precision(2, params)
+    assert m.last_xtwx_route() == "banded"
     assert rel_err(P.cpu().numpy(), om.scale_precision(st, 2)[1]) < 2e-5
 
 

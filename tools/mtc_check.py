@@ -51,3 +51,30 @@ m2 = wl2.model.build()
 lp0, g0 = m2.log_prob_and_grad(p)
 print("c3 tc vs cuda-core: logp %.2e grad %.2e" % (rel_err(lp1.cpu().numpy(), lp0.cpu().numpy()),
       max(rel_err(g1[c].cpu().numpy(), g0[c].cpu().numpy()) for c in range(0, 1024, 37))))
+
+# accuracy at n = 1M against the float64 kernel on the float32-rounded inputs (64 chains)
+import liesel_ptm_b200 as lp_
+def against_f64(tag):
+    C = 64
+    w32 = bw.build("c3_n1M_5loc_5scale_nb20_1024chains", chains=C, dtype=np.float32)
+    m32 = w32.model.build()
+    m64 = lp_.LocScalePTM(w32.y.astype(np.float64), m32.knots.astype(np.float64), to_float32=False)
+    for t, k in w32.model.all_terms():
+        b = t.basis
+        tm = lp_.term.f_ig(lp_.Basis(x=b.x.astype(np.float64), xname=b.xname, knots=b.knots.astype(np.float64),
+                                      Z=b.Z.astype(np.float64), penalty=b.penalty.astype(np.float64), nbases=b.nbases),
+                           fname="f" if k == 0 else "g")
+        tm.penalty_rank = t.penalty_rank
+        if k == 0: m64.loc += tm
+        else: m64.scale += tm
+    m64.build()
+    p32 = torch.from_numpy(w32.params).cuda()
+    lp32, g32 = m32.log_prob_and_grad(p32); route = m32.last_main_route()
+    lp64, g64 = m64.log_prob_and_grad(p32.double())
+    e_lp = ((lp32.double() - lp64).abs() / lp64.abs()).max().item()
+    e_g = ((g32.double() - g64).abs().amax(dim=1) / g64.abs().amax(dim=1))
+    print(f"[{tag} {route}] n=1M vs f64 kernel: logp {e_lp:.2e}  grad max {e_g.max().item():.2e} median {e_g.median().item():.2e}")
+os.environ.pop("PTM_MAIN_TC", None)
+against_f64("tc")
+os.environ["PTM_MAIN_TC"] = "0"
+against_f64("cuda-core")
