@@ -84,6 +84,7 @@ struct PtmProblem {
     int tc_flush = 0;  // PTM_TC_FLUSH
     int main_tc = 1;   // PTM_MAIN_TC: 0 = CUDA-core sweep only, 1 = tensor-core sweep when the model fits
     int mtc_items = 0; // PTM_MTC_ITEMS: work items per CTA of the tensor-core sweep (0 = default)
+    int mtc_nsw = 0;   // PTM_MTC_NSW: stager warps of k_main_tc (0 = default)
   } tune;
   // shard views share the device arrays of the handle they were made from
   const PtmProblem* base = nullptr;
@@ -123,7 +124,11 @@ void fill_tc(const ptm::TrafoConst<double>& s, ptm::TrafoConst<R>& d) {
   d.KK = s.KK; d.a = (R)s.a; d.b = (R)s.b; d.inv_dk = (R)s.inv_dk; d.w = (R)s.w;
   d.inv_w = (R)s.inv_w; d.min_eps = (R)s.min_eps; d.max_eps = (R)s.max_eps;
   d.inv_h = (R)s.inv_h; d.kap_scale = (R)s.kap_scale; d.ratio = (R)s.ratio;
-  d.frac_eps = sizeof(R) == 8 ? (R)1e-6 : (R)2e-2;
+  // distance (in cells) from a grid point below which the exact table decides the cell: the
+  // multiply-and-floor estimate carries ~1e-13 (double) / ~1.2e-4 (float: rounding of r - a and of
+  // the product) of a cell, so 1e-6 / 1e-3 keep the cell index bit-exact with searchsorted while
+  // a warp of 32 chains takes the table path in ~6 % of the float rows (it was 73 % at 2e-2)
+  d.frac_eps = sizeof(R) == 8 ? (R)1e-6 : (R)1e-3;
   d.nparam = s.nparam; d.J = s.J; d.dk = (R)s.dk; d.log_dk = (R)s.log_dk; d.k1 = (R)s.k1;
   d.log_KK = (R)s.log_KK;
   for (int i = 0; i < ptm::kMaxJ; ++i) d.Bk[i] = (R)s.Bk[i];
@@ -186,6 +191,7 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
     pr->tune.tc_flush = env_int("PTM_TC_FLUSH", 0);
     pr->tune.main_tc = env_int("PTM_MAIN_TC", 1);
     pr->tune.mtc_items = env_int("PTM_MTC_ITEMS", 0);
+    pr->tune.mtc_nsw = env_int("PTM_MTC_NSW", 0);
   }
   if (pr->T_loc == pr->T_scale && pr->T_loc > 0 && !getenv("PTM_NO_SHARED")) {
     std::vector<int> loc, sc;
@@ -397,7 +403,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
     const int Kt = K8[0] + K8[1];
     const int avail = (512 - 2 * Kt) / 2;
     int NT = avail >= 64 ? 64 : (avail >= 48 ? 48 : (avail >= 32 ? 32 : 0));
-    const int NSW = std::min(T, 6);
+    const int NSW = std::min(T, pr->tune.mtc_nsw > 0 ? std::min(pr->tune.mtc_nsw, 7) : 6);
     auto fwd_smem = [&](int nt) {
       return (size_t)2 * nt * Kt * 4 + (size_t)(NCC + 4) * 128 * 4 + (size_t)ptm::kMtcEvalWarps * NGV * 32 * 4 +
              (size_t)T * 4 * ptm::kKnotStride * 4 + (size_t)ptm::kMtcEvalWarps * ptm::kRegSlots * 32 * 8 +
@@ -578,22 +584,25 @@ int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gam
   g.Kt = k;
   const int threads = 32 * ((ptm::kMtcEvalWarps + pl.tc_NSW + 1 + 3) / 4 * 4);
   const int grid = std::min(plc.n_items, pr->num_sms);
+#define PTM_MTC_LAUNCH2(NTV, GR, MT)                                                   \
+  do {                                                                                 \
+    auto kern = ptm::k_main_tc<NTV, GR, MT>;                                           \
+    PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_fwd));                                  \
+    kern<<<grid, threads, pl.tc_smem_fwd, st>>>(g);                                    \
+  } while (0)
 #define PTM_MTC_LAUNCH(NTV)                                                            \
   do {                                                                                 \
-    if (want_grad) {                                                                   \
-      auto kern = ptm::k_main_tc<NTV, true>;                                           \
-      PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_fwd));                                \
-      kern<<<grid, threads, pl.tc_smem_fwd, st>>>(g);                                  \
+    if (threads <= 640) {                                                              \
+      if (want_grad) PTM_MTC_LAUNCH2(NTV, true, 640); else PTM_MTC_LAUNCH2(NTV, false, 640); \
     } else {                                                                           \
-      auto kern = ptm::k_main_tc<NTV, false>;                                          \
-      PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_fwd));                                \
-      kern<<<grid, threads, pl.tc_smem_fwd, st>>>(g);                                  \
+      if (want_grad) PTM_MTC_LAUNCH2(NTV, true, 768); else PTM_MTC_LAUNCH2(NTV, false, 768); \
     }                                                                                  \
   } while (0)
   if (pl.tc_NT == 64) PTM_MTC_LAUNCH(64);
   else if (pl.tc_NT == 48) PTM_MTC_LAUNCH(48);
   else PTM_MTC_LAUNCH(32);
 #undef PTM_MTC_LAUNCH
+#undef PTM_MTC_LAUNCH2
   PTM_CUDA(cudaGetLastError());
   ++g_launches;
   if (want_grad) {

@@ -130,8 +130,8 @@ __device__ __forceinline__ void named_bar(int id, int threads) {
 // ---------------------------------------------------------------------------------------
 // forward + point-wise part
 // ---------------------------------------------------------------------------------------
-template <int NT, bool GRAD>
-__global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
+template <int NT, bool GRAD, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
   const MainArgs<float>& a = g.a;
   constexpr int OPW = NT / 4;  // observations per eval warp and tile
   extern __shared__ __align__(128) unsigned char smem_mtc[];
@@ -188,9 +188,9 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
   uint32_t tg = 0;  // tiles this CTA has gone through (phase parity of all three barriers)
 
   // stager state: K column each (owned term, pass) wrote last, -1 = nothing to clear
-  int prev_k[4][2];
+  int prev_k[8][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) prev_k[i][0] = prev_k[i][1] = -1;
+  for (int i = 0; i < 8; ++i) prev_k[i][0] = prev_k[i][1] = -1;
 
   for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int cb = item / a.M, mchunk = item - cb * a.M;
@@ -246,13 +246,35 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
     if (is_stager) {
       // ---- design tile: clear what the previous tile wrote, write this tile's four entries
       //      per (term, observation), hi and lo halves
+      // covariate values of the next tile are requested one tile ahead: the fill of the design
+      // tile sits on the serial chain MMA(s) -> fill(s+1) -> MMA(s+1) of the single-buffered tile
+      float xn[8][2];
+      auto fetch_x = [&](int s) {
+        const long long base = o_begin + (long long)s * NT;
+#pragma unroll
+        for (int ti = 0; ti < 8; ++ti) {
+          const int t = sidx + ti * NSW;
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const long long gi = base + p * 32 + lane;
+            xn[ti][p] = 0.f;
+            if (t < T && p * 32 + lane < NT && gi < o_end) xn[ti][p] = a.X[(long long)t * a.n + gi];
+          }
+        }
+      };
+      if (ntiles > 0) fetch_x(0);
       for (int s = 0; s < ntiles; ++s, ++tg) {
+        float xc[8][2];
+#pragma unroll
+        for (int ti = 0; ti < 8; ++ti) { xc[ti][0] = xn[ti][0]; xc[ti][1] = xn[ti][1]; }
+        if (s + 1 < ntiles) fetch_x(s + 1);
         if (tg > 0) mtc_wait(barE, (tg - 1) & 1);  // the MMAs that read the tile have completed
         const long long base = o_begin + (long long)s * NT;
-        int ti = 0;
-        for (int t = sidx; t < T; t += NSW, ++ti) {
+#pragma unroll
+        for (int ti = 0; ti < 8; ++ti) {
+          const int t = sidx + ti * NSW;
+          if (t >= T) break;
           const float* kn = s_kn + t * 4 * kKnotStride;
-          const float* xt = a.X + (long long)t * a.n;
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
             const int o = p * 32 + lane;
@@ -272,7 +294,7 @@ __global__ void __launch_bounds__(768, 1) k_main_tc(const MainTcArgs g) {
             int nk = -1;
             if (gi < o_end) {
               float bb[4];
-              const int jj = basis_window_fast(xt[gi], kn, kn + kKnotStride, kn + 2 * kKnotStride, kn + 3 * kKnotStride,
+              const int jj = basis_window_fast(xc[ti][p], kn, kn + kKnotStride, kn + 2 * kKnotStride, kn + 3 * kKnotStride,
                                                a.nb[t], a.inv_dk[t], bb);
               nk = g.kcol[t] + jj;
 #pragma unroll
