@@ -412,7 +412,8 @@ Plan make_plan(const PtmProblem* pr, long long C) {
     while (NT > 32 && fwd_smem(NT) > 227 * 1024 - 1280) NT -= 16;
     if (Kt <= ptm::kMtcMaxK && NT > 0 && K16[0] + K16[1] <= 256 && len > 0) {
       pl.tc_smem_fwd = fwd_smem(NT);
-      pl.tc_smem_bwd = (size_t)2 * 2 * (K16[0] + K16[1]) * ptm::kGtcKT * 4 + (size_t)T * 4 * ptm::kKnotStride * 4 + 128;
+      pl.tc_smem_bwd = (size_t)2 * 2 * (K16[0] + K16[1]) * ptm::kGtcKT * 4 + (size_t)T * 4 * ptm::kKnotStride * 4 +
+                       (size_t)ptm::kGtcStages * ptm::kGtcTileBytes + 256;
       if (pl.tc_smem_fwd <= 227 * 1024 - 1280 && pl.tc_smem_bwd <= 227 * 1024 - 1280) {
         pl.tc = true;
         pl.tc_NT = NT; pl.tc_NSW = NSW;
@@ -425,7 +426,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
         Mt = std::max<long long>(1, (len + ch - 1) / ch);
         pl.tc_M = (int)Mt; pl.tc_chunk = ch;
         n_part_items = std::max<long long>(n_part_items, (long long)pl.CG * Mt);
-        g_bytes = (size_t)len * 2 * (size_t)pl.tc_CB * 128 * 4;
+        g_bytes = (size_t)(len + ptm::kGtcKT) * 2 * (size_t)pl.tc_CB * 128 * 4;  // one backward tile of padding per block
       }
     }
   }
@@ -559,6 +560,7 @@ int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gam
   fill_main_args<float>(pr, plc, C, Gamma, cc, partial, g.a);
   g.a.shared = 0;
   if (!want_grad) g.a.NSLOT = ptm::kLogpSlots;
+  g.Gld = std::max<long long>(pr->obs_end - pr->obs_begin, 0) + ptm::kGtcKT;
   g.G = G; g.CB = pl.tc_CB; g.Cpad = pl.tc_CB * 128; g.NT = pl.tc_NT; g.NSW = pl.tc_NSW;
   g.mode = want_grad ? ptm::kModeGrad : ptm::kModeLogp;
   g.flush = pr->tune.tc_flush > 0 ? pr->tune.tc_flush : 8;
@@ -608,7 +610,7 @@ int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gam
   if (want_grad) {
     auto kern = ptm::k_grad_tc;
     PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_bwd));
-    const int threads_b = 32 * ((ptm::kMtcEvalWarps + g.NSWb + 1 + 3) / 4 * 4);
+    const int threads_b = 32 * ((ptm::kMtcEvalWarps + g.NSWb + 2 + 3) / 4 * 4);  // loaders, stagers, MMA, copy
     kern<<<grid, threads_b, pl.tc_smem_bwd, st>>>(g);
     PTM_CUDA(cudaGetLastError());
     ++g_launches;

@@ -38,10 +38,13 @@ namespace ptm {
 constexpr int kMtcEvalWarps = 16;  // 4 chain quarters x 4 observation groups
 constexpr int kMtcMaxK = 224;
 constexpr int kGtcKT = 32;         // observations per backward K tile
+constexpr int kGtcStages = 3;      // G tiles in flight (bulk async copies into shared memory)
+constexpr int kGtcTileBytes = kGtcKT * 2 * 128 * 4;  // one G tile: [32 obs][2 predictors][128 chains] floats
 
 struct MainTcArgs {
   MainArgs<float> a;
-  float* G;            // [len][2][Cpad] dl/deta_mu, dl/deta_sigma (chain fastest)
+  float* G;            // [CB][Gld][2][128] dl/deta_mu, dl/deta_sigma of (chain block, observation), chain fastest
+  long long Gld;       // observations per chain block in G (shard length padded by one backward tile)
   int CB, Cpad;        // chain blocks of 128
   int Kt;              // forward K extent (both predictor blocks, each padded to 8)
   int Kq[2], kbase[2]; // forward K extent / first column of the mu and sigma blocks
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
       double a_logd = 0;
       const float sixth = 1.f / 6.f;
       const bool hasq0 = g.Kq[0] > 0, hasq1 = g.Kq[1] > 0;
-      float* Gp = g.G + (long long)cb * 128 + q4 * 32 + lane;
+      float* Gp = g.G + (long long)cb * g.Gld * 256 + q4 * 32 + lane;
       for (int s = 0; s < ntiles; ++s, ++tg) {
         const long long base = o_begin + (long long)s * NT + sub * OPW;
         // this warp's responses of the tile: one coalesced load, in flight while eta is waited for
@@ -443,9 +446,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
               const float gr = fmaf(lz, dzdr, ld * dddr);
               const float gmu = -gr * einv;
               const float gls = fmaf(-gr, r, -1.f);
-              float* gp2 = Gp + (gi - a.obs_begin) * 2 * g.Cpad;
+              float* gp2 = Gp + (gi - a.obs_begin) * 256;
               gp2[0] = gmu;
-              gp2[g.Cpad] = gls;
+              gp2[128] = gls;
               t_gb0 += gmu;
               t_gg0 += gls;
               float w[5];
@@ -523,6 +526,7 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
   const MainArgs<float>& a = g.a;
   extern __shared__ __align__(128) unsigned char smem_gtc[];
   __shared__ __align__(8) uint64_t s_bar[6];  // [0,1] A tile written, [2,3] B tile written, [4,5] MMAs done
+  __shared__ __align__(8) uint64_t s_gbar[2 * kGtcStages];  // [0..S) G tile landed (tx bytes), [S..2S) G tile read
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = a.T, NSW = g.NSWb;
@@ -531,12 +535,16 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
   const int bufb = 2 * halfb;
   unsigned char* s_B = smem_gtc;                                   // [2 buffers][hi, lo][Ntot x 32]
   float* s_kn = reinterpret_cast<float*>(s_B + 2 * bufb);          // [T][4][kKnotStride]
+  // ring of G tiles [32 obs][2][128 chains], filled by bulk async copies (one per K tile)
+  unsigned char* s_G = reinterpret_cast<unsigned char*>(s_kn + T * 4 * kKnotStride);
+  s_G += (128 - (smem_u32(s_G) & 127)) & 127;
   constexpr int sboB = (kGtcKT / 4) * 128;
 
   const bool is_load = warp < kMtcEvalWarps;
   const int sidx = warp - kMtcEvalWarps;
   const bool is_stager = sidx >= 0 && sidx < NSW;
   const bool is_mma = sidx == NSW;
+  const bool is_copy = sidx == NSW + 1;
   const int q4 = warp & 3, sub = (warp >> 2) & 3;
 
   for (int t = warp; t < T; t += blockDim.x >> 5) {
@@ -557,6 +565,10 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[2 + b])), "r"(NSW));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[4 + b])));
     }
+    for (int i = 0; i < kGtcStages; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_gbar[i])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_gbar[kGtcStages + i])), "r"(kMtcEvalWarps));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -569,6 +581,7 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
   const uint32_t barA = smem_u32(&s_bar[0]), barBf = smem_u32(&s_bar[2]), barM = smem_u32(&s_bar[4]);
+  const uint32_t barGf = smem_u32(&s_gbar[0]), barGe = smem_u32(&s_gbar[kGtcStages]);
   const uint32_t colA = 256;  // A tiles: [256 + b * 128 + q * 64 + {0: hi, 32: lo}], D in [0, Ntot)
   uint32_t tg = 0;            // K tiles this CTA has gone through (buffer = tg & 1, use count = tg >> 1)
 
@@ -625,37 +638,28 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
     };
 
     if (is_load) {
-      const float* Gp = g.G + (long long)cb * 128 + q4 * 32 + lane;
       int since = 0;
       bool first = true;
-      // this warp's 8 observations x 2 predictors of a K tile; the next tile's values are
-      // requested before the current ones are handed to the tensor cores
-      float v0[8], v1[8];
-      auto fetch = [&](int s) {
-        const long long base = o_begin + (long long)s * kGtcKT + sub * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const long long gi = base + j;
-          v0[j] = 0.f; v1[j] = 0.f;
-          if (gi < o_end) {
-            const float* p = Gp + (gi - a.obs_begin) * 2 * g.Cpad;
-            v0[j] = __ldcs(p);
-            v1[j] = __ldcs(p + g.Cpad);
-          }
-        }
-      };
-      if (ntiles > 0) fetch(0);
+      // this warp's 8 observations x 2 predictors of a K tile come out of the shared-memory ring
+      // the copy warp fills with one bulk async copy per tile (kGtcStages tiles in flight)
       for (int s = 0; s < ntiles; ++s, ++tg) {
         const int b = tg & 1;
         const uint32_t use = tg >> 1;
+        const uint32_t stg = tg % kGtcStages, sph = (tg / kGtcStages) & 1;
+        mtc_wait(barGf + 8 * stg, sph);
+        const float* gs = reinterpret_cast<const float*>(s_G + (size_t)stg * kGtcTileBytes) + q4 * 32 + lane;
+        const long long base = o_begin + (long long)s * kGtcKT + sub * 8;
         uint32_t hi[2][8], lo[2][8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float h0 = tf32_round(v0[j]), h1 = tf32_round(v1[j]);
-          hi[0][j] = __float_as_uint(h0); lo[0][j] = __float_as_uint(tf32_round(v0[j] - h0));
-          hi[1][j] = __float_as_uint(h1); lo[1][j] = __float_as_uint(tf32_round(v1[j] - h1));
+          float v0 = gs[((sub * 8 + j) * 2 + 0) * 128], v1 = gs[((sub * 8 + j) * 2 + 1) * 128];
+          if (base + j >= o_end) { v0 = 0.f; v1 = 0.f; }   // rows past the chunk: whatever the copy brought
+          const float h0 = tf32_round(v0), h1 = tf32_round(v1);
+          hi[0][j] = __float_as_uint(h0); lo[0][j] = __float_as_uint(tf32_round(v0 - h0));
+          hi[1][j] = __float_as_uint(h1); lo[1][j] = __float_as_uint(tf32_round(v1 - h1));
         }
-        if (s + 1 < ntiles) fetch(s + 1);
+        __syncwarp();
+        if (lane == 0) mtc_arrive(barGe + 8 * stg);   // this warp has read the ring slot
         if (use > 0) mtc_wait(barM + 8 * b, (use - 1) & 1);  // the MMAs that read A buffer b have completed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + colA + (uint32_t)(b * 128 + sub * 8);
@@ -776,6 +780,22 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
         __syncwarp();
         ++since;
         if (since == g.flush) since = 0;
+      }
+    } else if (is_copy) {
+      const float* Gc = g.G + ((long long)cb * g.Gld + (o_begin - a.obs_begin)) * 256;
+      for (int s = 0; s < ntiles; ++s, ++tg) {
+        const uint32_t stg = tg % kGtcStages, round = tg / kGtcStages;
+        if (lane == 0) {
+          if (round > 0) mtc_wait(barGe + 8 * stg, (round - 1) & 1);   // all loader warps have read the slot
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barGf + 8 * stg), "r"(kGtcTileBytes)
+                       : "memory");
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                  smem_u32(s_G + (size_t)stg * kGtcTileBytes)),
+              "l"(Gc + (long long)s * kGtcKT * 256), "r"(kGtcTileBytes), "r"(barGf + 8 * stg)
+              : "memory");
+        }
+        __syncwarp();
       }
     } else {
       tg += (uint32_t)ntiles;
