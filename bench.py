@@ -39,7 +39,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=DEFAULT_CONFIG)
-    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--dtype", default="f32", choices=["f64", "f32"],
+                    help="arithmetic type of the sweep; f32 is the reference's default (LocScalePTM to_float32=True, "
+                         "model/model.py:279-294); the other precision is measured in the same run under extra")
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the config's)")
     ap.add_argument("--n", type=int, default=0, help="override the number of observations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -284,6 +286,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     launches_per_step = model.last_launch_count()
+    route = model.last_main_route()
 
     # dominant kernel (k_main) duration, CUDA events on the launching stream
     model.profile(True)
@@ -332,8 +335,9 @@ def run_ours(args):
         torch.cuda.empty_cache()
         reps = max(3, min(K, 10))
         if world == 1:
-            if args.dtype == "f64":
-                bx._guard(extra, "c3_f32", lambda: bx.f32_c3(torch, bw, dev, peak, reps))
+            other = np.float64 if args.dtype == "f32" else np.float32
+            bx._guard(extra, "c3_f64" if args.dtype == "f32" else "c3_f32",
+                      lambda: bx.c3_other_dtype(torch, bw, dev, peak, reps, other))
             bx._guard(extra, "c4_information", lambda: bx.c4_information(torch, bw, dev, 5))
             bx._guard(extra, "ess", lambda: bx.ess(torch, bw, dev))
         else:
@@ -344,11 +348,12 @@ def run_ours(args):
         ms_per_step = total_ms / K
         value = n * C * world / (ms_per_step * 1e-3)
         achieved = n * C * wl.bytes_alg / (main_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                rec = json.load(open(tp))[f"{args.dtype}_{route}"]
+                traffic, traffic_src = rec["dram_bytes_per_step"], rec["source"]
             except Exception:
                 traffic = None
         itemsize = wl.params.dtype.itemsize
@@ -363,14 +368,16 @@ def run_ours(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
-                "traffic_source": "static: ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel on "
-                                  "this workload, profiles/r1_traffic.json (not re-measured in this run)",
-                "peak_source": peak_src, "kernel": "ptm::k_main",
+                "traffic_source": f"static, not re-measured in this run: {traffic_src}",
+                "peak_source": peak_src,
+                "kernel": "ptm::k_main_tc + ptm::k_grad_tc (tcgen05 route)" if route == "tcgen05" else "ptm::k_main",
+                "route": route,
                 "kernel_ms": main_ms, "pre_ms": pre_ms, "post_ms": post_ms,
                 "bytes_alg_per_eval": wl.bytes_alg,
-                "note": "algorithmic bytes = w*(1+T_x) per obs-chain eval; the kernel re-uses every "
-                        "observation across the 32 chains of a CTA, so real DRAM traffic is far lower "
-                        "(see traffic) and the limiter is the FP64/issue/shared-memory pipes",
+                "note": "algorithmic bytes = w*(1+T_x) per obs-chain eval; kernel_ms = CUDA events around the sweep "
+                        "kernel(s) of one step on the launching stream.  The observations are re-used across the "
+                        "chains of a CTA (32 in k_main, 128 in the tcgen05 route); the tcgen05 route moves "
+                        "dl/deta (8 B per eval) through HBM between its two kernels (see traffic)",
             },
             "e2e": {
                 "value": n * C * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,

@@ -35,11 +35,12 @@ def _guard(out, key, fn):
         out[key]["wall_s"] = round(time.perf_counter() - t0, 2)
 
 
-def f32_c3(torch, bw, dev, peak_gbs, reps):
-    wl = bw.build("c3_n1M_5loc_5scale_nb20_1024chains", dtype=np.float32, device=dev)
+def c3_other_dtype(torch, bw, dev, peak_gbs, reps, dtype):
+    """The headline workload at the other precision (float64 when the headline is float32)."""
+    wl = bw.build("c3_n1M_5loc_5scale_nb20_1024chains", dtype=dtype, device=dev)
     m = wl.model.build()
     p = torch.from_numpy(wl.params).to(dev)
-    lp = torch.empty(p.shape[0], dtype=torch.float32, device=dev)
+    lp = torch.empty(p.shape[0], dtype=p.dtype, device=dev)
     g = torch.empty_like(p)
     ms = _events(torch, lambda: m.log_prob_and_grad(p, lp, g), reps, 3)
     m.profile(True)
@@ -48,7 +49,8 @@ def f32_c3(torch, bw, dev, peak_gbs, reps):
     m.profile(False)
     evals = wl.n * p.shape[0]
     ach = evals * wl.bytes_alg / (k_ms * 1e-3) / 1e9
-    return {"workload": wl.name, "dtype": "f32", "ms_per_step": ms, "kernel_ms": k_ms,
+    return {"workload": wl.name, "dtype": "f64" if np.dtype(dtype) == np.float64 else "f32", "route": m.last_main_route(),
+            "ms_per_step": ms, "kernel_ms": k_ms,
             "value": evals / (ms * 1e-3), "unit": "obs*chain evals/s", "bytes_alg_per_eval": wl.bytes_alg,
             "roofline_frac": ach / peak_gbs, "finite": bool(torch.isfinite(lp).all() and torch.isfinite(g).all())}
 
