@@ -92,6 +92,12 @@ typedef struct {
   double trafo_lambda;         /* PTMSpline eps: transition width / (b - a) */
   const void* trafo_grid;      /* [1002] BSplineApprox.grid, or NULL to rebuild it
                                   with the restated jnp.linspace formula */
+  const int32_t* noncentered;  /* [T] or NULL: 1 = term.reparam_noncentered() (gam/var.py:176-197):
+                                  the parameter is the LATENT coefficient, coef = tau_t * latent,
+                                  prior latent ~ N(0, inv(K)) (scale 1); the IWLS factor is
+                                  tau_t * chol (iwls_proposals.py:82-89) */
+  int32_t trafo_noncentered;   /* PTMCoef(noncentered=True), var.py:100-107: delta = Z (tau_delta *
+                                  delta_z), delta_z ~ N(0, 1) */
 } PtmProblemDesc;
 
 typedef struct PtmProblem PtmProblem; /* opaque, immutable after create (tuning knobs in the

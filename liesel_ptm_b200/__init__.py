@@ -16,6 +16,7 @@ from .spline import (  # noqa: F401
     approx_grid,
     banded_basis,
     equidistant_knots,
+    lin,
     mixed_model,
     ps,
     term,
@@ -31,7 +32,7 @@ from .model import (  # noqa: F401
 
 __all__ = [
     "LocScalePTM", "FlatLogProb", "GaussianLocCholInfo", "GaussianScaleCholInfo",
-    "ps", "term", "PTMKnots", "LogIncKnots", "Penalty", "equidistant_knots",
+    "ps", "lin", "term", "PTMKnots", "LogIncKnots", "Penalty", "equidistant_knots",
     "mixed_model", "LinearConstraintEVD", "banded_basis", "approx_grid", "trafo_reparam", "Basis",
     "PtmError",
 ]

@@ -60,6 +60,8 @@ class PtmProblemDesc(C.Structure):
         ("trafo_Z", C.c_void_p),
         ("trafo_lambda", C.c_double),
         ("trafo_grid", C.c_void_p),
+        ("noncentered", C.POINTER(C.c_int32)),
+        ("trafo_noncentered", C.c_int32),
     ]
 
 

@@ -64,6 +64,7 @@ struct PtmProblem {
   int nparam = 0, J = 0, KK = 0, P = 0;
   int nb[ptm::kMaxTerms] = {0}, p[ptm::kMaxTerms] = {0}, pred[ptm::kMaxTerms] = {0};
   int rank[ptm::kMaxTerms] = {0}, qidx[ptm::kMaxTerms] = {0};
+  int nc[ptm::kMaxTerms] = {0}, nc_dz = 0;  // non-centred parameterisations
   int zoff[ptm::kMaxTerms] = {0}, koff[ptm::kMaxTerms] = {0}, boff[ptm::kMaxTerms] = {0};
   int goff[ptm::kMaxTerms] = {0};
   double inv_dk[ptm::kMaxTerms] = {0};
@@ -149,6 +150,7 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
       return fail(PTM_ERR_SHAPE, "predictor must be PTM_LOC or PTM_SCALE");
     if (!d->x[t] || !d->knots[t] || !d->Z[t] || !d->K[t]) return fail(PTM_ERR_NULL, "null term array");
     pr->nb[t] = nb; pr->p[t] = p; pr->pred[t] = d->predictor[t]; pr->rank[t] = d->rank[t];
+    pr->nc[t] = d->noncentered ? (d->noncentered[t] != 0) : 0;
     pr->qidx[t] = d->predictor[t] == PTM_LOC ? pr->T_loc++ : pr->T_scale++;
     pr->zoff[t] = zo; zo += nb * p;
     pr->koff[t] = ko; ko += p * p;
@@ -216,6 +218,7 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
   }
   pr->n = n;
   pr->nparam = d->nparam;
+  pr->nc_dz = d->trafo_noncentered != 0;
   pr->J = d->nparam + 1;
   pr->KK = pr->J - 3;
   pr->dz_off = bo;
@@ -523,8 +526,10 @@ void fill_pre_args(const PtmProblem* pr, const R* params, long long C, R* Gamma,
   pa.Zd = reinterpret_cast<const R*>(pr->d_Zd);
   pa.tc = reinterpret_cast<const ptm::TrafoConst<double>*>(pr->d_tc64);
   pa.C = (int)C; pa.P = pr->P; pa.T = pr->T; pa.dz_off = pr->dz_off;
+  pa.tau_off = pr->tau_off; pa.taud_off = pr->taud_off; pa.nc_dz = pr->nc_dz;
   for (int t = 0; t < pr->T; ++t) {
     pa.nb[t] = pr->nb[t]; pa.p[t] = pr->p[t]; pa.zoff[t] = pr->zoff[t]; pa.boff[t] = pr->boff[t];
+    pa.nc[t] = pr->nc[t];
   }
 }
 
@@ -693,6 +698,8 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   po.dz_off = pr->dz_off; po.tau_off = pr->tau_off; po.taud_off = pr->taud_off;
   po.n_obs = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
   po.add_priors = pr->add_priors;
+  po.nc_dz = pr->nc_dz;
+  for (int t = 0; t < pr->T; ++t) po.nc[t] = pr->nc[t];
   const size_t smem_post = ((size_t)ma.NSLOT * 32 + (size_t)std::max(pr->T, 1) * 32) * sizeof(double);
   if (want_grad) {
     auto kp = ptm::k_post<R, true>;
@@ -927,15 +934,7 @@ int xtwx_terms(const PtmProblem* pr, const int* terms, int nterms, const R* para
   R* cc = reinterpret_cast<R*>(wsb + pl.off_cc);
   double* xt = reinterpret_cast<double*>(wsb + pl.off_xt);
   ptm::PreArgs<R> pa;
-  memset(&pa, 0, sizeof pa);
-  pa.params = params; pa.Gamma = Gamma; pa.cc = cc;
-  pa.Zall = reinterpret_cast<const R*>(pr->d_Zall);
-  pa.Zd = reinterpret_cast<const R*>(pr->d_Zd);
-  pa.tc = reinterpret_cast<const ptm::TrafoConst<double>*>(pr->d_tc64);
-  pa.C = (int)C; pa.P = pr->P; pa.T = pr->T; pa.dz_off = pr->dz_off;
-  for (int t = 0; t < pr->T; ++t) {
-    pa.nb[t] = pr->nb[t]; pa.p[t] = pr->p[t]; pa.zoff[t] = pr->zoff[t]; pa.boff[t] = pr->boff[t];
-  }
+  fill_pre_args<R>(pr, params, C, Gamma, cc, pa);
   g_launches = 0;
   ptm::k_pre<R><<<(unsigned)C, 128, pr->P * sizeof(R), st>>>(pa);
   PTM_CUDA(cudaGetLastError());
@@ -954,6 +953,7 @@ int xtwx_terms(const PtmProblem* pr, const int* terms, int nterms, const R* para
   for (int t = 0; t < pr->T; ++t) {
     xa.nb[t] = pr->nb[t]; xa.p[t] = pr->p[t];
     xa.zoff[t] = pr->zoff[t]; xa.koff[t] = pr->koff[t]; xa.inv_dk[t] = (R)pr->inv_dk[t];
+    xa.nc[t] = pr->nc[t];
   }
   xa.const_w = loc ? 0 : 1;  // scale terms: W == 2 (iwls_proposals.py:118-119)
   if (loc)
@@ -1147,6 +1147,7 @@ int hessian_impl(const PtmProblem* pr, int block, int mode, const R* params, lon
   po.C = (int)C; po.P = pr->P; po.M = hp.M; po.NACC = hp.NACC; po.KK = pr->KK; po.mode = mode;
   po.add_priors = pr->add_priors;
   po.tau_off = pr->tau_off; po.taud_off = pr->taud_off; po.dz_off = pr->dz_off;
+  po.nc = hp.kind == ptm::kHessBeta ? pr->nc[block] : pr->nc_dz;
   if (hp.kind == ptm::kHessBeta) {
     po.term = block; po.nbt = pr->nb[block]; po.p = pr->p[block]; po.zoff = pr->zoff[block]; po.koff = pr->koff[block];
     const size_t sm = ((size_t)po.nbt * 4 + (size_t)po.nbt * po.p + 2 * (size_t)po.p * po.p) * sizeof(double);

@@ -415,6 +415,7 @@ struct HessPostArgs {
   R* chol;
   int C, P, M, NACC, KK, mode, add_priors;
   int term, nbt, p, zoff, koff, tau_off, taud_off, dz_off;
+  int nc;  // the block is in non-centred form: coef = scale * latent, prior scale 1
 };
 
 // beta_t block: one block (128 threads) per chain.
@@ -450,12 +451,15 @@ __global__ void k_hess_post_beta(const HessPostArgs<R> a) {
   }
   __syncthreads();
   const D tau = (D)a.params[(long long)c * a.P + a.tau_off + a.term];
-  const D is2 = a.add_priors ? 1.0 / (tau * tau) : 0.0;
+  // non-centred: d gamma / d latent = tau Z, prior latent ~ N(0, inv(K))
+  const D is2 = a.add_priors ? (a.nc ? 1.0 : 1.0 / (tau * tau)) : 0.0;
+  const D dsc = a.nc ? tau * tau : 1.0;
   const R* Kt = a.Kall + a.koff;
   for (int idx = tid; idx < p * p; idx += blockDim.x) {
     const int i = idx / p, k = idx - i * p;
     D v = 0.0;
     for (int r = 0; r < nbt; ++r) v = fma((D)Zt[r * p + i], s_mz[r * p + k], v);
+    v *= dsc;
     s_P[idx] = a.add_priors ? fma(is2, (D)Kt[idx], v) : v;
   }
   __syncthreads();
@@ -501,7 +505,7 @@ __global__ void k_hess_post_dz(const HessPostArgs<R> a) {
     for (int j = 0; j < np_; ++j) {
       D v = 0.0;
       for (int k = 0; k < dq; ++k) v = fma((D)a.Zd[j * dq + k], (D)dzp[k], v);
-      delta[j] = v;
+      delta[j] = a.nc ? v * (D)par[a.taud_off] : v;
     }
     coef_map_forward(tc, delta, ev, sm, vt);
     for (int j = 0; j <= J; ++j) { gvt[j] = j < NGV ? s_red[NGV * 5 + j] : 0.0; aVL[j] = aDL[j] = aVR[j] = aDR[j] = 0.0; }
@@ -583,7 +587,8 @@ __global__ void k_hess_post_dz(const HessPostArgs<R> a) {
     const int i = idx / dq, k = idx - i * dq;
     D v = 0.0;
     for (int l = 0; l < np_; ++l) v = fma((D)a.Zd[l * dq + i], s_W[l * dq + k], v);
-    if (a.add_priors && i == k) v += 1.0 / (taud * taud);
+    if (a.nc) v *= taud * taud;
+    if (a.add_priors && i == k) v += a.nc ? 1.0 : 1.0 / (taud * taud);
     s_M[idx] = v;
   }
   __syncthreads();

@@ -806,6 +806,9 @@ struct PreArgs {
   int C, P, T;
   int nb[kMaxTerms], p[kMaxTerms], zoff[kMaxTerms], boff[kMaxTerms];
   int dz_off;
+  // non-centred parameterisations (gam/var.py:176-197, var.py:100-107): the chain state holds
+  // the LATENT coefficients; coef = tau * latent
+  int nc[kMaxTerms], nc_dz, tau_off, taud_off;
 };
 
 template <typename R>
@@ -827,6 +830,7 @@ __global__ void k_pre(const PreArgs<R> a) {
       const R* b = s_par + a.boff[t];
       D v = 0.0;
       for (int k = 0; k < a.p[t]; ++k) v = fma((D)zr[k], (D)b[k], v);
+      if (a.nc[t]) v *= (D)s_par[a.tau_off + t];  // basis . (scale * coef), gam/var.py:190-193
       a.Gamma[((long long)t * kMaxNbases + j) * a.C + c] = (R)v;
     }
   }
@@ -838,7 +842,7 @@ __global__ void k_pre(const PreArgs<R> a) {
     for (int j = 0; j < np_; ++j) {
       D v = 0.0;
       for (int k = 0; k < np_ - 1; ++k) v = fma((D)a.Zd[j * (np_ - 1) + k], (D)dz[k], v);
-      delta[j] = v;
+      delta[j] = a.nc_dz ? v * (D)s_par[a.taud_off] : v;  // Z (scale * latent), var.py:104-105
     }
     coef_map_forward(tc, delta, e, sm, vt);
     D cfirst[5], clast[5];
@@ -880,6 +884,7 @@ struct PostArgs {
   int dz_off, tau_off, taud_off;
   long long n_obs;
   int add_priors;
+  int nc[kMaxTerms], nc_dz;  // non-centred parameterisations (see PreArgs)
 };
 
 template <typename R, bool GRAD>
@@ -919,13 +924,25 @@ __global__ void k_post(const PostArgs<R> a) {
       for (int k = 0; k < p; ++k) kb = fma((D)Kt[i * p + k], (D)b[k], kb);
       quad = fma((D)b[i], kb, quad);
     }
-    const D it2 = 1.0 / (tau * tau);
+    const D it2 = a.nc[t] ? 1.0 : 1.0 / (tau * tau);
     // one slot per (term, chain), summed over t in a fixed order below: bit-reproducible
-    s_lp[t * 32 + lane] = -(log(tau) * (D)a.rank[t] + 0.5 * quad * it2);
-    if (a.add_priors) {
-      if (GRAD) a.grad[(long long)c * a.ld_grad + a.tau_off + t] = (R)(-(D)a.rank[t] / tau + quad * it2 / tau);
-    } else if (GRAD) {
-      a.grad[(long long)c * a.ld_grad + a.tau_off + t] = R(0);
+    // (non-centred: latent ~ N(0, inv(K)) with scale 1, no log-scale term)
+    s_lp[t * 32 + lane] = a.nc[t] ? -0.5 * quad : -(log(tau) * (D)a.rank[t] + 0.5 * quad * it2);
+    if (GRAD) {
+      D gt = 0.0;
+      if (a.nc[t]) {
+        // d/d tau of basis . (tau * latent): latent' Z' dl/dgamma (data part only)
+        const R* Zt = a.Zall + a.zoff[t];
+        const D* gg = red + (kRegSlots + KK + 4 + a.goff[t]) * 32 + lane;
+        for (int k = 0; k < p; ++k) {
+          D v = 0.0;
+          for (int j = 0; j < a.nb[t]; ++j) v = fma((D)Zt[j * p + k], gg[j * 32], v);
+          gt = fma((D)b[k], v, gt);
+        }
+      } else if (a.add_priors) {
+        gt = -(D)a.rank[t] / tau + quad * it2 / tau;
+      }
+      a.grad[(long long)c * a.ld_grad + a.tau_off + t] = (R)gt;
     }
   }
   if (GRAD) {
@@ -942,12 +959,13 @@ __global__ void k_post(const PostArgs<R> a) {
         const D* gg = red + (kRegSlots + KK + 4 + a.goff[t]) * 32 + lane;
         D v = 0.0;
         for (int j = 0; j < nb; ++j) v = fma((D)Zt[j * p + k], gg[j * 32], v);
+        const D tau = (D)par[a.tau_off + t];
+        if (a.nc[t]) v *= tau;
         if (a.add_priors) {
-          const D tau = (D)par[a.tau_off + t];
           const R* b = par + a.boff[t];
           D kb = 0.0;
           for (int i = 0; i < p; ++i) kb = fma((D)Kt[k * p + i], (D)b[i], kb);
-          v -= kb / (tau * tau);
+          v -= a.nc[t] ? kb : kb / (tau * tau);
         }
         a.grad[(long long)c * a.ld_grad + a.boff[t] + k] = (R)v;
       }
@@ -970,7 +988,8 @@ __global__ void k_post(const PostArgs<R> a) {
              (D)a.n_obs * half_log_2pi;
       if (a.add_priors) {
         for (int t = 0; t < a.T; ++t) lp += s_lp[t * 32 + lane];
-        lp += -0.5 * ss / (taud * taud) - (D)(np_ - 1) * (log(taud) + half_log_2pi);
+        lp += a.nc_dz ? -0.5 * ss - (D)(np_ - 1) * half_log_2pi
+                      : -0.5 * ss / (taud * taud) - (D)(np_ - 1) * (log(taud) + half_log_2pi);
       }
       a.logp[(long long)c * a.ld_logp] = (R)lp;
       if (!GRAD && a.stats != nullptr) {
@@ -985,12 +1004,12 @@ __global__ void k_post(const PostArgs<R> a) {
         R* go = a.grad + (long long)c * a.ld_grad;
         go[0] = (R)red[SL_GB0 * 32 + lane];
         go[1] = (R)red[SL_GG0 * 32 + lane];
-        go[a.taud_off] = a.add_priors ? (R)(ss / (taud * taud * taud) - (D)(np_ - 1) / taud) : R(0);
+        D g_taud = (a.add_priors && !a.nc_dz) ? ss / (taud * taud * taud) - (D)(np_ - 1) / taud : 0.0;
         D delta[kMaxNparam], e[kMaxNparam], sm[kMaxNparam], vt[kMaxJ], gvt[kMaxJ], gdelta[kMaxNparam];
         for (int j = 0; j < np_; ++j) {
           D v = 0.0;
           for (int k = 0; k < np_ - 1; ++k) v = fma((D)a.Zd[j * (np_ - 1) + k], (D)dz[k], v);
-          delta[j] = v;
+          delta[j] = a.nc_dz ? v * taud : v;
         }
         coef_map_forward(tc, delta, e, sm, vt);
         for (int j = 0; j <= np_; ++j) gvt[j] = red[(kRegSlots + j) * 32 + lane];
@@ -1007,9 +1026,16 @@ __global__ void k_post(const PostArgs<R> a) {
         for (int k = 0; k < np_ - 1; ++k) {
           D v = 0.0;
           for (int j = 0; j < np_; ++j) v = fma((D)a.Zd[j * (np_ - 1) + k], gdelta[j], v);
-          if (a.add_priors) v -= (D)dz[k] / (taud * taud);
+          if (a.nc_dz) {
+            g_taud = fma((D)dz[k], v, g_taud);  // d/d tau_delta of Z (tau_delta * latent)
+            v *= taud;
+            if (a.add_priors) v -= (D)dz[k];
+          } else if (a.add_priors) {
+            v -= (D)dz[k] / (taud * taud);
+          }
           go[a.dz_off + k] = (R)v;
         }
+        go[a.taud_off] = (R)g_taud;
       }
     }
   }

@@ -47,6 +47,7 @@ struct XtwxArgs {
   long long n, obs_begin, obs_end, chunk_len;
   int C, P, T, KK, CG, M, n_items, To, NW;
   int nsc, nbt, sum_sc_nb, band_slots, const_w, tau_off, add_penalty;
+  int nc[kMaxTerms];  // non-centred terms: chol_info = tau * chol (iwls_proposals.py:82-89)
   int sc_term[kMaxTerms], sc_goff[kMaxTerms];  // scale terms feeding sigma
   int bt_term[kMaxTerms], bt_boff[kMaxTerms];  // requested terms, offset of their band block
   int nb[kMaxTerms], p[kMaxTerms], zoff[kMaxTerms], koff[kMaxTerms];
@@ -285,7 +286,7 @@ __global__ void k_xtwx_post(const XtwxArgs<R> a, int term, int boff, R* __restri
   }
   for (int idx = tid; idx < p * p; idx += blockDim.x) {
     const int i = idx / p, k = idx - i * p;
-    chol[(long long)c * p * p + idx] = k <= i ? (R)s_P[idx] : R(0);
+    chol[(long long)c * p * p + idx] = k <= i ? (R)(a.nc[t] ? tau * s_P[idx] : s_P[idx]) : R(0);
   }
 }
 

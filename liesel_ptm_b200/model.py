@@ -79,6 +79,9 @@ class LocScalePTM:
         # Z_delta is reparameterisation DATA (LAPACK-dependent eigenvector order); a caller
         # that exports it from the host model assigns it before build()
         self.trafo_Z = None
+        # PTMCoef(noncentered=...) (var.py:55, 100-107); new_ptm builds it with False
+        # (model/model.py:377); set before build() for the non-centred form
+        self.trafo_noncentered = False
         self._loc = _Predictor(_lib.PTM_LOC, "$\\mu$")
         self._scale = _Predictor(_lib.PTM_SCALE, "$\\sigma$")
         self.device = torch.device(device)
@@ -178,6 +181,8 @@ class LocScalePTM:
         d.trafo_lambda = self.trafo_lambda
         self.grid = approx_grid(self.knots)
         d.trafo_grid = arr(self.grid).ctypes.data
+        d.noncentered = i32_array([int(t.is_noncentered) for t, _ in self.terms] or [0])
+        d.trafo_noncentered = int(self.trafo_noncentered)
         h = C.c_void_p()
         _lib.check(lib.ptm_problem_create(C.byref(d), C.byref(h)))
         self._handle = h

@@ -243,12 +243,50 @@ class term:
         self.nbases = basis.ncoef
         self.ig_concentration = ig_concentration
         self.ig_scale = ig_scale
+        self.is_noncentered = False
+
+    def reparam_noncentered(self) -> "term":
+        """gam/var.py:176-197: ``coef ~ N(0, scale^2 inv(penalty))`` becomes ``latent ~ N(0,
+        inv(penalty)); coef = scale * latent``.  The chain state then holds the latent
+        coefficient; must be called before ``LocScalePTM.build()``."""
+        self.is_noncentered = True
+        return self
 
     @classmethod
     def f_ig(cls, basis: Basis, fname: str = "f", ig_concentration: float = 1.0,
-             ig_scale: float = 0.005) -> "term":
-        return cls(basis, name=f"{fname}({basis.xname})", ig_concentration=ig_concentration,
-                   ig_scale=ig_scale)
+             ig_scale: float = 0.005, noncentered: bool = False) -> "term":
+        t = cls(basis, name=f"{fname}({basis.xname})", ig_concentration=ig_concentration,
+                ig_scale=ig_scale)
+        if noncentered:  # gam/var.py:283-284, 379-380
+            t.reparam_noncentered()
+        return t
+
+
+def lin(x, xname: str | None = None, add_intercept: bool = False, penalty=None, dtype=np.float64) -> Basis:
+    """Linear basis (gam/var.py:1025-1061, Basis.new_linear 721-770): design ``[x]`` or ``[1, x]``.
+
+    The kernels evaluate every term through the banded cubic B-spline design, and cubic
+    B-splines reproduce linear functions exactly: with the Greville abscissae
+    ``g_j = (k_{j+1} + k_{j+2} + k_{j+3}) / 3`` of a four-basis knot vector over the range of x,
+    ``sum_j B_j(x) g_j = x`` and ``sum_j B_j(x) = 1``.  So the linear design is the spline
+    design with ``Z = [g]`` (or ``[1, g]``) -- no extra kernel path; parity to rounding (1e-15).
+    ``penalty`` is the (p, p) prior penalty of the wrapping ``term`` (identity by default, i.e.
+    an iid normal prior, the way the reference's notebooks wrap ``lin``)."""
+    if not xname:
+        raise ValueError("Either x must be a named lsl.Var, or xname must be set.")
+    x = np.asarray(x, dtype=dtype)
+    if x.ndim != 1:
+        raise ValueError("the B200 path takes one covariate column per linear term")
+    nb = 4
+    knots = equidistant_knots(x, n_param=nb, order=3, dtype=dtype)
+    banded_basis(x, knots)  # range check, raises like the reference
+    k = knots.astype(np.float64)
+    grev = np.array([(k[j + 1] + k[j + 2] + k[j + 3]) / 3.0 for j in range(nb)])
+    Z = np.stack([np.ones(nb), grev], axis=1) if add_intercept else grev[:, None]
+    p = Z.shape[1]
+    K = np.eye(p) if penalty is None else np.asarray(penalty, dtype=np.float64).reshape(p, p)
+    return Basis(x=x, xname=xname, knots=knots, Z=np.ascontiguousarray(Z.astype(dtype)),
+                 penalty=np.ascontiguousarray(K.astype(dtype)), nbases=nb)
 
 
 def trafo_reparam(nparam: int, dtype=np.float64):

@@ -497,6 +497,7 @@ class PSplineTerm:
     rank: int
     design: np.ndarray  # (n, p) dense B(x) @ Z as the reference stores it
     predictor: str = "loc"  # "loc" | "scale"
+    noncentered: bool = False  # term.reparam_noncentered(), gam/var.py:176-197
 
     @property
     def nb(self):
@@ -595,6 +596,18 @@ class PTMModel:
         self.spline = PTMSpline(self.knots.knots, eps=trafo_lambda)
         self.nparam = nparam
         self.Zd = trafo_Z(nparam, dtype)
+        self.trafo_noncentered = False  # PTMCoef(noncentered=True), var.py:100-107
+
+    def coef(self, st: "ChainState", c: int, t: int):
+        """The coefficient the term value sees: ``scale * coef`` in non-centred form
+        (gam/var.py:190-193), the parameter itself otherwise."""
+        b = st.beta[t][c]
+        return st.tau[c, t] * b if self.terms[t].noncentered else b
+
+    def delta_of(self, st: "ChainState", c: int):
+        """var.py:104-115: Z (scale * latent) in non-centred form, Z latent otherwise."""
+        dz = st.delta_z[c]
+        return (st.tau_delta[c] * dz if self.trafo_noncentered else dz) @ self.Zd.T
 
     # --- forward ---------------------------------------------------------
     def predictors(self, st: ChainState, c: int):
@@ -603,7 +616,7 @@ class PTMModel:
         mu = np.full(self.n, st.beta0[c], dtype=self.dtype)
         ls = np.full(self.n, st.gamma0[c], dtype=self.dtype)
         for t, term in enumerate(self.terms):
-            f = term.design @ st.beta[t][c]
+            f = term.design @ self.coef(st, c, t)
             if term.predictor == "loc":
                 mu = mu + f
             else:
@@ -616,7 +629,7 @@ class PTMModel:
         sd = np.exp(ls)
         r = (self.y - mu) / sd  # dist.py:735-736
         logdet_param = -np.log(sd)  # dist.py:738
-        delta = st.delta_z[c] @ self.Zd.T  # var.py:112-115
+        delta = self.delta_of(st, c)  # var.py:104-115
         theta = self.spline.compute_coef(delta)
         nan_mask = np.isnan(r)
         z, d = self.spline.dot_and_deriv_coef(r, theta)
@@ -639,14 +652,14 @@ class PTMModel:
         ls = np.full(y_new.shape[0], st.gamma0[c], dtype=self.dtype)
         for t, term in enumerate(self.terms):
             B = basis_matrix(np.asarray(X_new[t], dtype=self.dtype), term.knots, 3, outer_ok=False)
-            f = (B @ term.Z) @ st.beta[t][c]
+            f = (B @ term.Z) @ self.coef(st, c, t)
             if term.predictor == "loc":
                 mu = mu + f
             else:
                 ls = ls + f
         sd = np.exp(ls)
         r = (y_new - mu) / sd
-        theta = self.spline.compute_coef(st.delta_z[c] @ self.Zd.T)
+        theta = self.spline.compute_coef(self.delta_of(st, c))
         z, d = self.spline.dot_and_deriv_coef(r, theta)
         nan_mask = np.isnan(r)
         z = np.where(nan_mask, np.nan, z)
@@ -657,13 +670,17 @@ class PTMModel:
 
     def prior(self, st: ChainState, c: int):
         lp = self.dtype.type(0)
+        one = self.dtype.type(1)
         for t, term in enumerate(self.terms):
-            lp = lp + mvn_singular_logp(st.beta[t][c], term.K, st.tau[c, t], term.rank)
-        # delta_z ~ iid Normal(0, tau_delta): var.py:77-82 (tfd.Normal.log_prob, not in tree)
+            # non-centred: the prior's scale node is replaced by 1.0 (gam/var.py:188)
+            lp = lp + mvn_singular_logp(st.beta[t][c], term.K, one if term.noncentered else st.tau[c, t], term.rank)
+        # delta_z ~ iid Normal(0, tau_delta): var.py:77-82 (tfd.Normal.log_prob, not in tree);
+        # scale 1 in non-centred form (var.py:102-103)
+        sc = one if self.trafo_noncentered else st.tau_delta[c]
         lp = lp + np.sum(
-            -0.5 * (st.delta_z[c] / st.tau_delta[c]) ** 2
+            -0.5 * (st.delta_z[c] / sc) ** 2
             - self.dtype.type(LOG_2PI_HALF)
-            - np.log(st.tau_delta[c])
+            - np.log(sc)
         )
         return lp
 
@@ -747,13 +764,23 @@ class PTMModel:
             sm = sm / np.sum(sm)
             g_delta = e * g_e - sm * np.sum(e * g_e)
             pr = 1.0 if add_priors else 0.0
-            g_dz[c] = self.Zd.T @ g_delta - pr * st.delta_z[c] / st.tau_delta[c] ** 2
-            g_taud[c] = pr * (np.sum(st.delta_z[c] ** 2) / st.tau_delta[c] ** 3 - (self.nparam - 1) / st.tau_delta[c])
+            if self.trafo_noncentered:  # delta = Z (tau_delta * latent), latent ~ N(0, 1)
+                zg = self.Zd.T @ g_delta
+                g_dz[c] = st.tau_delta[c] * zg - pr * st.delta_z[c]
+                g_taud[c] = st.delta_z[c] @ zg
+            else:
+                g_dz[c] = self.Zd.T @ g_delta - pr * st.delta_z[c] / st.tau_delta[c] ** 2
+                g_taud[c] = pr * (np.sum(st.delta_z[c] ** 2) / st.tau_delta[c] ** 3 - (self.nparam - 1) / st.tau_delta[c])
             for t, term in enumerate(self.terms):
                 ge = g_mu if term.predictor == "loc" else g_ls
                 bt, tau = st.beta[t][c], st.tau[c, t]
-                g_beta[t][c] = term.design.T @ ge - pr * (term.K @ bt) / tau**2
-                g_tau[c, t] = pr * (-term.rank / tau + (bt @ term.K @ bt) / tau**3)
+                if term.noncentered:  # value = basis . (tau * latent), latent ~ N(0, inv(K))
+                    xg = term.design.T @ ge
+                    g_beta[t][c] = tau * xg - pr * (term.K @ bt)
+                    g_tau[c, t] = bt @ xg
+                else:
+                    g_beta[t][c] = term.design.T @ ge - pr * (term.K @ bt) / tau**2
+                    g_tau[c, t] = pr * (-term.rank / tau + (bt @ term.K @ bt) / tau**3)
             g_b0[c] = np.sum(g_mu)
             g_g0[c] = np.sum(g_ls)
         return logp, dict(beta=g_beta, tau=g_tau, delta_z=g_dz, tau_delta=g_taud, beta0=g_b0, gamma0=g_g0)
@@ -860,7 +887,7 @@ class PTMModel:
         s = np.exp(-ls)
         r = (y - mu) * s
         sp, ap = self.spline, self.spline.bspline
-        theta = sp.compute_coef(st.delta_z[c] @ self.Zd.T)
+        theta = sp.compute_coef(self.delta_of(st, c))
         tiny = np.finfo(self.dtype).tiny
         tH, tD, tD2 = ap.basis_grid @ theta, ap.basis_deriv_grid @ theta, ap.basis_deriv2_grid @ theta
         a, b, w = sp.min_knot, sp.max_knot, sp.transition_width
@@ -893,8 +920,10 @@ class PTMModel:
             X = term.design[rows]
             W = s * s * A if term.predictor == "loc" else r * r * A - r * g_r
             H = -(X.T @ (X * W[:, None]))
+            if term.noncentered:  # d eta / d latent = tau X, prior scale 1
+                H = H * st.tau[c, t] ** 2
             if add_priors:
-                H = H - term.K / st.tau[c, t] ** 2
+                H = H - (term.K if term.noncentered else term.K / st.tau[c, t] ** 2)
             return H
         # delta_z block: rows dz/dtheta, dd/dtheta (core: lerped G, G' rows; off the core through
         # the boundary values v_L, d_L / v_R, d_R = rows of G, G' at a and b)
@@ -926,7 +955,7 @@ class PTMModel:
         H_theta = -(bz.T @ bz) - bdw.T @ bdw
         g_theta = (-z) @ bz + inv_d @ bd
         # coefficient map delta -> theta (ptm.py:155-172, 210-230): first and second derivatives
-        delta = st.delta_z[c] @ self.Zd.T
+        delta = self.delta_of(st, c)
         npar = delta.shape[0]
         wts = log_sfn_weights(npar, self.dtype)
         sm = wts * np.exp(delta - np.max(delta))
@@ -941,8 +970,10 @@ class PTMModel:
         T2 = T2 - (g_e @ e) * dsm
         H_delta = J1.T @ H_theta @ J1 + T2
         H = self.Zd.T @ H_delta @ self.Zd
+        if self.trafo_noncentered:
+            H = H * st.tau_delta[c] ** 2
         if add_priors:
-            H = H - np.eye(npar - 1) / st.tau_delta[c] ** 2
+            H = H - np.eye(npar - 1) / (1.0 if self.trafo_noncentered else st.tau_delta[c] ** 2)
         return H
 
     @staticmethod
@@ -1014,6 +1045,8 @@ class PTMModel:
             Pc = Pc + 1e-6 * np.mean(np.diag(Pc)) * np.eye(p, dtype=self.dtype)
             P[c] = Pc
             L[c] = np.linalg.cholesky(Pc)
+            if term.noncentered:  # chol_info: scale * chol (iwls_proposals.py:82-89)
+                L[c] = st.tau[c, t] * L[c]
         return xtwx, P, L
 
     def scale_precision(self, st: ChainState, t: int):

@@ -203,3 +203,43 @@ def test_golden_basis_and_trafo():
         z, dd = sp.dot_and_deriv_n_fullbatch(t["r"], t["delta"][c])
         assert np.allclose(z, t["z"][c], rtol=1e-14, atol=1e-14)
     assert np.array_equal(sp.region_code(t["r"]).astype(np.int32), t["code"])
+
+
+def test_noncentered_form_is_the_centred_density_up_to_its_prior():
+    """gam/var.py:176-197, var.py:100-107: with coef = scale * latent the likelihood is the
+    centred one at coef, the prior is N(0, inv(K)) / N(0, 1) on the latent vector, and the
+    gradient follows by the chain rule (checked against central differences too)."""
+    y, X = o.synth_data(400, 1, 1, seed=2)
+    terms = [o.ps(X[0], 10, predictor="loc"), o.ps(X[1], 10, predictor="scale")]
+    om = o.PTMModel(y, terms, nparam=12)
+    st = o.synth_state(terms, 12, 2, seed=3, amp=0.2)
+    st.tau[:] = np.array([[0.7, 1.3], [1.1, 0.8]])
+    st.tau_delta[:] = np.array([0.6, 0.9])
+    lp_c, _ = om.logp_and_grad(st, add_priors=False)
+    # the same coefficients expressed through latent vectors
+    lat = o.ChainState(beta=[st.beta[t] / st.tau[:, t:t + 1] for t in range(2)], tau=st.tau.copy(),
+                       delta_z=st.delta_z / st.tau_delta[:, None], tau_delta=st.tau_delta.copy(),
+                       beta0=st.beta0.copy(), gamma0=st.gamma0.copy())
+    for t in terms:
+        t.noncentered = True
+    om.trafo_noncentered = True
+    lp_n, g = om.logp_and_grad(lat, add_priors=False)
+    assert np.allclose(lp_n, lp_c, rtol=1e-13)
+    lp_full = om.logp(lat)
+    prior = lp_full - lp_n
+    for c in range(2):
+        ref = sum(o.mvn_singular_logp(lat.beta[t][c], terms[t].K, 1.0, terms[t].rank) for t in range(2))
+        ref += float(o.normal_iid_logp(lat.delta_z[c][None, :], np.ones(1))[0])
+        assert abs(prior[c] - ref) < 1e-9
+    # chain rule against the CENTRED gradient (which the reference-code fixture pins): the
+    # declared derivatives of the custom_jvp are not finite-difference slopes, so the check is
+    # algebraic
+    for t in terms:
+        t.noncentered = False
+    om.trafo_noncentered = False
+    _, gc = om.logp_and_grad(st, add_priors=False)
+    for t in range(2):
+        assert np.allclose(g["beta"][t], st.tau[:, t:t + 1] * gc["beta"][t], rtol=1e-12, atol=1e-12)
+        assert np.allclose(g["tau"][:, t], np.sum(lat.beta[t] * gc["beta"][t], axis=1), rtol=1e-12, atol=1e-12)
+    assert np.allclose(g["delta_z"], st.tau_delta[:, None] * gc["delta_z"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(g["tau_delta"], np.sum(lat.delta_z * gc["delta_z"], axis=1), rtol=1e-12, atol=1e-12)
