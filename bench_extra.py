@@ -86,14 +86,22 @@ def ess(torch, bw, dev):
         start = wl.params.copy()
         L0 = m.layout
         start[:, 2:L0["delta_z"] + m.nparam - 1] *= 0.01
-        dr, info = mcmc.run_chains(m, torch.from_numpy(start).to(dev), warmup=warm, draws=draws, seed=0)
-        cols = list(range(L0["beta"][0] if m.terms else L0["delta_z"], L0["delta_z"] + m.nparam - 1))
-        e = np.array([mcmc.effective_sample_size(dr[:, :, j].T) for j in cols])
-        out[name] = {"chains": C, "warmup": warm, "draws": draws, "posterior_seconds": info["posterior_seconds"],
-                     "min_ess": float(e.min()), "min_ess_per_s": float(e.min() / info["posterior_seconds"]),
-                     "iterations_per_s": draws / info["posterior_seconds"],
-                     "sampler": "IWLS-MH per smooth term + HMC on delta_z over the fused operator (liesel_ptm_b200/mcmc.py); "
-                                "tau fixed -- not the reference's full kernel composition"}
+        rec = {}
+        for tag, kw in (("fixed_tau", {}), ("reference_composition", dict(sample_tau=True, pgibbs_intercepts=True))):
+            dr, info = mcmc.run_chains(m, torch.from_numpy(start).to(dev), warmup=warm, draws=draws, seed=0, **kw)
+            cols = list(range(L0["beta"][0] if m.terms else L0["delta_z"], L0["delta_z"] + m.nparam - 1))
+            if kw:
+                cols = cols + [L0["beta0"], L0["gamma0"]] + list(L0["tau"])
+            e = np.array([mcmc.effective_sample_size(dr[:, :, j].T) for j in cols])
+            rec[tag] = {"posterior_seconds": info["posterior_seconds"], "min_ess": float(e.min()),
+                        "min_ess_per_s": float(e.min() / info["posterior_seconds"]),
+                        "iterations_per_s": draws / info["posterior_seconds"], "cuda_graph": info["cuda_graph"],
+                        "accept_iwls": info["accept_iwls"], "accept_dz": info["accept_dz"]}
+        out[name] = {"chains": C, "warmup": warm, "draws": draws, **rec,
+                     "sampler": "liesel_ptm_b200/mcmc.py over the fused operator.  fixed_tau: IWLS-MH per smooth term + HMC "
+                                "on delta_z.  reference_composition: + inverse-gamma Gibbs on every tau^2 (gam/kernel.py:9-41) "
+                                "+ pseudo-Gibbs intercepts (predictor.py:133-175, 239-281); delta_z by HMC (NUTS in the "
+                                "reference), tau_delta fixed; min ESS over coefficients, intercepts and scales"}
     return out
 
 

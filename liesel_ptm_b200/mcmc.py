@@ -16,8 +16,14 @@ only through ``log_prob_and_grad`` / ``precision`` (the C ABI), for all chains a
   without an information matrix (the transformation coefficients delta_z; the reference
   samples them with NUTS from blackjax, which is out of scope).
 
-Smoothing scales tau are held fixed (their Gibbs / NUTS updates are O(1) per chain and
-stay with the host sampler).
+* ``gibbs_tau`` is the inverse-gamma Gibbs update of the smoothing variances
+  (``star_ig_gibbs``, gam/kernel.py:9-41: ``tau^2 ~ b' / Gamma(a')``, ``a' = a + rank / 2``,
+  ``b' = b + beta' K beta / 2``) over the fused quadratic forms (``ptm_quadform``), and
+  ``update_intercepts`` the pseudo-Gibbs recomputation of the two intercepts
+  (``loc_intercept_pgibbs`` / ``log_scale_intercept_pgibbs``, predictor.py:133-175, 239-281)
+  from the fused sufficient statistics in the sampler's sequential order.  With both switched
+  on ``run_chains`` runs the composition of the reference's default strategy except for the
+  blocks that have no information matrix (delta_z: HMC here, NUTS there; tau_delta: fixed).
 """
 
 from __future__ import annotations
@@ -190,9 +196,44 @@ def hmc_transition(model: LocScalePTM, params: torch.Tensor, lo: int, width: int
     return new, (torch.where(acc, logp_q, logp), torch.where(acc[:, None], grad_q, grad)), TransitionInfo(acc, la)
 
 
+def gibbs_tau(model: LocScalePTM, params: torch.Tensor, gen) -> torch.Tensor:
+    """``star_ig_gibbs`` (gam/kernel.py:9-41) for every smooth term and chain at once:
+    ``tau_t^2 = (b + beta' K beta / 2) / Gamma(a + rank / 2)`` with the term's inverse-gamma
+    hyper-parameters (gam/var.py:293-294, 352-360).  Non-centred terms are left alone (their
+    scale is sampled jointly with the latent coefficients in the reference).  Returns a new
+    parameter block."""
+    T = len(model.terms)
+    if T == 0:
+        return params
+    L = model.layout
+    quad = model.quadform(params)  # [C, T]
+    a = torch.tensor([t.ig_concentration + 0.5 * t.penalty_rank for t, _ in model.terms], dtype=params.dtype,
+                     device=params.device)
+    b = torch.tensor([t.ig_scale for t, _ in model.terms], dtype=params.dtype, device=params.device)
+    g = torch._standard_gamma(a.expand(params.shape[0], T).contiguous(), generator=gen)
+    tau = torch.sqrt((b + 0.5 * quad) / g)
+    out = params.clone()
+    keep = torch.tensor([bool(t.is_noncentered) for t, _ in model.terms], device=params.device)
+    cols = slice(L["tau"][0], L["tau"][0] + T)
+    out[:, cols] = torch.where(keep, params[:, cols], tau)
+    return out
+
+
+def update_intercepts(model: LocScalePTM, params: torch.Tensor) -> torch.Tensor:
+    """``loc_intercept_pgibbs`` then ``log_scale_intercept_pgibbs`` (predictor.py:133-175,
+    239-281): both intercepts recomputed from the current smooth terms, the log-scale
+    intercept seeing the updated location intercept (one fused sweep, ``ptm_intercept_stats``)."""
+    b0, g0 = model.compute_intercepts(params, sequential=True)
+    out = params.clone()
+    out[:, model.layout["beta0"]] = b0
+    out[:, model.layout["gamma0"]] = g0
+    return out
+
+
 def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: int, seed: int = 0,
                iwls_step: float = 1.0, dz_step: float = 0.05, target_accept: float = 0.8, n_leapfrog: int = 8,
-               reuse_information: bool = True, use_graph: bool = True):
+               reuse_information: bool = True, use_graph: bool = True, sample_tau: bool = False,
+               pgibbs_intercepts: bool = False):
     """Sweep per iteration: an IWLS-MH transition per smooth term, an HMC transition on
     delta_z.  Warm-up adapts the per-chain step sizes (Robbins-Monro on the acceptance
     probability) and, at 2/8 ... 7/8 of its length, the dense metric of delta_z from the
@@ -218,10 +259,15 @@ def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: in
     cache = None
     out = torch.empty((draws, C, params.shape[1]), dtype=params.dtype, device=params.device)
     scale_chol = {}
-    if reuse_information:
+    scale_xtx, scale_pen = {}, {}
+    if reuse_information:  # W == 2: X'WX of a scale term is constant, its factor only moves with tau
         for t in range(T):
             if not is_loc[t]:
-                scale_chol[t] = model.precision(t, params)[1].clone()
+                if sample_tau:
+                    scale_xtx[t] = model.xtwx(t, params).clone()
+                    scale_pen[t] = torch.from_numpy(np.asarray(model.terms[t][0].penalty)).to(params)
+                else:
+                    scale_chol[t] = model.precision(t, params)[1].clone()
     window = []
 
     def sweep(params, cache, it_warm, gen=gen):
@@ -236,7 +282,16 @@ def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: in
         for t in range(T):
             chol = None
             if reuse_information:
-                chol = loc_chol[k_loc] if is_loc[t] else scale_chol[t]
+                if is_loc[t]:
+                    chol = loc_chol[k_loc]
+                elif t in scale_chol:
+                    chol = scale_chol[t]
+                else:  # tau moves: penalty, ridge and factor on the constant 2 X'X
+                    from .parallel import finish_precision
+
+                    chol = finish_precision(scale_xtx[t], scale_pen[t], params[:, L["tau"][t]])[1]
+                    if model.terms[t][0].is_noncentered:
+                        chol = chol * params[:, L["tau"][t]][:, None, None]
             k_loc += 1 if is_loc[t] else 0
             params, cache, info = iwls_transition(model, params, t, istep[t], gen, cache, chol=chol)
             if it_warm is not None:
@@ -245,6 +300,15 @@ def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: in
             else:
                 acc_i = acc_i + info.accepted.double().mean() / T
         params, cache, info = hmc_transition(model, params, dz_lo, dz_w, step, n_leapfrog, metric_chol, gen, cache)
+        if sample_tau or pgibbs_intercepts:
+            # Gibbs blocks of the reference's composition; the cached logp / gradient are stale after
+            # them and are refreshed with one fused sweep
+            if sample_tau:
+                params = gibbs_tau(model, params, gen)
+            if pgibbs_intercepts:
+                params = update_intercepts(model, params)
+            lp_n, g_n = model.log_prob_and_grad(params)
+            cache = (lp_n.clone(), g_n.clone())
         return params, cache, info, acc_i
 
     # ---- warm-up (eager: host-side adaptation logic) -----------------------------------
