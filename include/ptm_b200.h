@@ -302,6 +302,17 @@ int ptm_predict_quantile_f32(const PtmProblem* prob, const float* params, int64_
                              const float* u, const float* x_new, int64_t m, float* yq,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* Predictive draws: ydraw[s, i] = mu_si + sigma_si * h_s^{-1}(Phi^{-1}(u[s, i])) with one uniform
+ * number per (sample, new row), u [S, m] -- TransformationDist._sample_n (dist.py:193-201:
+ * u ~ U(eps, 1), then _quantile).  The uniforms come from the caller (jax.random.uniform with
+ * the caller's key on the JAX side), so the draw is reproducible from the caller's seed. */
+int ptm_predict_sample_f64(const PtmProblem* prob, const double* params, int64_t n_samples,
+                           const double* u, const double* x_new, int64_t m, double* ydraw,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int ptm_predict_sample_f32(const PtmProblem* prob, const float* params, int64_t n_samples,
+                           const float* u, const float* x_new, int64_t m, float* ydraw,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* r [C, m] with h_c(r) = z for raw shape coefficients delta [C, nparam] and z [m] --
  * TransformationSpline.dot_inverse_n (bspline/util.py:105-122).  Exact inverse of the
  * reference's forward function (lerp cells in the core, quadratic transitions, linear

@@ -35,7 +35,7 @@ SYMBOLS = [
     "ptm_hessian_workspace_bytes", "ptm_hessian_block_f64", "ptm_hessian_block_f32",
     "ptm_pointwise_workspace_bytes", "ptm_pointwise_f64", "ptm_pointwise_f32",
     "ptm_problem_shared_designs", "ptm_predict_workspace_bytes", "ptm_predict_f64", "ptm_predict_f32",
-    "ptm_predict_quantile_f64", "ptm_predict_quantile_f32", "ptm_inverse_f64", "ptm_inverse_f32",
+    "ptm_predict_quantile_f64", "ptm_predict_quantile_f32", "ptm_predict_sample_f64", "ptm_predict_sample_f32", "ptm_inverse_f64", "ptm_inverse_f32",
     "ptm_last_launch_count", "ptm_last_main_route", "ptm_last_xtwx_route", "ptm_profile_enable", "ptm_last_kernel_ms", "ptm_last_error",
     "ptm_version",
 ]
@@ -152,6 +152,9 @@ def load() -> C.CDLL:
         f.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, sz, vp]
         f.restype = C.c_int
         f = getattr(lib, f"ptm_predict_quantile_{sfx}")
+        f.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, sz, vp]
+        f.restype = C.c_int
+        f = getattr(lib, f"ptm_predict_sample_{sfx}")
         f.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, sz, vp]
         f.restype = C.c_int
         f = getattr(lib, f"ptm_inverse_{sfx}")

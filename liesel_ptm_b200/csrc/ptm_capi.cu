@@ -808,7 +808,8 @@ size_t predict_ws_bytes(const PtmProblem* pr, long long S) {
 
 template <typename R>
 int predict_impl(const PtmProblem* pr, const R* params, long long S, const R* y_or_u, const R* x_new,
-                 long long m, R* z, R* logpdf, R* cdf, R* yq, void* ws, size_t ws_bytes, void* stream) {
+                 long long m, R* z, R* logpdf, R* cdf, R* yq, void* ws, size_t ws_bytes, void* stream,
+                 bool u_per_sample = false) {
   if (!pr || !params || !y_or_u || !ws) return fail(PTM_ERR_NULL, "null argument");
   if (pr->T > 0 && !x_new) return fail(PTM_ERR_NULL, "x_new is null");
   if (!z && !logpdf && !cdf && !yq) return fail(PTM_ERR_NULL, "no output requested");
@@ -829,6 +830,7 @@ int predict_impl(const PtmProblem* pr, const R* params, long long S, const R* y_
   ptm::PredictArgs<R> a;
   memset(&a, 0, sizeof a);
   a.y = y_or_u; a.X = x_new; a.m = m;
+  a.u_ld = u_per_sample ? m : 0;
   a.knots = reinterpret_cast<const R*>(pr->d_knots);
   a.Gamma = Gamma; a.cc = cc; a.grid = reinterpret_cast<const R*>(pr->d_grid);
   a.S = (int)S; a.T = pr->T; a.KK = pr->KK; a.sum_nb = pr->sum_nb;
@@ -1374,6 +1376,14 @@ int ptm_predict_quantile_f32(const PtmProblem* p, const float* params, int64_t S
                              const float* x_new, int64_t m, float* yq, void* ws, size_t wsb, void* st) {
   if (!yq) return fail(PTM_ERR_NULL, "yq is null");
   return predict_impl<float>(p, params, S, u, x_new, m, nullptr, nullptr, nullptr, yq, ws, wsb, st);
+}
+int ptm_predict_sample_f64(const PtmProblem* p, const double* params, int64_t S, const double* u,
+                           const double* x_new, int64_t m, double* ydraw, void* ws, size_t wsb, void* st) {
+  return predict_impl<double>(p, params, S, u, x_new, m, nullptr, nullptr, nullptr, ydraw, ws, wsb, st, true);
+}
+int ptm_predict_sample_f32(const PtmProblem* p, const float* params, int64_t S, const float* u,
+                           const float* x_new, int64_t m, float* ydraw, void* ws, size_t wsb, void* st) {
+  return predict_impl<float>(p, params, S, u, x_new, m, nullptr, nullptr, nullptr, ydraw, ws, wsb, st, true);
 }
 int ptm_inverse_f64(const PtmProblem* p, const double* delta, int64_t C, const double* z, int64_t m,
                     double* r, void* st) {

@@ -47,6 +47,8 @@ struct PredictArgs {
   R* out_logpdf;
   R* out_cdf;
   R* out_q;        // quantile mode: [S][m]
+  long long u_ld;  // quantile mode: 0 = one probability per row (u [m]); m = one per (sample, row)
+                   // (u [S][m]: predictive draws, TransformationDist._sample_n, dist.py:193-201)
 };
 
 // h(r), h'(r) with the chain's pieces in shared memory [KK*5] (ptm.py:412-478).
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(256) k_predict(const PredictArgs<R> a) {
     }
     const long long oi = (long long)s * a.m + i;
     if constexpr (QUANTILE) {
-      const R u = a.y[i];
+      const R u = a.y[(long long)s * a.u_ld + i];
       const R zq = std_normal_quantile(u);
       const R rq = trafo_inverse(ts, cb, s_H, a.grid, zq);
       a.out_q[oi] = inside ? fma(exp(es), rq, em) : nan;
@@ -306,6 +308,7 @@ __global__ void __launch_bounds__(kPredThreads) k_predict_obs(const PredictArgs<
       }
       const long long oi = (long long)(s0 + g) * a.m + i;
       if constexpr (QUANTILE) {
+        if (a.u_ld) zq = std_normal_quantile(a.y[(long long)(s0 + g) * a.u_ld + i]);
         const R rq = trafo_inverse(ts, s_cb[g], Hall + (long long)(s0 + g) * kGridN, a.grid, zq);
         a.out_q[oi] = inside ? fma(exp(es), rq, em) : nan;
       } else {

@@ -540,6 +540,31 @@ class LocScalePTM:
         return yq
 
     @_on_device
+    def sample(self, samples: torch.Tensor, newdata=None, generator: torch.Generator | None = None,
+               u: torch.Tensor | None = None) -> torch.Tensor:
+        """One predictive draw per (posterior sample, row): init_dist(samples, newdata=...).sample()
+        (TransformationDist._sample_n, dist.py:193-201: u ~ U(eps, 1), then the quantile
+        function).  ``u`` [S, m] may be supplied (e.g. jax.random.uniform with the caller's key)
+        for a reproducible draw; otherwise it is drawn here with ``generator``.  Returns [S, m]."""
+        samples = self._check_params(samples)
+        S = samples.shape[0]
+        m_rows = self.n if newdata is None else len(np.asarray(next(iter(newdata.values()))))
+        eps = float(np.finfo(self.np_dtype).eps)
+        if u is None:
+            u = eps + (1.0 - eps) * torch.rand((S, m_rows), dtype=self.dtype, device=self.device, generator=generator)
+        u = u.to(device=self.device, dtype=self.dtype).contiguous()
+        if u.shape != (S, m_rows):
+            raise ValueError(f"u must have shape ({S}, {m_rows})")
+        _, X, m = self._newdata(newdata, np.full(m_rows, 0.5, dtype=self.np_dtype))
+        ws = torch.empty(max(int(self._lib.ptm_predict_workspace_bytes(self._h, S)), 1),
+                         dtype=torch.uint8, device=self.device)
+        out = torch.empty((S, m), dtype=self.dtype, device=self.device)
+        f = getattr(self._lib, f"ptm_predict_sample_{self._sfx}")
+        _lib.check(f(self._h, samples.data_ptr(), S, u.data_ptr(), X.data_ptr(), m, out.data_ptr(),
+                     ws.data_ptr(), ws.numel(), self._stream()))
+        return out
+
+    @_on_device
     def intercept_stats(self, params: torch.Tensor) -> torch.Tensor:
         """[C, 5] sufficient statistics of the intercept pseudo-Gibbs updates: sum w, sum r,
         sum r^2, sum w^2, sum r w (w = exp(-eta_sigma), r = (y - eta_mu) w) over this handle's
