@@ -29,6 +29,7 @@
 // the TMEM-operand MMA form used here.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 
 #include "ptm_kernels.cuh"
 #include "ptm_xtwx_tc.cuh"
@@ -195,6 +196,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) prev_k[i][0] = prev_k[i][1] = -1;
 
+  // The roles run their own copies of the work-item loop (they meet at the CTA barriers only).
+  auto run_items = [&](auto role_c) {
+  constexpr int ROLE = decltype(role_c)::value;  // 0 = eval warps, 1 = stager / MMA / idle warps
   for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int cb = item / a.M, mchunk = item - cb * a.M;
     const long long o_begin = a.obs_begin + (long long)mchunk * a.chunk_len;
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
     const int cg = cb * 4 + q4;
 
     float beta0 = 0.f, gamma0 = 0.f;
-    if (is_eval) {
+    if constexpr (ROLE == 0) {
       // Gamma hi / lo of the 128 chains -> TMEM (thread = chain, 8 columns per store)
       for (int c0 = sub * 8; c0 < Kt; c0 += 32) {
         uint32_t hi[8], lo[8];
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
+    if constexpr (ROLE == 1) {
     if (is_stager) {
       // ---- design tile: clear what the previous tile wrote, write this tile's four entries
       //      per (term, observation), hi and lo halves
@@ -341,7 +346,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
         }
         __syncwarp();
       }
-    } else if (is_eval) {
+    } else {
+      tg += (uint32_t)ntiles;  // idle warps keep the tile count in step
+    }
+    } else {
       // =========================== eval warp ==========================================
       float* gvp = s_gv + (warp * NGV) * 32 + lane;
       const float* ccl = s_cc + q4 * 32 + lane;
@@ -506,14 +514,19 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
           }
       }
       named_bar(1, kMtcEvalWarps * 32);
-    } else {
-      tg += (uint32_t)ntiles;  // idle warps keep the tile count in step
     }
     // every warp leaves the item with the same tile count
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
+  };
+  // (setmaxnreg 96 / 48 on top of this split was measured slower: 17.6 against 16.7 ms at c3 --
+  //  the stagers spill at 48 registers and their tile fill sits on the serial chain of the
+  //  single-buffered design tile; the register file grants 512-register units per warp, so 104
+  //  for the eval warps does not fit and dead-locks in setmaxnreg.inc)
+  if (is_eval) run_items(std::integral_constant<int, 0>{});
+  else run_items(std::integral_constant<int, 1>{});
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
