@@ -127,6 +127,14 @@ __device__ __forceinline__ float mtc_log(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y * 0.69314718055994530942f;
 }
+// packed float32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: two observations of a chain per
+// instruction in the point-wise part)
+__device__ __forceinline__ float2 p2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 p1(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 psub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 __device__ __forceinline__ void named_bar(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -385,8 +393,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
         if (lane == 0) mtc_arrive(barC);
         float t_z2 = 0.f, t_ls = 0.f, t_gb0 = 0.f, t_gg0 = 0.f, t_ld = 0.f;
         const int cnt = (int)((o_end - base) < OPW ? (o_end - base) : OPW);
-#pragma unroll 2
-        for (int i = 0; i < cnt; ++i) {
+        auto eval_one = [&](int i) {
           const long long gi = base + i;
           {
             const float yv = eb[2 * OPW * 32 + i];
@@ -477,7 +484,160 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
               }
             }
           }
+        };
+        int i0 = 0;
+        if constexpr (GRAD) {
+          // ---- two observations of the chain in lockstep, packed float32x2 arithmetic --------
+          const float2 S1 = p1(ts.ratio), S3 = p1(3.f * ts.ratio), IDK = p1(ts.inv_dk);
+          for (; i0 + 1 < cnt; i0 += 2) {
+            const long long gi = base + i0;
+            const float2 yv = p2(eb[2 * OPW * 32 + i0], eb[2 * OPW * 32 + i0 + 1]);
+            const float2 em = padd(p1(beta0), hasq0 ? p2(eb[i0 * 32 + lane], eb[(i0 + 1) * 32 + lane]) : p1(0.f));
+            const float2 es = padd(p1(gamma0), hasq1 ? p2(eb[(OPW + i0) * 32 + lane], eb[(OPW + i0 + 1) * 32 + lane]) : p1(0.f));
+            // einv = exp(-es): 2^t (1 + e ln 2), t = fl(-es log2 e), e = the recovered rounding error
+            const float2 tt = pmul(es, p1(-1.4426950216293335f));
+            float2 ee = pfma(es, p1(-1.4426950216293335f), p2(-tt.x, -tt.y));
+            ee = pfma(es, p1(-1.9259629911266175e-8f), ee);
+            float2 ex;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(tt.x));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(tt.y));
+            const float2 einv = pfma(ex, pmul(ee, p1(0.69314718055994530942f)), ex);
+            const float2 r = pmul(psub(yv, em), einv);
+            const int code0 = region_code(ts, r.x), code1 = region_code(ts, r.y);
+            const bool core0 = code0 == 2, core1 = code1 == 2;
+            const float rc0 = r.x < ts.a ? ts.a : (r.x > ts.b ? ts.b : (r.x == r.x ? r.x : ts.a));
+            const float rc1 = r.y < ts.a ? ts.a : (r.y > ts.b ? ts.b : (r.y == r.y ? r.y : ts.a));
+            CoreEval<float> e0, e1;
+            core_locate_fast(ts, a.grid, rc0, e0);
+            core_locate_fast(ts, a.grid, rc1, e1);
+            const float* cp0 = ccl + (e0.kk * 5) * 128;
+            const float* cp1 = ccl + (e1.kk * 5) * 128;
+            const float2 c0 = p2(cp0[0], cp1[0]), c1 = p2(cp0[128], cp1[128]), c2 = p2(cp0[256], cp1[256]);
+            const float2 c3 = p2(cp0[384], cp1[384]), jmp = p2(cp0[512], cp1[512]);
+            const float2 u = p2(e0.u, e1.u), kap = p2(e0.kappa, e1.kappa), mm = p2(e0.mm, e1.mm);
+            // core_eval (ptm_math.cuh), two observations per instruction
+            const float2 b2 = pfma(u, c3, c2);
+            const float2 b1 = pfma(u, b2, c1);
+            const float2 P = pfma(u, b1, c0);
+            const float2 d1 = pfma(u, c3, b2);
+            const float2 Pp = pfma(u, d1, b1);
+            const float2 eh = pfma(u, c3, d1);  // P'' / 2
+            const float2 mm2 = pmul(mm, mm);
+            const float2 j3 = pmul(jmp, p1(3.f));
+            const float2 dH = pfma(jmp, pmul(mm2, mm), pmul(S1, pfma(S1, pfma(S1, c3, eh), Pp)));
+            float2 z = pfma(kap, dH, P);
+            const float2 dD = pfma(j3, mm2, pmul(S1, pfma(S3, c3, padd(eh, eh))));
+            float2 d = pmul(pfma(kap, dD, Pp), IDK);
+            const float2 dD2 = pfma(padd(j3, j3), mm, pmul(pmul(S3, p1(2.f)), c3));
+            float2 dddr = pmul(pmul(pfma(kap, dD2, padd(eh, eh)), IDK), IDK);
+            float2 dzdr = d;
+            float cf[2] = {0.f, 0.f}, qf[2] = {0.f, 0.f};
+            if (!(core0 && core1)) {
+              // transitions / tails of either observation: the scalar closed forms (ptm.py:349-410)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int code = h ? code1 : code0;
+                if (code == 2) continue;
+                const float rr = h ? r.y : r.x;
+                float zz, dd, dzr, ddr, cfac = 0.f, qfac = 0.f;
+                if (code == 1) {
+                  const float dL = ccl[(KK * 5 + 1) * 128], constL = ccl[(NCC + 0) * 128];
+                  const float poly = rr * ts.a - 0.5f * rr * rr;
+                  const float t1 = rr - poly * ts.inv_w;
+                  zz = (ts.inv_w * poly + dL * t1) + constL;
+                  const float q = (ts.a - rr) * ts.inv_w;
+                  dd = (1.f - q) * dL + q;
+                  dzr = dd; ddr = (dL - 1.f) * ts.inv_w;
+                  const float poly0 = ts.a * ts.a - 0.5f * ts.a * ts.a;
+                  cfac = t1 - (ts.a - poly0 * ts.inv_w);
+                  qfac = 1.f - q;
+                } else if (code == 3) {
+                  const float dR = ccl[(KK * 5 + 3) * 128], constR = ccl[(NCC + 1) * 128];
+                  const float poly = 0.5f * rr * rr - rr * ts.b;
+                  const float t1 = rr - poly * ts.inv_w;
+                  zz = (ts.inv_w * poly + dR * t1) + constR;
+                  const float q = (rr - ts.b) * ts.inv_w;
+                  dd = (1.f - q) * dR + q;
+                  dzr = dd; ddr = (1.f - dR) * ts.inv_w;
+                  const float poly0 = 0.5f * ts.b * ts.b - ts.b * ts.b;
+                  cfac = t1 - (ts.b - poly0 * ts.inv_w);
+                  qfac = 1.f - q;
+                } else if (code == 0) {
+                  zz = ccl[(NCC + 2) * 128] - (ts.min_eps - rr);
+                  dd = 1.f; dzr = 1.f; ddr = 0.f;
+                  cfac = cL_of(ts, ts.min_eps);
+                } else {
+                  zz = ccl[(NCC + 3) * 128] + (rr - ts.max_eps);
+                  dd = 1.f; dzr = 1.f; ddr = 0.f;
+                  cfac = cR_of(ts, ts.max_eps);
+                }
+                if (h) { z.y = zz; d.y = dd; dzdr.y = dzr; dddr.y = ddr; }
+                else { z.x = zz; d.x = dd; dzdr.x = dzr; dddr.x = ddr; }
+                cf[h] = cfac; qf[h] = qfac;
+              }
+            }
+            const float tiny = tiny_of<float>();
+            const bool ab0 = d.x > tiny, ab1 = d.y > tiny;
+            const float2 dcl = p2(ab0 ? d.x : tiny, ab1 ? d.y : tiny);
+            t_z2 = fmaf(z.x, z.x, t_z2); t_z2 = fmaf(z.y, z.y, t_z2);
+            t_ls += es.x + es.y;
+            t_ld += mtc_log(dcl.x) + mtc_log(dcl.y);
+            const float2 lz = p2(-z.x, -z.y);
+            const float2 ld = p2(ab0 ? mtc_rcp(dcl.x) : 0.f, ab1 ? mtc_rcp(dcl.y) : 0.f);
+            const float2 gr = pfma(lz, dzdr, pmul(ld, dddr));
+            const float2 ngr = p2(-gr.x, -gr.y);
+            const float2 gmu = pmul(ngr, einv);
+            const float2 gls = pfma(ngr, r, p1(-1.f));
+            float* gp2 = Gp + (gi - a.obs_begin) * 256;
+            gp2[0] = gmu.x; gp2[128] = gls.x; gp2[256] = gmu.y; gp2[384] = gls.y;
+            t_gb0 += gmu.x + gmu.y;
+            t_gg0 += gls.x + gls.y;
+            // core_backward (ptm_math.cuh) and the piece -> B-spline coefficient transform
+            const float2 lzc = p2(core0 ? lz.x : 0.f, core1 ? lz.y : 0.f);
+            const float2 ldc = p2(core0 ? ld.x : 0.f, core1 ? ld.y : 0.f);
+            const float2 bq = pmul(ldc, IDK);
+            const float2 u2 = pmul(u, u);
+            const float2 S2 = pmul(S1, S1);
+            const float2 phi1 = pfma(kap, S1, u);
+            const float2 phi2 = pfma(kap, pfma(u, padd(S1, S1), S2), u2);
+            const float2 phi3 = pfma(kap, pfma(u2, S3, pfma(u, pmul(S3, S1), pmul(S2, S1))), pmul(u2, u));
+            const float2 w0 = lzc;
+            const float2 w1 = pfma(lzc, phi1, bq);
+            const float2 w2 = pfma(lzc, phi2, pmul(padd(bq, bq), phi1));
+            const float2 bq3 = pmul(bq, p1(3.f));
+            const float2 w3 = pfma(lzc, phi3, pmul(bq3, phi2));
+            float2 w4 = pmul(kap, pfma(lzc, pmul(mm2, mm), pmul(bq3, mm2)));
+            if (e0.kk + 1 >= KK) w4.x = 0.f;
+            if (e1.kk + 1 >= KK) w4.y = 0.f;
+            const float2 g3 = psub(w3, w4);
+            const float2 SX = p1(sixth), HF = p1(0.5f);
+            const float2 o0 = pfma(psub(w0, g3), SX, pmul(psub(w2, w1), HF));
+            const float2 o1 = padd(psub(pmul(psub(pmul(w0, p1(4.f)), w4), SX), w2), pmul(g3, HF));
+            const float2 o2 = pfma(w0, SX, pmul(padd(psub(padd(w1, w2), g3), w4), HF));
+            const float2 o3 = psub(pmul(g3, SX), pmul(w4, HF));
+            const float2 o4 = pmul(w4, SX);
+            {
+              float* gp = gvp + e0.kk * 32;
+              gp[0] += o0.x; gp[32] += o1.x; gp[64] += o2.x; gp[96] += o3.x; gp[128] += o4.x;
+            }
+            {
+              float* gp = gvp + e1.kk * 32;   // after the first observation's stores: the rows may coincide
+              gp[0] += o0.y; gp[32] += o1.y; gp[64] += o2.y; gp[96] += o3.y; gp[128] += o4.y;
+            }
+            if (!(core0 && core1)) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int code = h ? code1 : code0;
+                if (code == 2) continue;
+                const float lzz = h ? lz.y : lz.x, ldd = h ? ld.y : ld.x;
+                const double dv = (double)fmaf(lzz, cf[h], ldd * qf[h]);
+                if (code <= 1) { a_gvl += (double)lzz; a_gdl += dv; }
+                else { a_gvr += (double)lzz; a_gdr += dv; }
+              }
+            }
+          }
         }
+        for (; i0 < cnt; ++i0) eval_one(i0);
         // per-tile float sums -> double (a tile is at most 16 observations per warp)
         a_z2 += (double)t_z2;
         a_ls += (double)t_ls;
