@@ -314,9 +314,9 @@ int ptm_predict_sample_f32(const PtmProblem* prob, const float* params, int64_t 
                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* r [C, m] with h_c(r) = z for raw shape coefficients delta [C, nparam] and z [m] --
- * TransformationSpline.dot_inverse_n (bspline/util.py:105-122).  Exact inverse of the
- * reference's forward function (lerp cells in the core, quadratic transitions, linear
- * tails); the reference interpolates a 1000-point table with interpax and its tests accept
+ * TransformationSpline.dot_inverse_n (bspline/util.py:105-122).  DEVIATION from the
+ * reference, on purpose: this is the EXACT inverse of the reference's forward function (lerp
+ * cells in the core, quadratic transitions, linear tails); the reference interpolates a 1000-point table with interpax and its tests accept
  * 1e-5 .. 1e-4 (tests/test_bspline/test_ptm.py:167-301). */
 int ptm_inverse_f64(const PtmProblem* prob, const double* delta, int64_t n_chains,
                     const double* z, int64_t m, double* r, void* stream);

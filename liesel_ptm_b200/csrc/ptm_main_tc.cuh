@@ -39,6 +39,10 @@ namespace ptm {
 constexpr int kMtcEvalWarps = 16;  // 4 chain quarters x 4 observation groups
 constexpr int kMtcMaxK = 224;
 constexpr int kGtcKT = 32;         // observations per backward K tile
+#ifndef PTM_GTC_HINT
+#define PTM_GTC_HINT 100   // mbarrier try_wait suspend hint (ns) of k_grad_tc: every wait of that kernel sits
+#define PTM_GTC_SLEEP 0    // on the serial chain copy -> split -> MMA, so its warps poll tightly
+#endif
 constexpr int kGtcStages = 3;      // G tiles in flight (bulk async copies into shared memory)
 constexpr int kGtcTileBytes = kGtcKT * 2 * 128 * 4;  // one G tile: [32 obs][2 predictors][128 chains] floats
 
@@ -91,16 +95,17 @@ __device__ __forceinline__ void mtc_ld4(uint32_t addr, uint32_t (&v)[4]) {
 }
 // Wait on an mbarrier phase with a back-off between polls: a spinning warp would take issue
 // slots from the eval warps of its scheduler (bounded like tc_wait: a protocol bug traps).
+template <int HINT_NS = 2000, int SLEEP_NS = 200>
 __device__ __forceinline__ void mtc_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  for (int it = 0; it < (1 << 22); ++it) {
+  for (int it = 0; it < (1 << 24); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(2000u)
+        : "r"(bar), "r"(parity), "r"((uint32_t)HINT_NS)
         : "memory");
     if (done) return;
-    __nanosleep(200);
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
   }
   __trap();
 }
@@ -819,7 +824,7 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
         const int b = tg & 1;
         const uint32_t use = tg >> 1;
         const uint32_t stg = tg % kGtcStages, sph = (tg / kGtcStages) & 1;
-        mtc_wait(barGf + 8 * stg, sph);
+        mtc_wait<PTM_GTC_HINT, PTM_GTC_SLEEP>(barGf + 8 * stg, sph);
         const float* gs = reinterpret_cast<const float*>(s_G + (size_t)stg * kGtcTileBytes) + q4 * 32 + lane;
         const long long base = o_begin + (long long)s * kGtcKT + sub * 8;
         uint32_t hi[2][8], lo[2][8];
@@ -833,7 +838,7 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
         }
         __syncwarp();
         if (lane == 0) mtc_arrive(barGe + 8 * stg);   // this warp has read the ring slot
-        if (use > 0) mtc_wait(barM + 8 * b, (use - 1) & 1);  // the MMAs that read A buffer b have completed
+        if (use > 0) mtc_wait<PTM_GTC_HINT, PTM_GTC_SLEEP>(barM + 8 * b, (use - 1) & 1);  // the MMAs that read A buffer b have completed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + colA + (uint32_t)(b * 128 + sub * 8);
         mtc_st8(addr, hi[0]);
@@ -847,7 +852,7 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
         ++since;
         if (since == g.flush || s == ntiles - 1) {
           // every MMA issued so far: wait for the commit of THIS tile
-          mtc_wait(barM + 8 * b, use & 1);
+          mtc_wait<PTM_GTC_HINT, PTM_GTC_SLEEP>(barM + 8 * b, use & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           flush_acc(first);
           // (the next tile's MMAs overwrite D only after ALL loader warps have arrived on its
@@ -885,14 +890,28 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) xc[i] = xn[i];
         if (s + 1 < ntiles) fetch_x(s + 1);
-        if (use > 0) mtc_wait(barM + 8 * b, (use - 1) & 1);
         const long long gi = o_begin + (long long)s * kGtcKT + lane;  // lane = observation of the K tile
+        // the basis windows are evaluated BEFORE waiting for the buffer: only the stores sit on
+        // the chain MMA(s) -> refill -> MMA(s + 2)
+        float bbv[4][4];
+        int nrv[4];
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti) {
+          const int t = sidx + ti * NSW;
+          nrv[ti] = -1;
+          if (t < T && gi < o_end) {
+            const float* kn = s_kn + t * 4 * kKnotStride;
+            const int jj = basis_window_fast(xc[ti], kn, kn + kKnotStride, kn + 2 * kKnotStride,
+                                             kn + 3 * kKnotStride, a.nb[t], a.inv_dk[t], bbv[ti]);
+            nrv[ti] = g.ncol[t] + jj;
+          }
+        }
+        if (use > 0) mtc_wait<PTM_GTC_HINT, PTM_GTC_SLEEP>(barM + 8 * b, (use - 1) & 1);
         unsigned char* colp = s_B + b * bufb + (lane >> 2) * 128 + (lane & 3) * 4;
 #pragma unroll
         for (int ti = 0; ti < 4; ++ti) {
           const int t = sidx + ti * NSW;
           if (t >= T) break;
-          const float* kn = s_kn + t * 4 * kKnotStride;
           const int pr = prev_r[ti][b];
           if (pr >= 0) {
 #pragma unroll
@@ -903,19 +922,15 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
               *reinterpret_cast<float*>(e + halfb) = 0.f;
             }
           }
-          int nr = -1;
-          if (gi < o_end) {
-            float bb[4];
-            const int jj = basis_window_fast(xc[ti], kn, kn + kKnotStride, kn + 2 * kKnotStride,
-                                             kn + 3 * kKnotStride, a.nb[t], a.inv_dk[t], bb);
-            nr = g.ncol[t] + jj;
+          const int nr = nrv[ti];
+          if (nr >= 0) {
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
               const int r = nr + m;
-              const float vh = tf32_round(bb[m]);
+              const float vh = tf32_round(bbv[ti][m]);
               unsigned char* e = colp + (r >> 3) * sboB + (r & 7) * 16;
               *reinterpret_cast<float*>(e) = vh;
-              *reinterpret_cast<float*>(e + halfb) = tf32_round(bb[m] - vh);
+              *reinterpret_cast<float*>(e + halfb) = tf32_round(bbv[ti][m] - vh);
             }
           }
           prev_r[ti][b] = nr;
@@ -930,8 +945,8 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
         const int b = tg & 1;
         const uint32_t use = tg >> 1;
         if (lane == 0) {
-          mtc_wait(barA + 8 * b, use & 1);
-          mtc_wait(barBf + 8 * b, use & 1);
+          mtc_wait<PTM_GTC_HINT, PTM_GTC_SLEEP>(barA + 8 * b, use & 1);
+          mtc_wait<PTM_GTC_HINT, PTM_GTC_SLEEP>(barBf + 8 * b, use & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
@@ -959,7 +974,7 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
       for (int s = 0; s < ntiles; ++s, ++tg) {
         const uint32_t stg = tg % kGtcStages, round = tg / kGtcStages;
         if (lane == 0) {
-          if (round > 0) mtc_wait(barGe + 8 * stg, (round - 1) & 1);   // all loader warps have read the slot
+          if (round > 0) mtc_wait<PTM_GTC_HINT, PTM_GTC_SLEEP>(barGe + 8 * stg, (round - 1) & 1);   // all loader warps have read the slot
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barGf + 8 * stg), "r"(kGtcTileBytes)
                        : "memory");
           asm volatile(
