@@ -569,7 +569,7 @@ int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gam
   g.G = G; g.CB = pl.tc_CB; g.Cpad = pl.tc_CB * 128; g.NT = pl.tc_NT; g.NSW = pl.tc_NSW;
   g.mode = want_grad ? ptm::kModeGrad : ptm::kModeLogp;
   g.flush = pr->tune.tc_flush > 0 ? pr->tune.tc_flush : 8;
-  g.NSWb = std::min(pr->T, 11);
+  g.NSWb = std::min(pr->T, 10);  // 16 loader + 10 stager + MMA + copy warps = 896 threads
   const int NGV = pr->KK + 4;
   memset(g.kterm, 255, sizeof g.kterm);
   for (size_t i = 0; i < sizeof g.dslot / sizeof g.dslot[0]; ++i) g.dslot[i] = -1;

@@ -177,6 +177,7 @@ def test_predict_shapes_vs_oracle(n_loc, n_scale, C, m):
         assert rel_err(yq[c], ref) < 1e-11
 
 
+@pytest.mark.gpu
 def test_predictive_draws_are_quantiles_of_per_sample_uniforms():
     """init_dist(samples).sample() (TransformationDist._sample_n, dist.py:193-201): one uniform
     per (posterior sample, row), pushed through the quantile function.  The draw with a given
