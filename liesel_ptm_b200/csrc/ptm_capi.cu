@@ -47,7 +47,7 @@ struct Plan {
   int TPW, NTW;  // smooth terms per term warp, term warps
   long long chunk_len;
   size_t smem_main;
-  size_t off_gamma, off_cc, off_partial, off_xt, off_scratch, off_G, total;
+  size_t off_gamma, off_cc, off_partial, off_xt, off_scratch, off_G, off_red, total;
   // tensor-core route of the float sweep (ptm_main_tc.cuh): its own chunking of the observations
   bool tc = false;
   int tc_NT = 0, tc_NSW = 0, tc_M = 0, tc_CB = 0;
@@ -421,7 +421,10 @@ Plan make_plan(const PtmProblem* pr, long long C) {
         pl.tc = true;
         pl.tc_NT = NT; pl.tc_NSW = NSW;
         pl.tc_CB = (int)((C + 127) / 128);
-        const long long items_per_sm = pr->tune.mtc_items > 0 ? pr->tune.mtc_items : 4;
+        // work items per CTA: every item re-loads Gamma / the piece table and drains the pipeline, so
+        // one wave when there are few chain blocks, two when eight blocks share the SMs (measured:
+        // tools/mtc_chains.py)
+        const long long items_per_sm = pr->tune.mtc_items > 0 ? pr->tune.mtc_items : (pl.tc_CB >= 8 ? 2 : 1);
         long long Mt = std::max<long long>(1, items_per_sm * pr->num_sms / pl.tc_CB);
         Mt = std::min(Mt, std::max<long long>(1, len / (8LL * 192)));
         long long ch = (len + Mt - 1) / Mt;
@@ -440,6 +443,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   pl.off_xt = off;    off = align_up(off + ptm::xtwx_workspace_bytes<R>(std::max(pr->sum_nb, 1), C), 256);
   pl.off_scratch = off; off = align_up(off + (size_t)C * sizeof(R), 256);
   pl.off_G = off;     off = align_up(off + g_bytes, 256);
+  pl.off_red = off;   off = align_up(off + (size_t)pl.CG * pl.NSLOT * 32 * sizeof(double), 256);
   pl.total = off;
   return pl;
 }
@@ -682,15 +686,24 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   }
   if (g_profile) PTM_CUDA(cudaEventRecord(g_ev[2], st));
 
+  // chunk partials -> one row per chain group (many CTAs), then the per-chain epilogue
+  double* red = reinterpret_cast<double*>(wsb + pl.off_red);
+  {
+    const int per = ma.NSLOT * 32;
+    const dim3 rgrid((unsigned)pl.CG, (unsigned)std::max(1, std::min(32, (2 * pr->num_sms + pl.CG - 1) / pl.CG)));
+    ptm::k_reduce_partials<<<rgrid, 256, 0, st>>>(partial, post_M, per, red);
+    PTM_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
   ptm::PostArgs<R> po;
   memset(&po, 0, sizeof po);
-  po.params = params; po.partial = partial; po.logp = logp; po.grad = grad; po.stats = stats;
+  po.params = params; po.partial = red; po.logp = logp; po.grad = grad; po.stats = stats;
   po.ld_logp = ld_logp; po.ld_grad = ld_grad ? ld_grad : pr->P;
   po.Zall = reinterpret_cast<const R*>(pr->d_Zall);
   po.Kall = reinterpret_cast<const R*>(pr->d_Kall);
   po.Zd = reinterpret_cast<const R*>(pr->d_Zd);
   po.tc = reinterpret_cast<const ptm::TrafoConst<double>*>(pr->d_tc64);
-  po.C = (int)C; po.P = pr->P; po.T = pr->T; po.M = post_M; po.NSLOT = ma.NSLOT; po.KK = pr->KK;
+  po.C = (int)C; po.P = pr->P; po.T = pr->T; po.M = 1; po.NSLOT = ma.NSLOT; po.KK = pr->KK;
   for (int t = 0; t < pr->T; ++t) {
     po.nb[t] = pr->nb[t]; po.p[t] = pr->p[t]; po.zoff[t] = pr->zoff[t]; po.koff[t] = pr->koff[t];
     po.boff[t] = pr->boff[t]; po.goff[t] = pr->goff[t]; po.rank[t] = pr->rank[t];

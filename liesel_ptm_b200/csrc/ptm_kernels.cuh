@@ -863,6 +863,22 @@ __global__ void k_pre(const PreArgs<R> a) {
 }
 
 // ------------------------------------------------------------------------------
+// Fixed-order reduction of the work-item partials over the observation chunks,
+//   out[cg][idx] = sum_m partial[cg][m][idx]   (idx over NSLOT x 32 lanes),
+// spread over many CTAs: k_post has one block per chain group only, which is 4 blocks at 128
+// chains per GPU (the strong-scaling share at 8 GPUs) against 592 chunks each.
+// ------------------------------------------------------------------------------
+__global__ void k_reduce_partials(const double* __restrict__ partial, int M, int per, double* __restrict__ out) {
+  const int cg = blockIdx.x;
+  const double* pp = partial + (long long)cg * M * per;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < per; idx += gridDim.y * blockDim.x) {
+    double v = 0.0;  // m ascending: deterministic
+    for (int m = 0; m < M; ++m) v += pp[(long long)m * per + idx];
+    out[(long long)cg * per + idx] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------
 // K_post: fixed-order reduction of the partials + chain rule + priors.
 // One block per chain group.
 // ------------------------------------------------------------------------------
