@@ -192,8 +192,14 @@ def fused_ps(x, nbases: int, xname: str, knots_out: dict, **kwargs):
 # ------------------------------------------------------------------------------------------
 # the operators: ffi_call + custom_vjp
 # ------------------------------------------------------------------------------------------
-def make_operators(prob: FusedProblem, max_chains: int = 4096) -> dict[str, Callable]:
-    """Differentiable ``logp(flat[P])`` and the information operators, vmappable over chains."""
+def make_operators(prob: FusedProblem, max_chains: int = 4) -> dict[str, Callable]:
+    """Differentiable ``logp(flat[P])`` and the information operators, vmappable over chains.
+
+    ``max_chains``: the chain batch the engine will vmap over (``num_chains`` of ``run_mcmc``).
+    XLA sizes result buffers at trace time, so the device workspace every call receives is
+    ``ptm_workspace_bytes(prob, max_chains)``.  On the float32 tensor-core route that includes
+    the dl/deta exchange buffer (8 bytes per observation and chain: 8.2 GB at n = 1M x 1024
+    chains), so pass the real chain count rather than a generous bound."""
     import jax
     import jax.numpy as jnp
 
@@ -332,19 +338,19 @@ class FusedObservedCholInfo:
         return self.ops["hessian_block"](self.interface._flat(model_state), self.block, self.size, self.mode)[1]
 
 
-def install(model, term_knots: dict, strategy_kwargs: dict | None = None) -> FusedProblem:
+def install(model, term_knots: dict, num_chains: int = 4) -> FusedProblem:
     """Everything a ``run_mcmc`` call needs: build the problem from a built reference model,
     register the FFI targets, swap the interface.  Usage::
 
         knots = {}
         model.loc += term.f_ig(fused_ps(x, nbases=20, xname="x", knots_out=knots))
         model.build()
-        fused.install(model, knots)
-        results = model.run_mcmc(seed=1, warmup=300, posterior=500)
+        fused.install(model, knots, num_chains=4)
+        results = model.run_mcmc(seed=1, warmup=300, posterior=500, num_chains=4)
     """
     register_ffi_targets()
     prob = FusedProblem.from_model(model, term_knots)
-    ops = make_operators(prob)
+    ops = make_operators(prob, max_chains=num_chains)
     model.interface = make_interface(model.graph, prob, ops)
     model._fused = (prob, ops)
     return prob
