@@ -50,7 +50,9 @@ struct Plan {
   size_t off_gamma, off_cc, off_partial, off_xt, off_scratch, off_G, off_red, total;
   // tensor-core route of the float sweep (ptm_main_tc.cuh): its own chunking of the observations
   bool tc = false;
+  bool tc_two_pass = false;  // eta_sigma by a first launch (each predictor fits tensor memory, not both)
   int tc_NT = 0, tc_NSW = 0, tc_M = 0, tc_CB = 0;
+  size_t off_E = 0;
   long long tc_chunk = 0;
   size_t tc_smem_fwd = 0, tc_smem_bwd = 0;
 };
@@ -393,7 +395,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   pl.grid = std::min(pl.n_items, pr->num_sms);
   // float problems whose coefficient count fits tensor memory: eta and the coefficient
   // gradients on tcgen05 (ptm_main_tc.cuh)
-  size_t g_bytes = 0;
+  size_t g_bytes = 0, e_bytes = 0;
   long long n_part_items = pl.n_items;
   if (sizeof(R) == 4 && pr->tune.main_tc && T >= 1 && T <= 24) {
     int K8[2] = {0, 0}, K16[2] = {0, 0};
@@ -403,7 +405,12 @@ Plan make_plan(const PtmProblem* pr, long long C) {
       K16[q] += (pr->nb[t] + 3) & ~3;
     }
     for (int q = 0; q < 2; ++q) { K8[q] = (K8[q] + 7) & ~7; K16[q] = (K16[q] + 15) & ~15; }
-    const int Kt = K8[0] + K8[1];
+    // both predictors in tensor memory at once, or -- when only each of them fits -- the
+    // two-pass form: eta_sigma by a first launch, the main launch carries the location terms
+    const bool two_pass = K8[0] + K8[1] > ptm::kMtcMaxK && K8[0] > 0 && K8[1] > 0 &&
+                          K8[0] <= ptm::kMtcMaxK && K8[1] <= ptm::kMtcMaxK;
+    const int Kt = two_pass ? std::max(K8[0], K8[1]) : K8[0] + K8[1];
+    const int K16t = two_pass ? std::max(K16[0], K16[1]) : K16[0] + K16[1];
     const int avail = (512 - 2 * Kt) / 2;
     int NT = avail >= 64 ? 64 : (avail >= 48 ? 48 : (avail >= 32 ? 32 : 0));
     const int NSW = std::min(T, pr->tune.mtc_nsw > 0 ? std::min(pr->tune.mtc_nsw, 7) : 6);
@@ -413,12 +420,13 @@ Plan make_plan(const PtmProblem* pr, long long C) {
              (size_t)ptm::kMtcEvalWarps * (2 * (nt / 4) * 32 + 32) * 4 + 128;
     };
     while (NT > 32 && fwd_smem(NT) > 227 * 1024 - 1280) NT -= 16;
-    if (Kt <= ptm::kMtcMaxK && NT > 0 && K16[0] + K16[1] <= 256 && len > 0) {
+    if (Kt <= ptm::kMtcMaxK && NT > 0 && K16t <= 256 && len > 0) {
       pl.tc_smem_fwd = fwd_smem(NT);
-      pl.tc_smem_bwd = (size_t)2 * 2 * (K16[0] + K16[1]) * ptm::kGtcKT * 4 + (size_t)T * 4 * ptm::kKnotStride * 4 +
+      pl.tc_smem_bwd = (size_t)2 * 2 * K16t * ptm::kGtcKT * 4 + (size_t)T * 4 * ptm::kKnotStride * 4 +
                        (size_t)ptm::kGtcStages * ptm::kGtcTileBytes + 256;
       if (pl.tc_smem_fwd <= 227 * 1024 - 1280 && pl.tc_smem_bwd <= 227 * 1024 - 1280) {
         pl.tc = true;
+        pl.tc_two_pass = two_pass;
         pl.tc_NT = NT; pl.tc_NSW = NSW;
         pl.tc_CB = (int)((C + 127) / 128);
         // work items per CTA: every item re-loads Gamma / the piece table and drains the pipeline, so
@@ -433,6 +441,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
         pl.tc_M = (int)Mt; pl.tc_chunk = ch;
         n_part_items = std::max<long long>(n_part_items, (long long)pl.CG * Mt);
         g_bytes = (size_t)(len + ptm::kGtcKT) * 2 * (size_t)pl.tc_CB * 128 * 4;  // one backward tile of padding per block
+        if (two_pass) e_bytes = (size_t)(len + ptm::kGtcKT) * (size_t)pl.tc_CB * 128 * 4;
       }
     }
   }
@@ -444,6 +453,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
   pl.off_scratch = off; off = align_up(off + (size_t)C * sizeof(R), 256);
   pl.off_G = off;     off = align_up(off + g_bytes, 256);
   pl.off_red = off;   off = align_up(off + (size_t)pl.CG * pl.NSLOT * 32 * sizeof(double), 256);
+  pl.off_E = off;     off = align_up(off + e_bytes, 256);
   pl.total = off;
   return pl;
 }
@@ -558,10 +568,36 @@ int check_device(const PtmProblem* pr) {
 
 bool is_sharded(const PtmProblem* pr) { return pr->obs_begin != 0 || pr->obs_end != pr->n || !pr->add_priors; }
 
+// K-column / D-column tables of the terms of the predictors in `mask` (bit 0 = location, bit 1 =
+// scale): forward K columns padded to 8 per predictor block, backward D columns to 16.
+void fill_tc_tables(const PtmProblem* pr, int mask, ptm::MainTcArgs& g) {
+  const int NGV = pr->KK + 4;
+  memset(g.kterm, 255, sizeof g.kterm);
+  for (size_t i = 0; i < sizeof g.dslot / sizeof g.dslot[0]; ++i) g.dslot[i] = -1;
+  for (int t = 0; t < ptm::kMaxTerms; ++t) g.kcol[t] = g.ncol[t] = -1;  // -1: the term is not in this launch
+  int k = 0, n = 0;
+  for (int q = 0; q < 2; ++q) {
+    g.kbase[q] = k; g.nbase[q] = n;
+    if (mask & (1 << q))
+      for (int t = 0; t < pr->T; ++t) {
+        if ((pr->pred[t] == PTM_LOC ? 0 : 1) != q) continue;
+        g.kcol[t] = k; g.ncol[t] = n;
+        for (int j = 0; j < pr->nb[t]; ++j) {
+          g.kterm[k + j] = (unsigned char)t; g.kj[k + j] = (unsigned char)j;
+          g.dslot[n + j] = (short)(ptm::kRegSlots + NGV + pr->goff[t] + j);
+        }
+        k += (pr->nb[t] + 3) & ~3; n += (pr->nb[t] + 3) & ~3;
+      }
+    k = (k + 7) & ~7; n = (n + 15) & ~15;
+    g.Kq[q] = k - g.kbase[q]; g.Nq[q] = n - g.nbase[q];
+  }
+  g.Kt = k;
+}
+
 // Tensor-core route of the float sweep: k_main_tc (+ k_grad_tc when the gradient is wanted).
 // Returns PTM_OK or an error; the caller has checked pl.tc.
 int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gamma, float* cc, double* partial,
-                   float* G, bool want_grad, cudaStream_t st) {
+                   float* G, float* E, bool want_grad, cudaStream_t st) {
   static thread_local ptm::MainTcArgs g;  // 3 KB of launch arguments: keep it off the stack hot path
   memset(&g, 0, sizeof g);
   Plan plc = pl;
@@ -570,59 +606,60 @@ int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gam
   g.a.shared = 0;
   if (!want_grad) g.a.NSLOT = ptm::kLogpSlots;
   g.Gld = std::max<long long>(pr->obs_end - pr->obs_begin, 0) + ptm::kGtcKT;
-  g.G = G; g.CB = pl.tc_CB; g.Cpad = pl.tc_CB * 128; g.NT = pl.tc_NT; g.NSW = pl.tc_NSW;
+  g.G = G; g.E = E; g.CB = pl.tc_CB; g.Cpad = pl.tc_CB * 128; g.NT = pl.tc_NT; g.NSW = pl.tc_NSW;
   g.mode = want_grad ? ptm::kModeGrad : ptm::kModeLogp;
   g.flush = pr->tune.tc_flush > 0 ? pr->tune.tc_flush : 8;
   g.NSWb = std::min(pr->T, 10);  // 16 loader + 10 stager + MMA + copy warps = 896 threads
-  const int NGV = pr->KK + 4;
-  memset(g.kterm, 255, sizeof g.kterm);
-  for (size_t i = 0; i < sizeof g.dslot / sizeof g.dslot[0]; ++i) g.dslot[i] = -1;
-  int k = 0, n = 0;
-  for (int q = 0; q < 2; ++q) {
-    g.kbase[q] = k; g.nbase[q] = n;
-    for (int t = 0; t < pr->T; ++t) {
-      if ((pr->pred[t] == PTM_LOC ? 0 : 1) != q) continue;
-      g.kcol[t] = k; g.ncol[t] = n;
-      for (int j = 0; j < pr->nb[t]; ++j) {
-        g.kterm[k + j] = (unsigned char)t; g.kj[k + j] = (unsigned char)j;
-        g.dslot[n + j] = (short)(ptm::kRegSlots + NGV + pr->goff[t] + j);
-      }
-      k += (pr->nb[t] + 3) & ~3; n += (pr->nb[t] + 3) & ~3;
-    }
-    k = (k + 7) & ~7; n = (n + 15) & ~15;
-    g.Kq[q] = k - g.kbase[q]; g.Nq[q] = n - g.nbase[q];
-  }
-  g.Kt = k;
   const int threads = 32 * ((ptm::kMtcEvalWarps + pl.tc_NSW + 1 + 3) / 4 * 4);
   const int grid = std::min(plc.n_items, pr->num_sms);
-#define PTM_MTC_LAUNCH2(NTV, GR, MT)                                                   \
+#define PTM_MTC_LAUNCH2(NTV, GR, MT, EO)                                               \
   do {                                                                                 \
-    auto kern = ptm::k_main_tc<NTV, GR, MT>;                                           \
+    auto kern = ptm::k_main_tc<NTV, GR, MT, EO>;                                       \
     PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_fwd));                                  \
     kern<<<grid, threads, pl.tc_smem_fwd, st>>>(g);                                    \
   } while (0)
-#define PTM_MTC_LAUNCH(NTV)                                                            \
+#define PTM_MTC_LAUNCH(NTV, EO)                                                        \
   do {                                                                                 \
-    if (threads <= 640) {                                                              \
-      if (want_grad) PTM_MTC_LAUNCH2(NTV, true, 640); else PTM_MTC_LAUNCH2(NTV, false, 640); \
+    if constexpr (EO) {  /* the eta-only launch has no gradient form */                \
+      if (threads <= 640) PTM_MTC_LAUNCH2(NTV, false, 640, true); else PTM_MTC_LAUNCH2(NTV, false, 768, true); \
+    } else if (threads <= 640) {                                                       \
+      if (want_grad) PTM_MTC_LAUNCH2(NTV, true, 640, false); else PTM_MTC_LAUNCH2(NTV, false, 640, false); \
     } else {                                                                           \
-      if (want_grad) PTM_MTC_LAUNCH2(NTV, true, 768); else PTM_MTC_LAUNCH2(NTV, false, 768); \
+      if (want_grad) PTM_MTC_LAUNCH2(NTV, true, 768, false); else PTM_MTC_LAUNCH2(NTV, false, 768, false); \
     }                                                                                  \
   } while (0)
-  if (pl.tc_NT == 64) PTM_MTC_LAUNCH(64);
-  else if (pl.tc_NT == 48) PTM_MTC_LAUNCH(48);
-  else PTM_MTC_LAUNCH(32);
+#define PTM_MTC_LAUNCH_NT(EO)                                                          \
+  do {                                                                                 \
+    if (pl.tc_NT == 64) PTM_MTC_LAUNCH(64, EO);                                        \
+    else if (pl.tc_NT == 48) PTM_MTC_LAUNCH(48, EO);                                   \
+    else PTM_MTC_LAUNCH(32, EO);                                                       \
+    PTM_CUDA(cudaGetLastError());                                                      \
+    ++g_launches;                                                                      \
+  } while (0)
+  if (pl.tc_two_pass) {
+    fill_tc_tables(pr, 2, g);   // scale terms: eta_sigma -> E
+    g.ext_sigma = 0;
+    PTM_MTC_LAUNCH_NT(true);
+    fill_tc_tables(pr, 1, g);   // location terms on the tensor cores, eta_sigma from E
+    g.ext_sigma = 1;
+    PTM_MTC_LAUNCH_NT(false);
+  } else {
+    fill_tc_tables(pr, 3, g);
+    PTM_MTC_LAUNCH_NT(false);
+  }
+#undef PTM_MTC_LAUNCH_NT
 #undef PTM_MTC_LAUNCH
 #undef PTM_MTC_LAUNCH2
-  PTM_CUDA(cudaGetLastError());
-  ++g_launches;
   if (want_grad) {
     auto kern = ptm::k_grad_tc;
     PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_bwd));
     const int threads_b = 32 * ((ptm::kMtcEvalWarps + g.NSWb + 2 + 3) / 4 * 4);  // loaders, stagers, MMA, copy
-    kern<<<grid, threads_b, pl.tc_smem_bwd, st>>>(g);
-    PTM_CUDA(cudaGetLastError());
-    ++g_launches;
+    for (int pass = 0; pass < (pl.tc_two_pass ? 2 : 1); ++pass) {
+      if (pl.tc_two_pass) fill_tc_tables(pr, 1 << pass, g);  // one predictor block of dGamma per launch
+      kern<<<grid, threads_b, pl.tc_smem_bwd, st>>>(g);
+      PTM_CUDA(cudaGetLastError());
+      ++g_launches;
+    }
   }
   return PTM_OK;
 }
@@ -667,7 +704,8 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   if constexpr (sizeof(R) == 4) {
     if (pl.tc) {
       rc = launch_main_tc(pr, pl, C, reinterpret_cast<float*>(Gamma), reinterpret_cast<float*>(cc), partial,
-                          reinterpret_cast<float*>(wsb + pl.off_G), want_grad, st);
+                          reinterpret_cast<float*>(wsb + pl.off_G), reinterpret_cast<float*>(wsb + pl.off_E),
+                          want_grad, st);
       if (rc != PTM_OK) return rc;
       post_M = pl.tc_M;
       took_tc = true;

@@ -34,6 +34,9 @@
 #include "ptm_kernels.cuh"
 #include "ptm_xtwx_tc.cuh"
 
+// the eta-only instantiation of k_main_tc leaves the point-wise accumulators unreferenced
+#pragma nv_diag_suppress 177
+
 namespace ptm {
 
 constexpr int kMtcEvalWarps = 16;  // 4 chain quarters x 4 observation groups
@@ -64,6 +67,11 @@ struct MainTcArgs {
   short dslot[2 * kMtcMaxK + 32];  // D column -> partial slot (-1 = padding)
   int flush;           // backward tiles between promotions to double
   int mode;            // kModeLogp / kModeGrad
+  // two-pass form for models whose two predictors do not fit tensor memory together (each
+  // K_q <= 224): a first launch writes eta_sigma of every (chain, observation) to HBM
+  // (ETAONLY kernel), the main launch takes eta_mu from the tensor cores and eta_sigma from there
+  float* E;            // [CB][Gld][128] eta_sigma; written by the ETAONLY launch, read when ext_sigma
+  int ext_sigma;
 };
 
 __device__ __forceinline__ void mtc_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -123,6 +131,8 @@ __device__ __forceinline__ float mtc_exp(float x) {
   return fmaf(y, e * 0.69314718055994530942f, y);
 }
 __device__ __forceinline__ float mtc_rcp(float x) {
+  // (a Newton step on top changes nothing measurable: the float gradient error of this route
+  //  sits in the f32 accumulation of G'B on the tensor cores, tools/mtc_acc.py)
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
@@ -147,7 +157,7 @@ __device__ __forceinline__ void named_bar(int id, int threads) {
 // ---------------------------------------------------------------------------------------
 // forward + point-wise part
 // ---------------------------------------------------------------------------------------
-template <int NT, bool GRAD, int MAXT>
+template <int NT, bool GRAD, int MAXT, bool ETAONLY = false>
 __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
   const MainArgs<float>& a = g.a;
   constexpr int OPW = NT / 4;  // observations per eval warp and tile
@@ -222,6 +232,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
     int chain = cb * 128 + q4 * 32 + lane;
     if (chain >= a.C) chain = a.C - 1;
     const int cg = cb * 4 + q4;
+    (void)cg;
 
     float beta0 = 0.f, gamma0 = 0.f;
     if constexpr (ROLE == 0) {
@@ -295,6 +306,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
         for (int ti = 0; ti < 8; ++ti) {
           const int t = sidx + ti * NSW;
           if (t >= T) break;
+          if (g.kcol[t] < 0) continue;  // two-pass form: the term belongs to the other launch
           const float* kn = s_kn + t * 4 * kKnotStride;
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
@@ -366,20 +378,48 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
       // =========================== eval warp ==========================================
       float* gvp = s_gv + (warp * NGV) * 32 + lane;
       const float* ccl = s_cc + q4 * 32 + lane;
+      (void)gvp; (void)ccl;
       double a_z2 = 0, a_ls = 0, a_gb0 = 0, a_gg0 = 0, a_gvl = 0, a_gdl = 0, a_gvr = 0, a_gdr = 0;
       double a_logd = 0;
       const float sixth = 1.f / 6.f;
-      const bool hasq0 = g.Kq[0] > 0, hasq1 = g.Kq[1] > 0;
+      const bool hasq0 = g.Kq[0] > 0, ext = g.ext_sigma != 0, hasq1 = g.Kq[1] > 0 || ext;
       float* Gp = g.G + (long long)cb * g.Gld * 256 + q4 * 32 + lane;
+      float* Ep = g.E + (long long)cb * g.Gld * 128 + q4 * 32 + lane;
       for (int s = 0; s < ntiles; ++s, ++tg) {
         const long long base = o_begin + (long long)s * NT + sub * OPW;
         // this warp's responses of the tile: one coalesced load, in flight while eta is waited for
         float yreg = 0.f;
         if (lane < OPW && base + lane < o_end) yreg = a.y[base + lane];
+        float ev_ext[OPW];  // eta_sigma of the first launch (two-pass form), also in flight during the wait
+#pragma unroll
+        for (int c = 0; c < OPW; ++c) ev_ext[c] = 0.f;
+        if (!ETAONLY && ext) {
+#pragma unroll
+          for (int c = 0; c < OPW; ++c)
+            if (base + c < o_end) ev_ext[c] = __ldcs(Ep + (base + c - a.obs_begin) * 128);
+        }
         mtc_wait(barE, tg & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + etaCol + (uint32_t)(sub * OPW);
         float* eb = s_eta + warp * (2 * OPW * 32 + 32);
+        (void)eb;
+        if constexpr (ETAONLY) {
+          // eta of the one predictor this launch carries -> HBM, nothing else
+          const uint32_t ecol = addr + (g.Kq[0] > 0 ? 0u : (uint32_t)NT);
+#pragma unroll
+          for (int c = 0; c < OPW; c += 4) {
+            uint32_t v[4];
+            mtc_ld4(ecol + c, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (base + c + j < o_end) Ep[(base + c + j - a.obs_begin) * 128] = __uint_as_float(v[j]);
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mtc_arrive(barC);
+        }
+        if constexpr (!ETAONLY) {
 #pragma unroll
         for (int c = 0; c < OPW; c += 4) {
           uint32_t v[4], w[4];
@@ -389,7 +429,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             eb[(c + j) * 32 + lane] = __uint_as_float(v[j]);
-            eb[(OPW + c + j) * 32 + lane] = __uint_as_float(w[j]);
+            eb[(OPW + c + j) * 32 + lane] = ext ? ev_ext[c + j] : __uint_as_float(w[j]);
           }
         }
         if (lane < OPW) eb[2 * OPW * 32 + lane] = yreg;
@@ -648,7 +688,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
         a_ls += (double)t_ls;
         if (GRAD) { a_gb0 += (double)t_gb0; a_gg0 += (double)t_gg0; }
         a_logd += (double)t_ld;
+        }  // !ETAONLY
       }
+      if constexpr (!ETAONLY) {
       double* rp = s_red + (warp * kRegSlots) * 32 + lane;
       rp[SL_Z2 * 32] = a_z2;
       rp[SL_LS * 32] = a_ls;
@@ -679,6 +721,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
           }
       }
       named_bar(1, kMtcEvalWarps * 32);
+      }
     }
     // every warp leaves the item with the same tile count
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -899,7 +942,7 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
         for (int ti = 0; ti < 4; ++ti) {
           const int t = sidx + ti * NSW;
           nrv[ti] = -1;
-          if (t < T && gi < o_end) {
+          if (t < T && gi < o_end && g.ncol[t] >= 0) {
             const float* kn = s_kn + t * 4 * kKnotStride;
             const int jj = basis_window_fast(xc[ti], kn, kn + kKnotStride, kn + 2 * kKnotStride,
                                              kn + 3 * kKnotStride, a.nb[t], a.inv_dk[t], bbv[ti]);
@@ -998,3 +1041,5 @@ __global__ void __launch_bounds__(896, 1) k_grad_tc(const MainTcArgs g) {
 }
 
 }  // namespace ptm
+
+#pragma nv_diag_default 177

@@ -28,6 +28,8 @@ SHAPES = [
     dict(n=50, n_loc=0, n_scale=1, nbases=20, C=257),       # scale terms only, three chain blocks
     dict(n=1, n_loc=1, n_scale=1, nbases=8, C=1),
     dict(n=6000, n_loc=4, n_scale=3, nbases=24, C=33),      # K = 168: 48-observation tiles
+    dict(n=7000, n_loc=10, n_scale=10, nbases=20, C=40),    # the c5 term structure: K = 200 + 200, two-pass form
+    dict(n=3000, n_loc=7, n_scale=2, nbases=30, C=129),     # K = 224 + 64: two-pass, unequal blocks
 ]
 
 
@@ -68,7 +70,7 @@ def test_tc_route_selection(monkeypatch):
     f64 = build_case(n=700, n_loc=2, n_scale=1, nbases=12, C=4, dtype=np.float64)
     f64.model.log_prob(torch.from_numpy(f64.params).cuda())
     assert f64.model.last_main_route() == "cuda-core"
-    big = build_case(n=700, n_loc=8, n_scale=2, nbases=30, C=4, dtype=np.float32)   # K = 320 > 224
+    big = build_case(n=700, n_loc=8, n_scale=2, nbases=30, C=4, dtype=np.float32)   # K_loc = 256 > 224
     pb = torch.from_numpy(big.params).cuda()
     lp, g = big.model.log_prob_and_grad(pb)
     assert big.model.last_main_route() == "cuda-core"
