@@ -50,7 +50,11 @@ struct Plan {
   size_t off_gamma, off_cc, off_partial, off_xt, off_scratch, off_G, off_red, total;
   // tensor-core route of the float sweep (ptm_main_tc.cuh): its own chunking of the observations
   bool tc = false;
-  bool tc_two_pass = false;  // eta_sigma by a first launch (each predictor fits tensor memory, not both)
+  // launches of the tensor-core sweep: term masks of the eta-only groups (one predictor each, <= 224
+  // coefficients) followed by the main group; ext_mask = predictors with an external part
+  int tc_npass = 0;
+  unsigned tc_terms[8] = {0};
+  int tc_ext_mask = 0;
   int tc_NT = 0, tc_NSW = 0, tc_M = 0, tc_CB = 0;
   size_t off_E = 0;
   long long tc_chunk = 0;
@@ -405,28 +409,64 @@ Plan make_plan(const PtmProblem* pr, long long C) {
       K16[q] += (pr->nb[t] + 3) & ~3;
     }
     for (int q = 0; q < 2; ++q) { K8[q] = (K8[q] + 7) & ~7; K16[q] = (K16[q] + 15) & ~15; }
-    // both predictors in tensor memory at once, or -- when only each of them fits -- the
-    // two-pass form: eta_sigma by a first launch, the main launch carries the location terms
-    const bool two_pass = K8[0] + K8[1] > ptm::kMtcMaxK && K8[0] > 0 && K8[1] > 0 &&
-                          K8[0] <= ptm::kMtcMaxK && K8[1] <= ptm::kMtcMaxK;
-    const int Kt = two_pass ? std::max(K8[0], K8[1]) : K8[0] + K8[1];
-    const int K16t = two_pass ? std::max(K16[0], K16[1]) : K16[0] + K16[1];
+    // Groups of terms per launch.  Everything in one launch when the coefficients fit tensor
+    // memory (2 K columns for Gamma hi / lo); otherwise eta-only launches peel off groups of
+    // <= 224 coefficients of one predictor (largest predictor first) until the rest fits.
+    unsigned groups[8] = {0};
+    int ngroups = 0, ext_mask = 0, Kt = 0, K16t = 0;
+    bool groups_ok = true;
+    {
+      int nb4[ptm::kMaxTerms];
+      bool left[ptm::kMaxTerms];
+      int rest[2] = {0, 0};
+      for (int t = 0; t < T; ++t) {
+        nb4[t] = (pr->nb[t] + 3) & ~3;
+        left[t] = true;
+        rest[pr->pred[t] == PTM_LOC ? 0 : 1] += nb4[t];
+      }
+      auto pad8 = [](int v) { return (v + 7) & ~7; };
+      while (pad8(rest[0]) + pad8(rest[1]) > ptm::kMtcMaxK) {
+        if (ngroups >= 7) { groups_ok = false; break; }
+        const int q = rest[0] >= rest[1] ? 0 : 1;
+        unsigned m = 0;
+        int k = 0;
+        for (int t = 0; t < T; ++t)
+          if (left[t] && (pr->pred[t] == PTM_LOC ? 0 : 1) == q && k + nb4[t] <= ptm::kMtcMaxK) {
+            m |= 1u << t; k += nb4[t]; left[t] = false;
+          }
+        if (!m) { groups_ok = false; break; }
+        rest[q] -= k;
+        groups[ngroups++] = m;
+        ext_mask |= 1 << q;
+        Kt = std::max(Kt, pad8(k));
+        K16t = std::max(K16t, (k + 15) & ~15);
+      }
+      unsigned m = 0;
+      for (int t = 0; t < T; ++t) if (left[t]) m |= 1u << t;
+      groups[ngroups++] = m;  // the main launch (may be empty of terms: every term went external)
+      Kt = std::max(Kt, pad8(rest[0]) + pad8(rest[1]));
+      K16t = std::max(K16t, ((rest[0] + 15) & ~15) + ((rest[1] + 15) & ~15));
+    }
+    const bool two_pass = ngroups > 1;
     const int avail = (512 - 2 * Kt) / 2;
     int NT = avail >= 64 ? 64 : (avail >= 48 ? 48 : (avail >= 32 ? 32 : 0));
     const int NSW = std::min(T, pr->tune.mtc_nsw > 0 ? std::min(pr->tune.mtc_nsw, 7) : 6);
     auto fwd_smem = [&](int nt) {
       return (size_t)2 * nt * Kt * 4 + (size_t)(NCC + 4) * 128 * 4 + (size_t)ptm::kMtcEvalWarps * NGV * 32 * 4 +
-             (size_t)T * 4 * ptm::kKnotStride * 4 + (size_t)ptm::kMtcEvalWarps * ptm::kRegSlots * 32 * 8 +
-             (size_t)ptm::kMtcEvalWarps * (2 * (nt / 4) * 32 + 32) * 4 + 128;
+             (size_t)T * 4 * ptm::kKnotStride * 4 +
+             std::max((size_t)ptm::kMtcEvalWarps * ptm::kRegSlots * 32 * 8,            // reduction scratch, aliased
+                      (size_t)ptm::kMtcEvalWarps * (2 * (nt / 4) * 32 + 32) * 4) + 128;  // onto the eta buffers
     };
     while (NT > 32 && fwd_smem(NT) > 227 * 1024 - 1280) NT -= 16;
-    if (Kt <= ptm::kMtcMaxK && NT > 0 && K16t <= 256 && len > 0) {
+    if (groups_ok && Kt <= ptm::kMtcMaxK && NT > 0 && K16t <= 256 && len > 0) {
       pl.tc_smem_fwd = fwd_smem(NT);
       pl.tc_smem_bwd = (size_t)2 * 2 * K16t * ptm::kGtcKT * 4 + (size_t)T * 4 * ptm::kKnotStride * 4 +
                        (size_t)ptm::kGtcStages * ptm::kGtcTileBytes + 256;
       if (pl.tc_smem_fwd <= 227 * 1024 - 1280 && pl.tc_smem_bwd <= 227 * 1024 - 1280) {
         pl.tc = true;
-        pl.tc_two_pass = two_pass;
+        pl.tc_npass = ngroups;
+        for (int i = 0; i < ngroups; ++i) pl.tc_terms[i] = groups[i];
+        pl.tc_ext_mask = ext_mask;
         pl.tc_NT = NT; pl.tc_NSW = NSW;
         pl.tc_CB = (int)((C + 127) / 128);
         // work items per CTA: every item re-loads Gamma / the piece table and drains the pipeline, so
@@ -441,7 +481,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
         pl.tc_M = (int)Mt; pl.tc_chunk = ch;
         n_part_items = std::max<long long>(n_part_items, (long long)pl.CG * Mt);
         g_bytes = (size_t)(len + ptm::kGtcKT) * 2 * (size_t)pl.tc_CB * 128 * 4;  // one backward tile of padding per block
-        if (two_pass) e_bytes = (size_t)(len + ptm::kGtcKT) * (size_t)pl.tc_CB * 128 * 4;
+        if (two_pass) e_bytes = 2 * (size_t)(len + ptm::kGtcKT) * (size_t)pl.tc_CB * 128 * 4;  // E[0], E[1]
       }
     }
   }
@@ -568,9 +608,9 @@ int check_device(const PtmProblem* pr) {
 
 bool is_sharded(const PtmProblem* pr) { return pr->obs_begin != 0 || pr->obs_end != pr->n || !pr->add_priors; }
 
-// K-column / D-column tables of the terms of the predictors in `mask` (bit 0 = location, bit 1 =
-// scale): forward K columns padded to 8 per predictor block, backward D columns to 16.
-void fill_tc_tables(const PtmProblem* pr, int mask, ptm::MainTcArgs& g) {
+// K-column / D-column tables of the terms in `term_mask`: forward K columns padded to 8 per
+// predictor block, backward D columns to 16.
+void fill_tc_tables(const PtmProblem* pr, unsigned term_mask, ptm::MainTcArgs& g) {
   const int NGV = pr->KK + 4;
   memset(g.kterm, 255, sizeof g.kterm);
   for (size_t i = 0; i < sizeof g.dslot / sizeof g.dslot[0]; ++i) g.dslot[i] = -1;
@@ -578,9 +618,9 @@ void fill_tc_tables(const PtmProblem* pr, int mask, ptm::MainTcArgs& g) {
   int k = 0, n = 0;
   for (int q = 0; q < 2; ++q) {
     g.kbase[q] = k; g.nbase[q] = n;
-    if (mask & (1 << q))
+    {
       for (int t = 0; t < pr->T; ++t) {
-        if ((pr->pred[t] == PTM_LOC ? 0 : 1) != q) continue;
+        if ((pr->pred[t] == PTM_LOC ? 0 : 1) != q || !(term_mask & (1u << t))) continue;
         g.kcol[t] = k; g.ncol[t] = n;
         for (int j = 0; j < pr->nb[t]; ++j) {
           g.kterm[k + j] = (unsigned char)t; g.kj[k + j] = (unsigned char)j;
@@ -588,6 +628,7 @@ void fill_tc_tables(const PtmProblem* pr, int mask, ptm::MainTcArgs& g) {
         }
         k += (pr->nb[t] + 3) & ~3; n += (pr->nb[t] + 3) & ~3;
       }
+    }
     k = (k + 7) & ~7; n = (n + 15) & ~15;
     g.Kq[q] = k - g.kbase[q]; g.Nq[q] = n - g.nbase[q];
   }
@@ -606,7 +647,7 @@ int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gam
   g.a.shared = 0;
   if (!want_grad) g.a.NSLOT = ptm::kLogpSlots;
   g.Gld = std::max<long long>(pr->obs_end - pr->obs_begin, 0) + ptm::kGtcKT;
-  g.G = G; g.E = E; g.CB = pl.tc_CB; g.Cpad = pl.tc_CB * 128; g.NT = pl.tc_NT; g.NSW = pl.tc_NSW;
+  g.G = G; g.E[0] = g.E[1] = E; g.CB = pl.tc_CB; g.Cpad = pl.tc_CB * 128; g.NT = pl.tc_NT; g.NSW = pl.tc_NSW;
   g.mode = want_grad ? ptm::kModeGrad : ptm::kModeLogp;
   g.flush = pr->tune.tc_flush > 0 ? pr->tune.tc_flush : 8;
   g.NSWb = std::min(pr->T, 10);  // 16 loader + 10 stager + MMA + copy warps = 896 threads
@@ -636,17 +677,25 @@ int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gam
     PTM_CUDA(cudaGetLastError());                                                      \
     ++g_launches;                                                                      \
   } while (0)
-  if (pl.tc_two_pass) {
-    fill_tc_tables(pr, 2, g);   // scale terms: eta_sigma -> E
-    g.ext_sigma = 0;
-    PTM_MTC_LAUNCH_NT(true);
-    fill_tc_tables(pr, 1, g);   // location terms on the tensor cores, eta_sigma from E
-    g.ext_sigma = 1;
-    PTM_MTC_LAUNCH_NT(false);
-  } else {
-    fill_tc_tables(pr, 3, g);
-    PTM_MTC_LAUNCH_NT(false);
+  size_t e_stride = 0;
+  {
+    const long long len = std::max<long long>(pr->obs_end - pr->obs_begin, 0);
+    e_stride = (size_t)(len + ptm::kGtcKT) * (size_t)pl.tc_CB * 128;
   }
+  g.E[0] = E; g.E[1] = E + e_stride;
+  bool seen[2] = {false, false};
+  for (int i = 0; i + 1 < pl.tc_npass; ++i) {   // eta-only launches: one predictor's group each
+    fill_tc_tables(pr, pl.tc_terms[i], g);
+    const int q = g.Kq[0] > 0 ? 0 : 1;
+    g.e_acc = seen[q] ? 1 : 0;
+    g.ext_mask = 0;
+    seen[q] = true;
+    PTM_MTC_LAUNCH_NT(true);
+  }
+  fill_tc_tables(pr, pl.tc_terms[pl.tc_npass - 1], g);
+  g.e_acc = 0;
+  g.ext_mask = pl.tc_ext_mask;
+  PTM_MTC_LAUNCH_NT(false);
 #undef PTM_MTC_LAUNCH_NT
 #undef PTM_MTC_LAUNCH
 #undef PTM_MTC_LAUNCH2
@@ -654,8 +703,11 @@ int launch_main_tc(const PtmProblem* pr, const Plan& pl, long long C, float* Gam
     auto kern = ptm::k_grad_tc;
     PTM_CUDA(ptm::ensure_smem(kern, pl.tc_smem_bwd));
     const int threads_b = 32 * ((ptm::kMtcEvalWarps + g.NSWb + 2 + 3) / 4 * 4);  // loaders, stagers, MMA, copy
-    for (int pass = 0; pass < (pl.tc_two_pass ? 2 : 1); ++pass) {
-      if (pl.tc_two_pass) fill_tc_tables(pr, 1 << pass, g);  // one predictor block of dGamma per launch
+    for (int i = 0; i < pl.tc_npass; ++i) {   // one launch per group: its blocks of dGamma
+      if (pl.tc_npass > 1) {
+        if (!pl.tc_terms[i]) continue;          // (a main launch without terms)
+        fill_tc_tables(pr, pl.tc_terms[i], g);
+      }
       kern<<<grid, threads_b, pl.tc_smem_bwd, st>>>(g);
       PTM_CUDA(cudaGetLastError());
       ++g_launches;

@@ -67,11 +67,13 @@ struct MainTcArgs {
   short dslot[2 * kMtcMaxK + 32];  // D column -> partial slot (-1 = padding)
   int flush;           // backward tiles between promotions to double
   int mode;            // kModeLogp / kModeGrad
-  // two-pass form for models whose two predictors do not fit tensor memory together (each
-  // K_q <= 224): a first launch writes eta_sigma of every (chain, observation) to HBM
-  // (ETAONLY kernel), the main launch takes eta_mu from the tensor cores and eta_sigma from there
-  float* E;            // [CB][Gld][128] eta_sigma; written by the ETAONLY launch, read when ext_sigma
-  int ext_sigma;
+  // multi-pass form for models whose coefficients do not fit tensor memory at once: eta-only
+  // launches (ETAONLY kernel) carry groups of <= 224 coefficients of ONE predictor and write /
+  // accumulate its partial predictor to HBM; the main launch carries the remaining terms on the
+  // tensor cores and adds the external parts
+  float* E[2];         // [CB][Gld][128] partial eta_mu / eta_sigma of the eta-only launches
+  int e_acc;           // eta-only launch: add to E instead of overwriting it
+  int ext_mask;        // main launch: bit q = add E[q] to predictor q
 };
 
 __device__ __forceinline__ void mtc_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -172,8 +174,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
   float* s_cc = reinterpret_cast<float*>(s_B + 2 * bbytes);                 // [NCC + 4][128]
   float* s_gv = s_cc + (NCC + 4) * 128;                                     // [16][NGV][32]
   float* s_kn = s_gv + (GRAD ? kMtcEvalWarps * NGV * 32 : 0);               // [T][4][kKnotStride]
-  double* s_red = reinterpret_cast<double*>(s_kn + T * 4 * kKnotStride + ((T * 4 * kKnotStride) & 1));  // [16][kRegSlots][32]
-  float* s_eta = reinterpret_cast<float*>(s_red + kMtcEvalWarps * kRegSlots * 32);  // [16][2 OPW][32] eta + [OPW] y per eval warp
+  // [16][kRegSlots][32] doubles of the item-end reduction, ALIASED onto the per-warp eta buffers
+  // [16][2 OPW][32] + [32]: the reduction scratch is written after an item's last tile and read
+  // before the next item's first one (eval warps only, between their named barriers)
+  double* s_red = reinterpret_cast<double*>(s_kn + T * 4 * kKnotStride + ((T * 4 * kKnotStride) & 1));
+  float* s_eta = reinterpret_cast<float*>(s_red);
 
   const bool is_eval = warp < kMtcEvalWarps;
   const int sidx = warp - kMtcEvalWarps;
@@ -382,21 +387,29 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
       double a_z2 = 0, a_ls = 0, a_gb0 = 0, a_gg0 = 0, a_gvl = 0, a_gdl = 0, a_gvr = 0, a_gdr = 0;
       double a_logd = 0;
       const float sixth = 1.f / 6.f;
-      const bool hasq0 = g.Kq[0] > 0, ext = g.ext_sigma != 0, hasq1 = g.Kq[1] > 0 || ext;
+      const bool ext0 = (g.ext_mask & 1) != 0, ext1 = (g.ext_mask & 2) != 0;
+      const bool mma0 = g.Kq[0] > 0, mma1 = g.Kq[1] > 0, hasq0 = mma0 || ext0, hasq1 = mma1 || ext1;
       float* Gp = g.G + (long long)cb * g.Gld * 256 + q4 * 32 + lane;
-      float* Ep = g.E + (long long)cb * g.Gld * 128 + q4 * 32 + lane;
+      const long long eoff = (long long)cb * g.Gld * 128 + q4 * 32 + lane;
+      const float* Ex0 = g.E[0] + eoff;
+      const float* Ex1 = g.E[1] + eoff;
+      float* Eout = g.E[mma0 ? 0 : 1] + eoff;  // eta-only launch: its one predictor
       for (int s = 0; s < ntiles; ++s, ++tg) {
         const long long base = o_begin + (long long)s * NT + sub * OPW;
         // this warp's responses of the tile: one coalesced load, in flight while eta is waited for
         float yreg = 0.f;
         if (lane < OPW && base + lane < o_end) yreg = a.y[base + lane];
-        float ev_ext[OPW];  // eta_sigma of the first launch (two-pass form), also in flight during the wait
+        // external parts of the predictors (multi-pass form), also in flight during the wait
+        float ex0[OPW], ex1[OPW];
 #pragma unroll
-        for (int c = 0; c < OPW; ++c) ev_ext[c] = 0.f;
-        if (!ETAONLY && ext) {
+        for (int c = 0; c < OPW; ++c) { ex0[c] = 0.f; ex1[c] = 0.f; }
+        if (!ETAONLY && (ext0 || ext1)) {
 #pragma unroll
           for (int c = 0; c < OPW; ++c)
-            if (base + c < o_end) ev_ext[c] = __ldcs(Ep + (base + c - a.obs_begin) * 128);
+            if (base + c < o_end) {
+              if (ext0) ex0[c] = __ldcs(Ex0 + (base + c - a.obs_begin) * 128);
+              if (ext1) ex1[c] = __ldcs(Ex1 + (base + c - a.obs_begin) * 128);
+            }
         }
         mtc_wait(barE, tg & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -413,7 +426,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (base + c + j < o_end) Ep[(base + c + j - a.obs_begin) * 128] = __uint_as_float(v[j]);
+              if (base + c + j < o_end) {
+                float* ep = Eout + (base + c + j - a.obs_begin) * 128;
+                *ep = g.e_acc ? *ep + __uint_as_float(v[j]) : __uint_as_float(v[j]);
+              }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
@@ -428,8 +444,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            eb[(c + j) * 32 + lane] = __uint_as_float(v[j]);
-            eb[(OPW + c + j) * 32 + lane] = ext ? ev_ext[c + j] : __uint_as_float(w[j]);
+            eb[(c + j) * 32 + lane] = (mma0 ? __uint_as_float(v[j]) : 0.f) + ex0[c + j];
+            eb[(OPW + c + j) * 32 + lane] = (mma1 ? __uint_as_float(w[j]) : 0.f) + ex1[c + j];
           }
         }
         if (lane < OPW) eb[2 * OPW * 32 + lane] = yreg;
@@ -691,6 +707,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
         }  // !ETAONLY
       }
       if constexpr (!ETAONLY) {
+      named_bar(1, kMtcEvalWarps * 32);  // every eval warp is done with its eta buffer (aliased below)
       double* rp = s_red + (warp * kRegSlots) * 32 + lane;
       rp[SL_Z2 * 32] = a_z2;
       rp[SL_LS * 32] = a_ls;
