@@ -343,12 +343,12 @@ int ptm_pointwise_f32(const PtmProblem* prob, const float* params, int64_t n_sam
 int ptm_last_launch_count(void);
 
 /* Route the last logp / logp_grad sweep on this thread took: 0 = CUDA-core sweep (k_main);
- * 1 = tcgen05 sweep (float problems whose coefficient count fits tensor memory -- sum of nbases
- * <= 224, or <= 224 per predictor in the two-pass form: eta = Gamma B' and the coefficient
- * gradients G' B on the tensor cores with the 3xTF32 split, ptm_main_tc.cuh).  PTM_MAIN_TC=0 in
- * the environment at create time forces the CUDA-core sweep.  On the tensor-core route
- * ptm_workspace_bytes() includes the dl/deta exchange buffer (8 bytes per observation and chain,
- * 12 in the two-pass form). */
+ * 1 = tcgen05 sweep (float problems: eta = Gamma B' and the coefficient gradients G' B on the
+ * tensor cores with the 3xTF32 split, ptm_main_tc.cuh; one launch when sum of nbases <= 224,
+ * otherwise groups of terms of one predictor in eta-only passes whose partial predictors go
+ * through the workspace).  PTM_MAIN_TC=0 in the environment at create time forces the CUDA-core
+ * sweep.  On the tensor-core route ptm_workspace_bytes() includes the dl/deta exchange buffer
+ * (8 bytes per observation and chain, 16 in the several-pass form). */
 int ptm_last_main_route(void);
 
 /* Route the last information sweep (ptm_xtwx / ptm_loc_precision / ptm_loc_precision_all)

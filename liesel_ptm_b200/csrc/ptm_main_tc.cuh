@@ -24,9 +24,12 @@
 //       `flush` tiles.
 //
 // TMEM budget (512 columns): 2 K (Gamma hi, lo) + 2 NT (eta)  and  2 K16 + 256 (G tiles), so the
-// route takes models with K = sum of bases <= 224 (c3: 5 + 5 terms x 20 -> 208, NT = 48); larger
-// models use the CUDA-core sweep (k_main).  tools/micro/umma_ts.cu is the known-answer test of
-// the TMEM-operand MMA form used here.
+// single-launch form takes models with K = sum of bases <= 224 (c3: 5 + 5 terms x 20 -> 208,
+// NT = 32 by shared memory).  Larger models run in several passes (make_plan, ptm_capi.cu):
+// groups of whole terms of one predictor (<= 224 coefficients) go through the ETAONLY
+// instantiation, which writes / accumulates its partial predictor to E[q] in HBM; the main launch
+// carries the remaining terms and adds the external parts (ext_mask); k_grad_tc runs once per
+// group.  tools/micro/umma_ts.cu is the known-answer test of the TMEM-operand MMA form used here.
 #pragma once
 #include <cstdint>
 #include <type_traits>
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
         for (int ti = 0; ti < 8; ++ti) {
           const int t = sidx + ti * NSW;
           if (t >= T) break;
-          if (g.kcol[t] < 0) continue;  // two-pass form: the term belongs to the other launch
+          if (g.kcol[t] < 0) continue;  // several-pass form: the term belongs to another launch
           const float* kn = s_kn + t * 4 * kKnotStride;
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
