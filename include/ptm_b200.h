@@ -87,7 +87,7 @@ typedef struct {
   const void* const* K;        /* [T] -> [p_t, p_t] penalty after reparams */
   const int32_t* rank;         /* [T] rank of K_t */
   int32_t nparam;              /* shape parameters of h (J = nparam + 1 bases) */
-  const void* trafo_knots;     /* [nparam + 5] PTMKnots(a, b, nparam).knots */
+  const void* trafo_knots;     /* [nparam + 5] PTMKnots(a, b, nparam).knots (see trafo_variant) */
   const void* trafo_Z;         /* [nparam, nparam - 1] delta = Z delta_z */
   double trafo_lambda;         /* PTMSpline eps: transition width / (b - a) */
   const void* trafo_grid;      /* [1002] BSplineApprox.grid, or NULL to rebuild it
@@ -98,7 +98,18 @@ typedef struct {
                                   tau_t * chol (iwls_proposals.py:82-89) */
   int32_t trafo_noncentered;   /* PTMCoef(noncentered=True), var.py:100-107: delta = Z (tau_delta *
                                   delta_z), delta_z ~ N(0, 1) */
+  int32_t trafo_variant;       /* PTMDist(bspline=...), model/model.py:98-131:
+                                  PTM_TRAFO_PTM (0): PTMSpline, trafo_knots [nparam + 5];
+                                  PTM_TRAFO_ONION (1): OnionSpline (bspline/onion.py:13-138), trafo_knots
+                                  [nparam + 11] = OnionKnots(a, b, nparam).knots, J = nparam + 7 bases
+                                  (nparam <= 34), identity off the core, trafo_lambda unused;
+                                  PTM_TRAFO_IDENTITY (2): GaussianPseudoTransformationDist
+                                  (dist.py:766-850, LocScalePTM.new_gaussian model/model.py:386-417):
+                                  h = identity; the delta_z / tau_delta entries of the parameter
+                                  rows are ignored, carry no prior, and get a zero gradient */
 } PtmProblemDesc;
+
+enum { PTM_TRAFO_PTM = 0, PTM_TRAFO_ONION = 1, PTM_TRAFO_IDENTITY = 2 };
 
 typedef struct PtmProblem PtmProblem; /* opaque, immutable after create (tuning knobs in the
                                           environment are read once, at create) */

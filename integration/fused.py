@@ -145,7 +145,13 @@ class FusedProblem:
         d.rank = i32([int(np.linalg.matrix_rank(np.asarray(t.coef.dist_node["penalty"].value)))
                       for _, _, t in terms] or [0])
         coef = model.trafo  # PTMCoef (var.py:45-119): knots, Z, latent_coef
-        d.nparam = int(np.asarray(coef.knots).shape[0] - 5)
+        # PTMDist(bspline=...) (model/model.py:98-131): the dist node's partial class tells the variant
+        pdc = getattr(model.response.dist_node, "partial_dist_class", None)
+        bs_inst = getattr(pdc, "keywords", {}).get("bspline", None)
+        variant = 1 if type(bs_inst).__name__ == "OnionSpline" else (
+            2 if getattr(getattr(pdc, "func", None), "__name__", "") == "GaussianPseudoTransformationDist" else 0)
+        d.trafo_variant = variant
+        d.nparam = int(np.asarray(coef.knots).shape[0] - (11 if variant == 1 else 5))
         d.trafo_knots = arr(coef.knots).ctypes.data
         d.trafo_Z = arr(coef.Z).ctypes.data
         d.trafo_lambda = float(model.trafo_lambda)

@@ -12,6 +12,7 @@ from .spline import (  # noqa: F401
     LinearConstraintEVD,
     LogIncKnots,
     Penalty,
+    OnionKnots,
     PTMKnots,
     approx_grid,
     banded_basis,
@@ -32,7 +33,7 @@ from .model import (  # noqa: F401
 
 __all__ = [
     "LocScalePTM", "FlatLogProb", "GaussianLocCholInfo", "GaussianScaleCholInfo",
-    "ps", "lin", "term", "PTMKnots", "LogIncKnots", "Penalty", "equidistant_knots",
+    "ps", "lin", "term", "PTMKnots", "OnionKnots", "LogIncKnots", "Penalty", "equidistant_knots",
     "mixed_model", "LinearConstraintEVD", "banded_basis", "approx_grid", "trafo_reparam", "Basis",
     "PtmError",
 ]

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("PTM_B200_LIB", os.path.join(_HERE, "libptm_b200.so"))
 
 PTM_F32, PTM_F64 = 0, 1
 PTM_LOC, PTM_SCALE = 0, 1
+PTM_TRAFO_PTM, PTM_TRAFO_ONION, PTM_TRAFO_IDENTITY = 0, 1, 2
 
 STATUS = {
     0: "PTM_OK", 1: "PTM_ERR_NULL", 2: "PTM_ERR_SHAPE", 3: "PTM_ERR_DTYPE",
@@ -62,6 +63,7 @@ class PtmProblemDesc(C.Structure):
         ("trafo_grid", C.c_void_p),
         ("noncentered", C.POINTER(C.c_int32)),
         ("trafo_noncentered", C.c_int32),
+        ("trafo_variant", C.c_int32),
     ]
 
 

@@ -68,6 +68,7 @@ struct PtmProblem {
   long long n = 0;
   int T = 0, T_loc = 0, T_scale = 0;
   int nparam = 0, J = 0, KK = 0, P = 0;
+  int variant = 0;  // PTM_TRAFO_*
   int nb[ptm::kMaxTerms] = {0}, p[ptm::kMaxTerms] = {0}, pred[ptm::kMaxTerms] = {0};
   int rank[ptm::kMaxTerms] = {0}, qidx[ptm::kMaxTerms] = {0};
   int nc[ptm::kMaxTerms] = {0}, nc_dz = 0;  // non-centred parameterisations
@@ -136,7 +137,7 @@ void fill_tc(const ptm::TrafoConst<double>& s, ptm::TrafoConst<R>& d) {
   // the product) of a cell, so 1e-6 / 1e-3 keep the cell index bit-exact with searchsorted while
   // a warp of 32 chains takes the table path in ~6 % of the float rows (it was 73 % at 2e-2)
   d.frac_eps = sizeof(R) == 8 ? (R)1e-6 : (R)1e-3;
-  d.nparam = s.nparam; d.J = s.J; d.dk = (R)s.dk; d.log_dk = (R)s.log_dk; d.k1 = (R)s.k1;
+  d.nparam = s.nparam; d.J = s.J; d.e_off = s.e_off; d.variant = s.variant; d.dk = (R)s.dk; d.log_dk = (R)s.log_dk; d.k1 = (R)s.k1;
   d.log_KK = (R)s.log_KK;
   for (int i = 0; i < ptm::kMaxJ; ++i) d.Bk[i] = (R)s.Bk[i];
   for (int i = 0; i < ptm::kMaxNparam; ++i) d.wts[i] = (R)s.wts[i];
@@ -225,7 +226,8 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
   pr->n = n;
   pr->nparam = d->nparam;
   pr->nc_dz = d->trafo_noncentered != 0;
-  pr->J = d->nparam + 1;
+  pr->variant = d->trafo_variant;
+  pr->J = d->nparam + (d->trafo_variant == PTM_TRAFO_ONION ? 7 : 1);  // ptm.py:55-57, onion.py:50-59
   pr->KK = pr->J - 3;
   pr->dz_off = bo;
   pr->tau_off = bo + d->nparam - 1;
@@ -243,14 +245,19 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
   ptm::TrafoConst<double>& tc = pr->tc64;
   memset(&tc, 0, sizeof tc);
   tc.nparam = d->nparam; tc.J = J; tc.KK = J - 3;
+  const bool onion = d->trafo_variant == PTM_TRAFO_ONION;
+  tc.variant = d->trafo_variant;
+  tc.e_off = onion ? 4 : 1;
   tc.a = tk[3]; tc.b = tk[J];
   double dsum = 0;
   for (int i = 0; i + 1 < L; ++i) dsum += tk[i + 1] - tk[i];
   tc.dk = dsum / (L - 1);
   tc.log_dk = std::log(tc.dk);
   tc.inv_dk = 1.0 / tc.dk;
-  tc.k1 = tk[3];
-  double eps = d->trafo_lambda;
+  tc.k1 = onion ? tk[2] : tk[3];
+  // the onion form has boundary value a and slope 1 by construction, so any transition is the
+  // identity off the core (onion.py:133-138); the width only has to be finite
+  double eps = onion ? 0.1 : d->trafo_lambda;
   if (eps < 1e-6) return fail(PTM_ERR_SHAPE, "eps is < 1e-6; that is numerically unstable.");
   tc.w = eps * (tc.b - tc.a);
   tc.inv_w = 1.0 / tc.w;
@@ -258,9 +265,16 @@ int create_impl(const PtmProblemDesc* d, PtmProblem* pr) {
   tc.max_eps = tc.b + tc.w;
   tc.inv_h = (double)(ptm::kGridN - 1) / (tc.b - tc.a);
   tc.kap_scale = (double)ptm::kGridN / (double)(ptm::kGridN - 1);
+  // Gaussian model: the sweep evaluates the PTM spline at delta = 0, whose samples are the identity;
+  // with the exact lerp weight (instead of the reference's range/1000 step, approx.py:375-380) the
+  // lerp of those samples is the identity too, h' = 1 (dist.py:846-850: value, zeros)
+  if (d->trafo_variant == PTM_TRAFO_IDENTITY) tc.kap_scale = 1.0;
   tc.ratio = (double)tc.KK / (double)(ptm::kGridN - 1);
   tc.log_KK = std::log((double)(J - 3));
-  {
+  if (onion) {  // onion.py:74-108: sum of the free increments = nparam * dk, no weights, theta_0 = knots[2]
+    tc.log_KK = std::log((double)d->nparam);
+    for (int j = 0; j < d->nparam; ++j) tc.wts[j] = 1.0;
+  } else {
     std::vector<double> row;
     host_basis_row(tk, J, tk[3], row);
     double run = 0;
@@ -1158,6 +1172,8 @@ template <typename R>
 int make_hess_plan(const PtmProblem* pr, int block, long long C, HessPlan& hp) {
   if (block != PTM_BLOCK_DELTA_Z && (block < 0 || block >= pr->T)) return fail(PTM_ERR_SHAPE, "block: term index or PTM_BLOCK_DELTA_Z");
   const bool dz = block == PTM_BLOCK_DELTA_Z;
+  if (dz && pr->variant == PTM_TRAFO_IDENTITY)
+    return fail(PTM_ERR_SHAPE, "the Gaussian model (PTM_TRAFO_IDENTITY) has no shape-parameter block");
   hp.kind = dz ? ptm::kHessDeltaZ : ptm::kHessBeta;
   hp.d = dz ? pr->nparam - 1 : pr->p[block];
   hp.NACC = ptm::hess_nacc(hp.kind, dz ? 0 : pr->nb[block], pr->KK);
@@ -1289,6 +1305,10 @@ int ptm_problem_create(const PtmProblemDesc* d, PtmProblem** out) {
   if (d->n < 0) return fail(PTM_ERR_SHAPE, "n must be >= 0");
   if (d->n_terms < 0 || d->n_terms > PTM_MAX_TERMS) return fail(PTM_ERR_SHAPE, "n_terms out of range");
   if (d->nparam < 4 || d->nparam > PTM_MAX_NPARAM) return fail(PTM_ERR_SHAPE, "nparam must be in [4, 40]");
+  if (d->trafo_variant < PTM_TRAFO_PTM || d->trafo_variant > PTM_TRAFO_IDENTITY)
+    return fail(PTM_ERR_SHAPE, "trafo_variant must be PTM_TRAFO_PTM, PTM_TRAFO_ONION or PTM_TRAFO_IDENTITY");
+  if (d->trafo_variant == PTM_TRAFO_ONION && d->nparam + 7 > PTM_MAX_NPARAM + 1)
+    return fail(PTM_ERR_SHAPE, "onion form: nparam must be <= 34 (nparam + 7 bases)");
   if (!d->y && d->n > 0) return fail(PTM_ERR_NULL, "y is null");
   if (!d->trafo_knots || !d->trafo_Z) return fail(PTM_ERR_NULL, "trafo arrays are null");
   if (d->n_terms > 0 && (!d->x || !d->nbases || !d->ncoef || !d->predictor || !d->knots || !d->Z || !d->K || !d->rank))

@@ -473,7 +473,7 @@ __global__ void k_hess_post_dz(const HessPostArgs<R> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x, tid = threadIdx.x;
   const TrafoConst<D>& tc = *a.tc;
-  const int KK = a.KK, NGV = KK + 4, np_ = tc.nparam, J = np_ + 1, dq = np_ - 1;
+  const int KK = a.KK, NGV = KK + 4, np_ = tc.nparam, J = tc.J, eo = tc.e_off, dq = np_ - 1;
   D* s_red = reinterpret_cast<D*>(smem_raw);  // [NACC]
   D* s_M = s_red + a.NACC;                    // [J][J]   vt space, then theta space
   D* s_E = s_M + J * J;                       // [np][np] e space, then delta space
@@ -511,15 +511,17 @@ __global__ void k_hess_post_dz(const HessPostArgs<R> a) {
     for (int j = 0; j <= J; ++j) { gvt[j] = j < NGV ? s_red[NGV * 5 + j] : 0.0; aVL[j] = aDL[j] = aVR[j] = aDR[j] = 0.0; }
     D g1[5] = {1.0, 0.0, 0.0, 0.0, 0.0}, g2[5] = {0.0, tc.inv_dk, 0.0, 0.0, 0.0};
     D g3[5] = {1.0, 1.0, 1.0, 1.0, 0.0}, g4[5] = {0.0, tc.inv_dk, 2.0 * tc.inv_dk, 3.0 * tc.inv_dk, 0.0};
-    piece_coefs_backward(g1, 0, KK, aVL);
-    piece_coefs_backward(g2, 0, KK, aDL);
-    piece_coefs_backward(g3, KK - 1, KK, aVR);
-    piece_coefs_backward(g4, KK - 1, KK, aDR);
+    if (tc.variant == kTrafoPtm) {  // the onion form is the identity off the core (onion.py:133-138)
+      piece_coefs_backward(g1, 0, KK, aVL);
+      piece_coefs_backward(g2, 0, KK, aDL);
+      piece_coefs_backward(g3, KK - 1, KK, aVR);
+      piece_coefs_backward(g4, KK - 1, KK, aDR);
+    }
     for (int j = 0; j < J; ++j)
       gvt[j] += sc[HS_GVL] * aVL[j] + sc[HS_GDL] * aDL[j] + sc[HS_GVR] * aVR[j] + sc[HS_GDR] * aDR[j];
     D run = 0.0;
     for (int j = J - 1; j >= 0; --j) { run += gvt[j]; gth[j] = run; }  // vt = cumsum(theta)
-    for (int j = 0; j < np_; ++j) ge[j] = gth[j + 1] - tc.Bk[j + 1] * gth[0];
+    for (int j = 0; j < np_; ++j) ge[j] = gth[j + eo] - tc.Bk[j + eo] * gth[0];
   }
   __syncthreads();
   // M_vt [J][J] from the band (5 diagonals) + boundary outer products
@@ -545,11 +547,11 @@ __global__ void k_hess_post_dz(const HessPostArgs<R> a) {
     for (int k = J - 1; k >= 0; --k) { run += s_M[i * J + k]; s_M[i * J + k] = run; }
   }
   __syncthreads();
-  // e space: theta_0 = k1 - Bk[1:] . e, theta_{j+1} = e_j
+  // e space: theta_0 = k1 - Bk[e_off:] . e, theta_{j + e_off} = e_j
   for (int idx = tid; idx < np_ * np_; idx += blockDim.x) {
     const int j = idx / np_, l = idx - j * np_;
-    const D bj = tc.Bk[j + 1], bl = tc.Bk[l + 1];
-    s_E[idx] = s_M[(j + 1) * J + (l + 1)] - bj * s_M[0 * J + (l + 1)] - bl * s_M[(j + 1) * J + 0] + bj * bl * s_M[0];
+    const D bj = tc.Bk[j + eo], bl = tc.Bk[l + eo];
+    s_E[idx] = s_M[(j + eo) * J + (l + eo)] - bj * s_M[0 * J + (l + eo)] - bl * s_M[(j + eo) * J + 0] + bj * bl * s_M[0];
   }
   __syncthreads();
   // delta space: de_j/ddelta_l = e_j (1[j=l] - sm_l).  W = info_e Je, then Je' W

@@ -843,6 +843,10 @@ __global__ void k_pre(const PreArgs<R> a) {
       D v = 0.0;
       for (int k = 0; k < np_ - 1; ++k) v = fma((D)a.Zd[j * (np_ - 1) + k], (D)dz[k], v);
       delta[j] = a.nc_dz ? v * (D)s_par[a.taud_off] : v;  // Z (scale * latent), var.py:104-105
+      // Gaussian model (bspline="identity", dist.py:766-850): the transformation is the identity,
+      // which is what the PTM spline's samples are at delta = 0 (tests/test_predictor.py:14-22 of
+      // the reference); the host sets the exact lerp weight for this variant (kap_scale = 1)
+      if (tc.variant == kTrafoIdentity) delta[j] = 0.0;
     }
     coef_map_forward(tc, delta, e, sm, vt);
     D cfirst[5], clast[5];
@@ -1004,8 +1008,9 @@ __global__ void k_post(const PostArgs<R> a) {
              (D)a.n_obs * half_log_2pi;
       if (a.add_priors) {
         for (int t = 0; t < a.T; ++t) lp += s_lp[t * 32 + lane];
-        lp += a.nc_dz ? -0.5 * ss - (D)(np_ - 1) * half_log_2pi
-                      : -0.5 * ss / (taud * taud) - (D)(np_ - 1) * (log(taud) + half_log_2pi);
+        if (tc.variant != kTrafoIdentity)  // the Gaussian model has no shape parameters
+          lp += a.nc_dz ? -0.5 * ss - (D)(np_ - 1) * half_log_2pi
+                        : -0.5 * ss / (taud * taud) - (D)(np_ - 1) * (log(taud) + half_log_2pi);
       }
       a.logp[(long long)c * a.ld_logp] = (R)lp;
       if (!GRAD && a.stats != nullptr) {
@@ -1028,10 +1033,12 @@ __global__ void k_post(const PostArgs<R> a) {
           delta[j] = a.nc_dz ? v * taud : v;
         }
         coef_map_forward(tc, delta, e, sm, vt);
-        for (int j = 0; j <= np_; ++j) gvt[j] = red[(kRegSlots + j) * 32 + lane];
-        // boundary gradients fold into the first / last piece (ptm.py:417-419)
-        const D gvl = red[SL_GVL * 32 + lane], gdl = red[SL_GDL * 32 + lane];
-        const D gvr = red[SL_GVR * 32 + lane], gdr = red[SL_GDR * 32 + lane];
+        for (int j = 0; j < tc.J; ++j) gvt[j] = red[(kRegSlots + j) * 32 + lane];
+        // boundary gradients fold into the first / last piece (ptm.py:417-419); the onion form is
+        // the identity off the core whatever the coefficients are (onion.py:133-138)
+        const bool bnd = tc.variant == kTrafoPtm;
+        const D gvl = bnd ? red[SL_GVL * 32 + lane] : 0.0, gdl = bnd ? red[SL_GDL * 32 + lane] : 0.0;
+        const D gvr = bnd ? red[SL_GVR * 32 + lane] : 0.0, gdr = bnd ? red[SL_GDR * 32 + lane] : 0.0;
         {
           D gc[5] = {gvl, gdl * tc.inv_dk, 0.0, 0.0, 0.0};
           piece_coefs_backward(gc, 0, KK, gvt);
@@ -1049,9 +1056,9 @@ __global__ void k_post(const PostArgs<R> a) {
           } else if (a.add_priors) {
             v -= (D)dz[k] / (taud * taud);
           }
-          go[a.dz_off + k] = (R)v;
+          go[a.dz_off + k] = tc.variant == kTrafoIdentity ? R(0) : (R)v;
         }
-        go[a.taud_off] = (R)g_taud;
+        go[a.taud_off] = tc.variant == kTrafoIdentity ? R(0) : (R)g_taud;
       }
     }
   }

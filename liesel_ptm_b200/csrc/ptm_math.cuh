@@ -26,7 +26,8 @@
 namespace ptm {
 
 constexpr int kMaxNbases = 32;
-constexpr int kMaxNparam = 40;   // shape parameters; J = nparam + 1 <= 41
+constexpr int kMaxNparam = 40;   // shape parameters; J = nparam + 1 <= 41 (onion form: nparam + 7 <= 41)
+constexpr int kTrafoPtm = 0, kTrafoOnion = 1, kTrafoIdentity = 2;  // model/model.py:98-131
 constexpr int kMaxJ = kMaxNparam + 1;
 constexpr int kGridN = 1000;     // BSplineApprox ngrid (ptm.py:312)
 
@@ -208,21 +209,27 @@ struct TrafoScal {
 template <typename R>
 struct TrafoConst : TrafoScal<R> {
   int nparam;      // shape parameters
-  int J;           // nparam + 1 bases of h
+  int J;           // bases of h: nparam + 1 (ptm.py:55-57), nparam + 7 for the onion knots (onion.py:50-59)
+  int e_off;       // theta index of the first free increment: 1 (ptm.py:214-218), 4 (onion.py:94, 108)
+  int variant;     // kTrafoPtm / kTrafoOnion / kTrafoIdentity
   R dk;            // mean knot step (ptm.py:208)
   R log_dk;
-  R k1;            // knots[3] (ptm.py:201)
-  R log_KK;        // log(J - 3)  (ptm.py:122)
-  R Bk[kMaxJ];     // (B(k1) S) row, ptm.py:202-205
-  R wts[kMaxNparam];  // log_sfn weights 1/6, 5/6, 1, ..., 5/6, 1/6
+  R k1;            // theta_0 offset: knots[3] (ptm.py:201), knots[2] for the onion form (onion.py:108)
+  R log_KK;        // log(J - 3) (ptm.py:122); log(nparam) for the onion form (onion.py:79, 89-90)
+  R Bk[kMaxJ];     // (B(k1) S) row, ptm.py:202-205 (zero for the onion form)
+  R wts[kMaxNparam];  // log_sfn weights 1/6, 5/6, 1, ..., 5/6, 1/6 (ones for the onion form)
 };
 
 // ---- coefficient map delta -> theta -> cumulative B-spline coefficients ---------
-// theta[0] = k1 - Bk[1:] . e, theta[1:] = e = exp(delta - lsfn + log dk);
-// vt = cumsum(theta) are the B-spline coefficients of h on the core.
+// theta[0] = k1 - Bk[e_off:] . e, then e_off - 1 fixed increments dk, e = exp(delta - lsfn + log dk),
+// and e_off - 1 fixed increments dk again (none for the PTM form, three for the onion form,
+// onion.py:81-108); vt = cumsum(theta) are the B-spline coefficients of h on the core.
 template <typename R>
-PTM_HD void coef_map_forward(const TrafoConst<R>& tc, const R* delta, R* e, R* sm, R* vt) {
-  const int np_ = tc.nparam;
+PTM_HD void coef_map_forward(const TrafoConst<R>& tc, const R* delta_in, R* e, R* sm, R* vt) {
+  const int np_ = tc.nparam, eo = tc.e_off;
+  // Gaussian model (dist.py:766-850): the shape parameters are ignored, h is the spline of delta = 0
+  R delta[kMaxNparam];
+  for (int j = 0; j < np_; ++j) delta[j] = tc.variant == kTrafoIdentity ? R(0) : delta_in[j];
   R mx = delta[0];
   for (int j = 1; j < np_; ++j) mx = delta[j] > mx ? delta[j] : mx;
   R ssum = R(0);
@@ -236,14 +243,14 @@ PTM_HD void coef_map_forward(const TrafoConst<R>& tc, const R* delta, R* e, R* s
   for (int j = 0; j < np_; ++j) {
     sm[j] *= inv;
     e[j] = exp(delta[j] - lsfn + tc.log_dk);
-    dot += tc.Bk[j + 1] * e[j];
+    dot += tc.Bk[j + eo] * e[j];
   }
   R run = tc.k1 - dot;  // theta[0]
-  vt[0] = run;
-  for (int j = 0; j < np_; ++j) {
-    run += e[j];
-    vt[j + 1] = run;
-  }
+  int i = 0;
+  vt[i++] = run;
+  for (int j = 1; j < eo; ++j) { run += tc.dk; vt[i++] = run; }
+  for (int j = 0; j < np_; ++j) { run += e[j]; vt[i++] = run; }
+  for (int j = 1; j < eo; ++j) { run += tc.dk; vt[i++] = run; }
 }
 
 // Monomial coefficients (local coordinate u in [0,1)) of piece kk from the uniform
@@ -289,17 +296,17 @@ PTM_HD void piece_coefs_backward(const R* gc, int kk, int KK, R* gvt) {
 template <typename R>
 PTM_HD void coef_map_backward(const TrafoConst<R>& tc, const R* gvt, const R* e,
                               const R* sm, R* gdelta) {
-  const int np_ = tc.nparam;
+  const int np_ = tc.nparam, eo = tc.e_off;
   // reverse cumsum: gtheta[j] = sum_{l >= j} gvt[l]
   R run = R(0);
   R gth[kMaxJ];
-  for (int j = np_; j >= 0; --j) {
+  for (int j = tc.J - 1; j >= 0; --j) {
     run += gvt[j];
     gth[j] = run;
   }
   R tot = R(0);
   for (int j = 0; j < np_; ++j) {
-    const R ge = gth[j + 1] - tc.Bk[j + 1] * gth[0];
+    const R ge = gth[j + eo] - tc.Bk[j + eo] * gth[0];
     gdelta[j] = e[j] * ge;
     tot += gdelta[j];
   }

@@ -28,6 +28,7 @@ from . import _lib
 from .spline import Basis, PTMKnots, approx_grid, term, trafo_reparam
 
 _NP = {torch.float64: np.float64, torch.float32: np.float32}
+_VARIANTS = {"ptm": _lib.PTM_TRAFO_PTM, "onion": _lib.PTM_TRAFO_ONION, "identity": _lib.PTM_TRAFO_IDENTITY}
 
 
 def _on_device(fn):
@@ -68,13 +69,20 @@ class LocScalePTM:
     """Location-scale penalized transformation model, B200 hot path."""
 
     def __init__(self, response, knots, trafo_lambda: float = 0.1, to_float32: bool = True,
-                 device: str | torch.device = "cuda") -> None:
+                 device: str | torch.device = "cuda", bspline: str = "ptm") -> None:
+        """``bspline``: "ptm" (PTMSpline over ``PTMKnots``), "onion" (OnionSpline over
+        ``OnionKnots``; experimental in the reference) or "identity" (the Gaussian location-scale
+        model), as ``PTMDist`` switches them (model/model.py:98-131, 292)."""
+        if bspline not in _VARIANTS:
+            raise ValueError(f"bspline must be one of {sorted(_VARIANTS)}, got {bspline!r}")
+        self.bspline = bspline
         self.to_float32 = to_float32
         self.dtype = torch.float32 if to_float32 else torch.float64
         self.np_dtype = _NP[self.dtype]
         self.response = np.ascontiguousarray(np.asarray(response), dtype=self.np_dtype)
         self.knots = np.ascontiguousarray(np.asarray(knots), dtype=self.np_dtype)
-        self.nparam = self.knots.shape[0] - 5
+        # bases of h minus one (ptm.py:55-57) / minus seven (onion.py:50-59)
+        self.nparam = self.knots.shape[0] - (11 if bspline == "onion" else 5)
         self.trafo_lambda = float(trafo_lambda)
         # Z_delta is reparameterisation DATA (LAPACK-dependent eigenvector order); a caller
         # that exports it from the host model assigns it before build()
@@ -104,6 +112,15 @@ class LocScalePTM:
         knots = PTMKnots(a, b, nparam=nparam, dtype=dtype)
         return cls(response, knots.knots, trafo_lambda=trafo_lambda, to_float32=to_float32,
                    device=device)
+
+    @classmethod
+    def new_gaussian(cls, response, to_float32: bool = True, device="cuda"):
+        """Shortcut for a Gaussian location-scale model (model/model.py:386-417): the same knots
+        argument as the reference passes, ``bspline="identity"``.  The parameter rows keep the
+        (ignored) shape-parameter entries so that the layout is the one of every other model."""
+        dtype = np.float32 if to_float32 else np.float64
+        return cls(response, np.linspace(-3.0, 3.0, 10).astype(dtype), to_float32=to_float32,
+                   device=device, bspline="identity")
 
     # -- reference surface: model.loc += ..., model.scale += ... ------------------------
     @property
@@ -183,6 +200,7 @@ class LocScalePTM:
         d.trafo_grid = arr(self.grid).ctypes.data
         d.noncentered = i32_array([int(t.is_noncentered) for t, _ in self.terms] or [0])
         d.trafo_noncentered = int(self.trafo_noncentered)
+        d.trafo_variant = _VARIANTS[self.bspline]
         h = C.c_void_p()
         _lib.check(lib.ptm_problem_create(C.byref(d), C.byref(h)))
         self._handle = h
@@ -678,7 +696,7 @@ def _hessian_block(self, block, params: torch.Tensor, mode: int = HESS_RAW, with
         d = self.terms[blk][0].basis.ncoef
     nbytes = self._lib.ptm_hessian_workspace_bytes(self._h, Cn, blk)
     if nbytes == 0:
-        raise _lib.PtmError(_lib.PTM_ERR_SHAPE, self._lib.ptm_last_error().decode())
+        raise _lib.PtmError(2, self._lib.ptm_last_error().decode())  # PTM_ERR_SHAPE
     ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
     info = torch.empty((Cn, d, d), dtype=self.dtype, device=self.device)
     chol = torch.empty_like(info) if with_chol else None

@@ -66,6 +66,21 @@ class PTMKnots:
 LogIncKnots = PTMKnots
 
 
+class OnionKnots:
+    """Knots of the onion spline (bspline/onion.py:13-59): nparam free increments on [a, b], three
+    fixed increments of one knot step on either side, nparam + 7 bases."""
+
+    def __init__(self, a: float, b: float, nparam: int, order: int = 3, dtype=np.float64) -> None:
+        self.a, self.b, self.nparam, self.order = a, b, nparam, order
+        m = nparam + 5
+        self.step = (self.b - self.a) / (m - 3)
+        k1 = a - self.step
+        k2 = b + self.step
+        self.knots = equidistant_knots(
+            np.array([k1, k2], dtype=dtype), order=order, n_param=nparam + 7, eps=0.0, dtype=dtype
+        )
+
+
 def approx_grid(knots, ngrid: int = 1000):
     """BSplineApprox.grid (bspline/approx.py:372-380): [min-step, linspace, max+step]."""
     knots = np.asarray(knots)

@@ -13,7 +13,7 @@ The oracle is therefore pinned against outputs of the REFERENCE'S OWN SOURCE FIL
 executed here over NumPy stand-ins for jax / tfp (tests/golden/jaxshim,
 tests/golden/make_reference_golden.py -> tests/golden/ref_*.npz): bspline/approx.py,
 bspline/ptm.py, bspline/util.py, dist.py, gam/dist.py, constraint.py, penalty.py,
-iwls_proposals.py, predictor.py (intercept formulas) run unmodified.  tests/test_reference_golden.py: knots, dense bases,
+iwls_proposals.py, predictor.py (intercept formulas), bspline/onion.py run unmodified.  tests/test_reference_golden.py: knots, dense bases,
 grid tables, theta(delta), h / h' over all five regions are BIT-EQUAL; per-observation
 log-densities agree to 1e-13, the gradient to 1e-14 of its norm against forward mode
 through the reference's code with its declared custom_jvp rules, precision / Cholesky to
@@ -285,6 +285,15 @@ class PTMCoefMap:
         self.B = B @ S  # (1, J)
         self.step = np.diff(self.knots).mean()
 
+    e_off = 1  # theta index of the first free increment
+
+    def weights(self, nparam, dtype):
+        return log_sfn_weights(nparam, dtype)
+
+    def theta0_row(self, nparam):
+        """d(-theta_0)/d e_j: theta_0 = k1 - Bk[1:] . e (ptm.py:214-218)."""
+        return self.B[0][1:1 + nparam]
+
     def __call__(self, delta):
         """delta (..., nparam) -> theta (..., J).  ptm.py:155-172, 210-230."""
         delta = np.asarray(delta)
@@ -433,6 +442,89 @@ class PTMSpline:
         kap = np.clip(np.where(den > 0, (z[m] - H[i]) / np.where(den > 0, den, 1.0), 0.0), 0.0, 1.0)
         r[m] = np.minimum(g[i] + kap * ap.step, b)
         return r
+
+
+class OnionKnots:
+    """bspline/onion.py:13-59."""
+
+    def __init__(self, a, b, nparam, order=3, dtype=np.float64):
+        self.a, self.b, self.nparam, self.order = a, b, nparam, order
+        m = nparam + 5
+        self.step = (self.b - self.a) / (m - 3)
+        k1 = a - self.step
+        k2 = b + self.step
+        self.knots = equidistant_knots(
+            np.array([k1, k2], dtype=dtype), order=order, n_param=nparam + 7, eps=0.0, dtype=dtype
+        )
+
+
+class OnionCoefMap:
+    """bspline/onion.py:62-112 (``get_onion_fn``)."""
+
+    e_off = 4
+
+    def __init__(self, knots):
+        self.knots = np.asarray(knots)
+        self.m = self.knots.size - 6
+        self.dk = np.diff(self.knots).mean()
+        self.nparam = self.knots.size - 11
+        self.denominator = np.log((self.m - 5) * self.dk)
+
+    def weights(self, nparam, dtype):
+        return np.ones((nparam,), dtype=dtype)
+
+    def theta0_row(self, nparam):
+        return np.zeros((nparam,), dtype=self.knots.dtype)  # theta_0 = knots[2], a constant
+
+    def __call__(self, delta):
+        delta = np.asarray(delta)
+        dk3 = np.log(np.full(delta.shape[:-1] + (3,), self.dk, dtype=delta.dtype))
+        corr = logsumexp(delta)[..., None] - self.denominator
+        full = np.concatenate([dk3, delta - corr, dk3], axis=-1)
+        k2 = np.full(delta.shape[:-1] + (1,), self.knots[2], dtype=delta.dtype)
+        return np.concatenate([k2, np.exp(full)], axis=-1)
+
+
+class OnionSpline(PTMSpline):
+    """bspline/onion.py:115-138: the lerped spline on [knots[3], knots[-4]], the identity (value x,
+    derivative 1, no dependence on the coefficients) elsewhere."""
+
+    identity_outside = True
+
+    def __init__(self, knots):
+        super().__init__(knots, eps=0.1)  # the transition constants are not used
+        self.coef_map = OnionCoefMap(self.knots)
+
+    def region_code(self, x):
+        """0 / 4 = identity to the left / right of the core, 2 = core (NaN -> 4)."""
+        return np.where((x >= self.min_knot) & (x <= self.max_knot), 2, np.where(x < self.min_knot, 0, 4))
+
+    def dot_and_deriv_coef(self, x, theta):
+        x = np.asarray(x)
+        fx, dx = self.bspline.dot_and_deriv_n(x, theta)
+        in_core = (x >= self.min_knot) & (x <= self.max_knot)
+        return np.where(in_core, fx, x), np.where(in_core, dx, x.dtype.type(1))
+
+    def dot_inverse_exact(self, z, delta):
+        raise NotImplementedError("oracle: inverse of the onion form is not restated")
+
+
+class IdentitySpline(PTMSpline):
+    """GaussianPseudoTransformationDist (dist.py:766-850): ``transformation_and_logdet_spline``
+    returns (value, 0), i.e. h = identity and log h' = 0 whatever the coefficients are."""
+
+    identity_outside = True
+    identity_everywhere = True
+
+    def region_code(self, x):
+        return np.where(x < self.min_knot, 0, 4)
+
+    def dot_and_deriv_coef(self, x, theta):
+        x = np.asarray(x)
+        return x + x.dtype.type(0), np.ones_like(x)
+
+    def dot_inverse_exact(self, z, delta):
+        return np.atleast_1d(np.asarray(z, dtype=self.knots.dtype)).copy()
 
 
 # --------------------------------------------------------------------------
@@ -587,13 +679,21 @@ class ChainState:
 class PTMModel:
     """Restates what one ``model.log_prob(state)`` evaluates."""
 
-    def __init__(self, y, terms, nparam=20, a=-4.0, b=4.0, trafo_lambda=0.1, dtype=np.float64):
+    def __init__(self, y, terms, nparam=20, a=-4.0, b=4.0, trafo_lambda=0.1, dtype=np.float64, bspline="ptm"):
         self.dtype = np.dtype(dtype)
         self.y = np.asarray(y, dtype=dtype)
         self.n = self.y.shape[0]
         self.terms = list(terms)
-        self.knots = PTMKnots(a, b, nparam, dtype=dtype)
-        self.spline = PTMSpline(self.knots.knots, eps=trafo_lambda)
+        self.bspline = bspline  # PTMDist(bspline=...), model/model.py:98-131
+        if bspline == "onion":
+            self.knots = OnionKnots(a, b, nparam, dtype=dtype)
+            self.spline = OnionSpline(self.knots.knots)
+        elif bspline == "identity":  # new_gaussian, model/model.py:386-417: knots linspace(-3, 3, 10)
+            self.knots = PTMKnots(a, b, nparam, dtype=dtype)
+            self.spline = IdentitySpline(self.knots.knots, eps=trafo_lambda)
+        else:
+            self.knots = PTMKnots(a, b, nparam, dtype=dtype)
+            self.spline = PTMSpline(self.knots.knots, eps=trafo_lambda)
         self.nparam = nparam
         self.Zd = trafo_Z(nparam, dtype)
         self.trafo_noncentered = False  # PTMCoef(noncentered=True), var.py:100-107
@@ -676,6 +776,8 @@ class PTMModel:
             lp = lp + mvn_singular_logp(st.beta[t][c], term.K, one if term.noncentered else st.tau[c, t], term.rank)
         # delta_z ~ iid Normal(0, tau_delta): var.py:77-82 (tfd.Normal.log_prob, not in tree);
         # scale 1 in non-centred form (var.py:102-103)
+        if self.bspline == "identity":  # no shape parameters in the Gaussian model
+            return lp
         sc = one if self.trafo_noncentered else st.tau_delta[c]
         lp = lp + np.sum(
             -0.5 * (st.delta_z[c] / sc) ** 2
@@ -753,16 +855,19 @@ class PTMModel:
             g_dl = np.sum(np.where(m1, lz * cL + ld * (1 - qL), 0.0)) + np.sum(np.where(m0, lz * cLe, 0.0))
             g_vr = np.sum(np.where(m3 | m4, lz, 0.0))
             g_dr = np.sum(np.where(m3, lz * cR + ld * (1 - qR), 0.0)) + np.sum(np.where(m4, lz * cRe, 0.0))
-            g_theta = g_theta + g_vl * Bb0[0] + g_dl * Bb1[0] + g_vr * Bb0[1] + g_dr * Bb1[1]
-            # coefficient map backward (ptm.py:155-172, 210-218)
+            if not getattr(sp, "identity_outside", False):
+                g_theta = g_theta + g_vl * Bb0[0] + g_dl * Bb1[0] + g_vr * Bb0[1] + g_dr * Bb1[1]
+            # coefficient map backward (ptm.py:155-172, 210-218; onion.py:81-108)
             delta = f["delta"]
-            e = theta[1:]
-            Bk = sp.coef_map.B[0]
-            g_e = g_theta[1:] - Bk[1:] * g_theta[0]
-            wts = log_sfn_weights(self.nparam, self.dtype)
+            cm = sp.coef_map
+            e = theta[cm.e_off:cm.e_off + self.nparam]
+            g_e = g_theta[cm.e_off:cm.e_off + self.nparam] - cm.theta0_row(self.nparam) * g_theta[0]
+            wts = cm.weights(self.nparam, self.dtype)
             sm = wts * np.exp(delta - np.max(delta))
             sm = sm / np.sum(sm)
             g_delta = e * g_e - sm * np.sum(e * g_e)
+            if self.bspline == "identity":
+                g_delta = np.zeros_like(g_delta)
             pr = 1.0 if add_priors else 0.0
             if self.trafo_noncentered:  # delta = Z (tau_delta * latent), latent ~ N(0, 1)
                 zg = self.Zd.T @ g_delta
@@ -771,6 +876,9 @@ class PTMModel:
             else:
                 g_dz[c] = self.Zd.T @ g_delta - pr * st.delta_z[c] / st.tau_delta[c] ** 2
                 g_taud[c] = pr * (np.sum(st.delta_z[c] ** 2) / st.tau_delta[c] ** 3 - (self.nparam - 1) / st.tau_delta[c])
+            if self.bspline == "identity":
+                g_dz[c] = 0.0
+                g_taud[c] = 0.0
             for t, term in enumerate(self.terms):
                 ge = g_mu if term.predictor == "loc" else g_ls
                 bt, tau = st.beta[t][c], st.tau[c, t]
@@ -950,6 +1058,9 @@ class PTMModel:
         qR = np.where(rt, 1 - (r - b) / w, dt(0))
         bd = np.where(left[:, None], qL[:, None] * Gd[ia][None, :], bd)
         bd = np.where(right[:, None], qR[:, None] * Gd[ib][None, :], bd)
+        if getattr(sp, "identity_outside", False):  # onion.py:133-138: no coefficient enters off the core
+            bz = np.where((left | right)[:, None], dt(0), bz)
+            bd = np.where((left | right)[:, None], dt(0), bd)
         inv_d = np.where(above, 1 / dsafe, dt(0))
         bdw = bd * inv_d[:, None]
         H_theta = -(bz.T @ bz) - bdw.T @ bdw
@@ -957,15 +1068,21 @@ class PTMModel:
         # coefficient map delta -> theta (ptm.py:155-172, 210-230): first and second derivatives
         delta = self.delta_of(st, c)
         npar = delta.shape[0]
-        wts = log_sfn_weights(npar, self.dtype)
+        if self.bspline == "identity":
+            raise ValueError("the Gaussian model has no shape-parameter block")
+        cm = sp.coef_map
+        wts = cm.weights(npar, self.dtype)
         sm = wts * np.exp(delta - np.max(delta))
         sm = sm / sm.sum()
-        e = theta[1:]
-        Bk = sp.coef_map.B[0]
+        eo = cm.e_off
+        e = theta[eo:eo + npar]
+        Bk = cm.theta0_row(npar)
         J1e = e[:, None] * (np.eye(npar) - sm[None, :])  # de_j / ddelta_l
-        J1 = np.vstack([-(Bk[1:] @ J1e)[None, :], J1e])  # dtheta / ddelta  (J x npar)
+        J1 = np.zeros((theta.shape[0], npar), dtype=self.dtype)  # dtheta / ddelta  (J x npar)
+        J1[0] = -(Bk @ J1e)
+        J1[eo:eo + npar] = J1e
         dsm = sm[:, None] * (np.eye(npar) - sm[None, :])  # dsm_l / ddelta_m
-        g_e = g_theta[1:] - Bk[1:] * g_theta[0]
+        g_e = g_theta[eo:eo + npar] - Bk * g_theta[0]
         T2 = np.einsum("j,jl,jm->lm", g_e * e, np.eye(npar) - sm[None, :], np.eye(npar) - sm[None, :])
         T2 = T2 - (g_e @ e) * dsm
         H_delta = J1.T @ H_theta @ J1 + T2

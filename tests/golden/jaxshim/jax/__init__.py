@@ -134,6 +134,10 @@ class _IndexTrick:
         self.obj = obj
 
     def __getitem__(self, item):
+        if isinstance(item, tuple) and any(_isdual(x) for x in item):
+            # r_[(scalar, dual vector)]: numpy's index trick would iterate the Dual forever
+            assert self.obj is _np.r_
+            return _np.concatenate([x if _isdual(x) else _np.atleast_1d(x) for x in item])
         return _wrap(self.obj[item])
 
 

@@ -416,6 +416,106 @@ def ref_logp(m, out):
              loglik_i=ll_i, loglik_i_nan=ll_i_nan, prior=pri, logp=lp, grad=grad, grad_fd=grad_fd)
 
 
+def ref_variants(m, out):
+    """PTMDist(bspline="onion" | "identity") (model/model.py:98-131) on the data and chain states
+    of ref_logp_n257.npz: OnionKnots / get_onion_fn / OnionSpline (bspline/onion.py, run
+    unmodified) through LocScaleTransformationDist, and GaussianPseudoTransformationDist
+    (dist.py:766-850)."""
+    import jax.numpy as jnp
+    from jax._dual import Dual
+    from tensorflow_probability.substrates.jax import distributions as tfd
+
+    onion = importlib.import_module("liesel_ptm.bspline.onion")
+    assert onion.__file__.startswith(REF), onion.__file__
+    d0 = np.load(os.path.join(out, "ref_logp_n257.npz"))
+    y, params, tau, tau_d, Z_delta = d0["y"], d0["params"], d0["tau"], d0["tau_delta"], d0["trafo_Z"]
+    nparam = int(d0["nparam"])
+    basis = [d0["basis_loc"], d0["basis_scale"]]
+    Zs = [d0["Z0"], d0["Z1"]]
+    Ks = [d0["K0"], d0["K1"]]
+    ranks = [int(d0["rank0"]), int(d0["rank1"])]
+    p = Zs[0].shape[1]
+    C, P = params.shape
+    n_h = int(d0["hess_n"])
+
+    kn = onion.OnionKnots(-4.0, 4.0, nparam)
+    sp = onion.OnionSpline(kn.knots)
+    rng = np.random.default_rng(8)
+    g = A(sp.bspline.grid)
+    r = np.concatenate([g[::9], np.nextafter(g[::9], -np.inf), np.nextafter(g[::9], np.inf), g[-3:], g[:3],
+                        np.linspace(-9, 9, 201), rng.normal(scale=2.5, size=200)])
+    delta = np.stack([np.zeros(nparam), rng.normal(size=nparam), 0.3 * rng.normal(size=nparam)])
+    theta = np.stack([A(sp.compute_coef(dd)) for dd in delta])
+    z = np.zeros((3, r.size))
+    dz = np.zeros_like(z)
+    for c in range(3):
+        zz, dd = sp.dot_and_deriv_n_fullbatch(r, delta[c])
+        z[c], dz[c] = A(zz), A(dd)
+
+    def make_dist(kind, delta_, mu, sigma):
+        if kind == "onion":
+            return m.dist.LocScaleTransformationDist(coef=delta_, loc=mu, scale=sigma, bspline=sp, batched=False)
+        return m.dist.GaussianPseudoTransformationDist(coef=delta_, loc=mu, scale=sigma, batched=False)
+
+    def total(kind, dv, c, rows, per_obs=False):
+        b_loc, b_scale, dzv = dv[:p], dv[p:2 * p], dv[2 * p:]
+        mu = basis[0][rows] @ (Zs[0] @ b_loc)
+        sigma = np.exp(basis[1][rows] @ (Zs[1] @ b_scale))
+        ll = make_dist(kind, Z_delta @ dzv, mu, sigma).log_prob(jnp.asarray(y[rows]))
+        if per_obs:
+            return ll
+        tot = np.sum(ll)
+        for t, b in enumerate((b_loc, b_scale)):
+            dd = m.gamdist.MultivariateNormalSingular(loc=0.0, scale=tau[c, t], penalty=Ks[t], penalty_rank=ranks[t])
+            tot = tot + dd.log_prob(b)
+        if kind == "onion":  # the Gaussian model has no shape parameters (new_gaussian adds no trafo term)
+            tot = tot + np.sum(tfd.Normal(loc=0.0, scale=tau_d[c]).log_prob(dzv))
+        return tot
+
+    res = {}
+    allrows = slice(None)
+    for kind in ("onion", "identity"):
+        ll_i = np.zeros((C, y.shape[0]))
+        lp = np.zeros(C)
+        grad = np.zeros((C, P))
+        for c in range(C):
+            ll_i[c] = A(total(kind, params[c], c, allrows, per_obs=True))
+            lp[c] = float(total(kind, params[c], c, allrows))
+            for k in range(P):
+                e = np.zeros(P)
+                e[k] = 1.0
+                t_ = total(kind, Dual(params[c], e), c, allrows)
+                grad[c, k] = float(t_.t) if isinstance(t_, Dual) else 0.0
+        res[kind] = (ll_i, lp, grad)
+
+    def hessian_block(kind, v, c, lo, hi):
+        dd = hi - lo
+        H = np.zeros((dd, dd))
+        rows = slice(0, n_h)
+        for i in range(dd):
+            ei = np.zeros(P)
+            ei[lo + i] = 1.0
+            for j in range(i + 1):
+                ej = np.zeros(P)
+                ej[lo + j] = 1.0
+                tot = total(kind, Dual(Dual(v, ej, 1), ei, 2), c, rows)
+                H[i, j] = H[j, i] = float(tot.t.t)
+        return H
+
+    hess = {"onion_loc": hessian_block("onion", params[0], 0, 0, p),
+            "onion_scale": hessian_block("onion", params[0], 0, p, 2 * p),
+            "onion_dz": hessian_block("onion", params[0], 0, 2 * p, P),
+            "identity_loc": hessian_block("identity", params[0], 0, 0, p),
+            "identity_scale": hessian_block("identity", params[0], 0, p, 2 * p)}
+    np.savez(os.path.join(out, "ref_variants_n257.npz"),
+             onion_knots=A(kn.knots), onion_step=A(kn.step), onion_grid=g, r=r, delta=delta, onion_theta=theta,
+             onion_z=z, onion_d=dz, onion_min_knot=A(sp.min_knot), onion_max_knot=A(sp.max_knot),
+             onion_loglik_i=res["onion"][0], onion_logp=res["onion"][1], onion_grad=res["onion"][2],
+             identity_loglik_i=res["identity"][0], identity_logp=res["identity"][1],
+             identity_grad=res["identity"][2], hess_n=n_h,
+             **{f"hess_{k}": v for k, v in hess.items()})
+
+
 def main():
     warnings.filterwarnings("ignore")
     np.seterr(all="ignore")
@@ -424,6 +524,7 @@ def main():
     ref_basis(m, out)
     ref_trafo(m, out)
     ref_logp(m, out)
+    ref_variants(m, out)
     print("reference fixtures written to", out)
 
 

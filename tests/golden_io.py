@@ -16,16 +16,21 @@ def load(name):
     return np.load(os.path.join(GOLDEN, name))
 
 
-def model_from_fixture(d, dtype=np.float64, device="cuda:0", n_rows=None):
+def model_from_fixture(d, dtype=np.float64, device="cuda:0", n_rows=None, bspline="ptm"):
     """Product model built from the fixture's reparameterisation DATA (Z, K, knots);
-    ``n_rows`` keeps the first observations only."""
+    ``n_rows`` keeps the first observations only; ``bspline`` as PTMDist takes it
+    (model/model.py:98-131)."""
     if n_rows is not None:
         d = dict(d)
         d["y"] = d["y"][:n_rows]
         for t in range(int(d["n_terms"])):
             d[f"x{t}"] = d[f"x{t}"][:n_rows]
-    model = lp.LocScalePTM.new_ptm(d["y"].astype(dtype), nparam=int(d["nparam"]),
-                                   to_float32=(np.dtype(dtype) == np.float32), device=device)
+    f32 = np.dtype(dtype) == np.float32
+    if bspline == "ptm":
+        model = lp.LocScalePTM.new_ptm(d["y"].astype(dtype), nparam=int(d["nparam"]), to_float32=f32, device=device)
+    else:
+        kn = (lp.OnionKnots if bspline == "onion" else lp.PTMKnots)(-4.0, 4.0, int(d["nparam"]), dtype=dtype)
+        model = lp.LocScalePTM(d["y"].astype(dtype), kn.knots, to_float32=f32, device=device, bspline=bspline)
     for t in range(int(d["n_terms"])):
         Z = d[f"Z{t}"].astype(dtype)
         basis = lp.Basis(x=d[f"x{t}"].astype(dtype), xname=f"x{t}", knots=d[f"knots{t}"].astype(dtype),
@@ -42,13 +47,13 @@ def model_from_fixture(d, dtype=np.float64, device="cuda:0", n_rows=None):
     return model
 
 
-def oracle_from_fixture(d):
+def oracle_from_fixture(d, bspline="ptm"):
     terms = [
         o.term_from_reparam(d[f"x{t}"], d[f"knots{t}"], d[f"Z{t}"], d[f"K{t}"], int(d[f"rank{t}"]),
                             "loc" if int(d[f"pred{t}"]) == 0 else "scale")
         for t in range(int(d["n_terms"]))
     ]
-    om = o.PTMModel(d["y"], terms, nparam=int(d["nparam"]))
+    om = o.PTMModel(d["y"], terms, nparam=int(d["nparam"]), bspline=bspline)
     om.Zd = d["trafo_Z"]
     return om
 

@@ -36,15 +36,20 @@ def rel_err(a, b):
 
 def build_case(n=500, n_loc=2, n_scale=1, nbases=12, nparam=20, C=3, dtype=np.float64, seed=0,
                build=True, y_override=None, amp=0.1, beta0=0.05, gamma0=-0.03, tau=None,
-               nbases_list=None, device="cuda:0") -> Case:
+               nbases_list=None, device="cuda:0", bspline="ptm") -> Case:
     y, X = o.synth_data(max(n, 64), n_loc, n_scale, seed=seed, dtype=dtype)
     y, X = y[:n], X[:, :n]
     if y_override is not None:
         y = y_override(y)
     T = n_loc + n_scale
     nbl = nbases_list or [nbases] * T
-    model = lp.LocScalePTM.new_ptm(y, nparam=nparam, to_float32=(np.dtype(dtype) == np.float32),
-                                   device=device)
+    if bspline == "ptm":
+        model = lp.LocScalePTM.new_ptm(y, nparam=nparam, to_float32=(np.dtype(dtype) == np.float32),
+                                       device=device)
+    else:
+        kn = (lp.OnionKnots if bspline == "onion" else lp.PTMKnots)(-4.0, 4.0, nparam, dtype=dtype)
+        model = lp.LocScalePTM(y, kn.knots, to_float32=(np.dtype(dtype) == np.float32), device=device,
+                               bspline=bspline)
     oterms = []
     for t in range(T):
         # knots from the covariate's design range (not the sample) so that n = 1 works
@@ -57,7 +62,7 @@ def build_case(n=500, n_loc=2, n_scale=1, nbases=12, nparam=20, C=3, dtype=np.fl
             model.scale += tm
         oterms.append(o.term_from_reparam(X[t], basis.knots, basis.Z, basis.penalty, tm.penalty_rank,
                                           "loc" if t < n_loc else "scale"))
-    omodel = o.PTMModel(y, oterms, nparam=nparam, dtype=dtype)
+    omodel = o.PTMModel(y, oterms, nparam=nparam, dtype=dtype, bspline=bspline)
     omodel.Zd = lp.trafo_reparam(nparam, dtype)  # same reparameterisation data on both sides
     st = o.synth_state(oterms, nparam, C, seed=seed + 1, dtype=dtype, amp=amp)
     st.beta0[:] = beta0

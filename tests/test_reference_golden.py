@@ -168,7 +168,7 @@ def test_reference_fixtures_are_reproducible(tmp_path):
     script = os.path.join(golden_io.GOLDEN, "make_reference_golden.py")
     env = dict(os.environ, PTM_GOLDEN_OUT=str(tmp_path))
     subprocess.run([sys.executable, script], check=True, env=env, capture_output=True, timeout=600)
-    for name in ("ref_basis_nb20.npz", "ref_trafo_nparam20.npz", "ref_logp_n257.npz"):
+    for name in ("ref_basis_nb20.npz", "ref_trafo_nparam20.npz", "ref_logp_n257.npz", "ref_variants_n257.npz"):
         new, old = np.load(tmp_path / name), golden_io.load(name)
         assert sorted(new.files) == sorted(old.files)
         for k in old.files:
