@@ -465,9 +465,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
             const float es = gamma0 + (hasq1 ? eb[(OPW + i) * 32 + lane] : 0.f);
             const float einv = mtc_exp(-es);
             const float r = (yv - em) * einv;
-            const int code = region_code(ts, r);
-            const bool core = code == 2;
-            const float rc = r < ts.a ? ts.a : (r > ts.b ? ts.b : (r == r ? r : ts.a));
+            const float rc = fminf(fmaxf(r, ts.a), ts.b);  // NaN -> a
+            const bool core = rc == r;
+            const int code = core ? 2 : region_code(ts, r);
             CoreEval<float> ev;
             core_locate_fast(ts, a.grid, rc, ev);
             const float* cp = ccl + (ev.kk * 5) * 128;
@@ -567,18 +567,26 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(tt.y));
             const float2 einv = pfma(ex, pmul(ee, p1(0.69314718055994530942f)), ex);
             const float2 r = pmul(psub(yv, em), einv);
-            const int code0 = region_code(ts, r.x), code1 = region_code(ts, r.y);
-            const bool core0 = code0 == 2, core1 = code1 == 2;
-            const float rc0 = r.x < ts.a ? ts.a : (r.x > ts.b ? ts.b : (r.x == r.x ? r.x : ts.a));
-            const float rc1 = r.y < ts.a ? ts.a : (r.y > ts.b ? ts.b : (r.y == r.y ? r.y : ts.a));
-            CoreEval<float> e0, e1;
-            core_locate_fast(ts, a.grid, rc0, e0);
-            core_locate_fast(ts, a.grid, rc1, e1);
+            // clamp to the core (NaN -> a); a point is in the core iff the clamp left it alone
+            const float2 rc = p2(fminf(fmaxf(r.x, ts.a), ts.b), fminf(fmaxf(r.y, ts.a), ts.b));
+            const bool core0 = rc.x == r.x, core1 = rc.y == r.y;
+            // core_locate_fast (ptm_math.cuh) for both observations
+            const float2 tg2 = pmul(psub(rc, p1(ts.a)), p1(ts.inv_h));
+            float2 fm = p2(floorf(tg2.x), floorf(tg2.y));
+            float2 frac = psub(tg2, fm);
+            if (frac.x < ts.frac_eps || frac.x > 1.f - ts.frac_eps) grid_cell_exact(ts, a.grid, rc.x, fm.x, frac.x);
+            if (frac.y < ts.frac_eps || frac.y > 1.f - ts.frac_eps) grid_cell_exact(ts, a.grid, rc.y, fm.y, frac.y);
+            const float2 pp = pmul(fm, S1);
+            const float kmax = (float)(KK - 1);
+            const float2 fk = p2(fminf(floorf(pp.x), kmax), fminf(floorf(pp.y), kmax));
+            struct { int kk; } e0{(int)fk.x}, e1{(int)fk.y};
+            const float2 u = psub(pp, fk), kap = pmul(frac, p1(ts.kap_scale));
+            const float2 over = padd(padd(u, S1), p1(-1.f));
+            const float2 mm = p2(fmaxf(over.x, 0.f), fmaxf(over.y, 0.f));
             const float* cp0 = ccl + (e0.kk * 5) * 128;
             const float* cp1 = ccl + (e1.kk * 5) * 128;
             const float2 c0 = p2(cp0[0], cp1[0]), c1 = p2(cp0[128], cp1[128]), c2 = p2(cp0[256], cp1[256]);
             const float2 c3 = p2(cp0[384], cp1[384]), jmp = p2(cp0[512], cp1[512]);
-            const float2 u = p2(e0.u, e1.u), kap = p2(e0.kappa, e1.kappa), mm = p2(e0.mm, e1.mm);
             // core_eval (ptm_math.cuh), two observations per instruction
             const float2 b2 = pfma(u, c3, c2);
             const float2 b1 = pfma(u, b2, c1);
@@ -600,9 +608,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
               // transitions / tails of either observation: the scalar closed forms (ptm.py:349-410)
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                const int code = h ? code1 : code0;
-                if (code == 2) continue;
+                if (h ? core1 : core0) continue;
                 const float rr = h ? r.y : r.x;
+                const int code = region_code(ts, rr);
                 float zz, dd, dzr, ddr, cfac = 0.f, qfac = 0.f;
                 if (code == 1) {
                   const float dL = ccl[(KK * 5 + 1) * 128], constL = ccl[(NCC + 0) * 128];
@@ -691,8 +699,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
             if (!(core0 && core1)) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                const int code = h ? code1 : code0;
-                if (code == 2) continue;
+                if (h ? core1 : core0) continue;
+                const int code = region_code(ts, h ? r.y : r.x);
                 const float lzz = h ? lz.y : lz.x, ldd = h ? ld.y : ld.x;
                 const double dv = (double)fmaf(lzz, cf[h], ldd * qf[h]);
                 if (code <= 1) { a_gvl += (double)lzz; a_gdl += dv; }
