@@ -397,29 +397,53 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
       const float* Ex0 = g.E[0] + eoff;
       const float* Ex1 = g.E[1] + eoff;
       float* Eout = g.E[mma0 ? 0 : 1] + eoff;  // eta-only launch: its one predictor
-      for (int s = 0; s < ntiles; ++s, ++tg) {
-        const long long base = o_begin + (long long)s * NT + sub * OPW;
-        // this warp's responses of the tile: one coalesced load, in flight while eta is waited for
-        float yreg = 0.f;
-        if (lane < OPW && base + lane < o_end) yreg = a.y[base + lane];
-        // external parts of the predictors (multi-pass form), also in flight during the wait
+      const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + etaCol + (uint32_t)(sub * OPW);
+      constexpr int EBS = 2 * OPW * 32 + 32;  // floats of the eta buffer: [2][OPW][32 chains] + the responses
+      float* eb = s_eta + warp * EBS;
+      (void)eb;
+      // eta of tile s2 -> the warp's shared buffer (+ the external parts of the multi-pass form, + the
+      // responses), then the accumulators go back to the MMA warp
+      auto copy_eta = [&](int s2, float ynew, float* ebuf, uint32_t par) {
+        const long long b2 = o_begin + (long long)s2 * NT + sub * OPW;
         float ex0[OPW], ex1[OPW];
 #pragma unroll
         for (int c = 0; c < OPW; ++c) { ex0[c] = 0.f; ex1[c] = 0.f; }
-        if (!ETAONLY && (ext0 || ext1)) {
+        if (ext0 || ext1) {  // in flight during the wait
 #pragma unroll
           for (int c = 0; c < OPW; ++c)
-            if (base + c < o_end) {
-              if (ext0) ex0[c] = __ldcs(Ex0 + (base + c - a.obs_begin) * 128);
-              if (ext1) ex1[c] = __ldcs(Ex1 + (base + c - a.obs_begin) * 128);
+            if (b2 + c < o_end) {
+              if (ext0) ex0[c] = __ldcs(Ex0 + (b2 + c - a.obs_begin) * 128);
+              if (ext1) ex1[c] = __ldcs(Ex1 + (b2 + c - a.obs_begin) * 128);
             }
         }
+        mtc_wait(barE, par);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < OPW; c += 4) {
+          uint32_t v[4], w[4];
+          mtc_ld4(addr + c, v);
+          mtc_ld4(addr + NT + c, w);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ebuf[(c + j) * 32 + lane] = (mma0 ? __uint_as_float(v[j]) : 0.f) + ex0[c + j];
+            ebuf[(OPW + c + j) * 32 + lane] = (mma1 ? __uint_as_float(w[j]) : 0.f) + ex1[c + j];
+          }
+        }
+        if (lane < OPW) ebuf[2 * OPW * 32 + lane] = ynew;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mtc_arrive(barC);
+      };
+      (void)copy_eta;
+      // this warp's responses of a tile: one coalesced load, requested a tile ahead
+      float yreg = 0.f;
+      if (ntiles > 0 && lane < OPW && o_begin + sub * OPW + lane < o_end) yreg = a.y[o_begin + sub * OPW + lane];
+      for (int s = 0; s < ntiles; ++s, ++tg) {
+        const long long base = o_begin + (long long)s * NT + sub * OPW;
+        if constexpr (ETAONLY) {
         mtc_wait(barE, tg & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + etaCol + (uint32_t)(sub * OPW);
-        float* eb = s_eta + warp * (2 * OPW * 32 + 32);
-        (void)eb;
-        if constexpr (ETAONLY) {
           // eta of the one predictor this launch carries -> HBM, nothing else
           const uint32_t ecol = addr + (g.Kq[0] > 0 ? 0u : (uint32_t)NT);
 #pragma unroll
@@ -439,22 +463,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
           if (lane == 0) mtc_arrive(barC);
         }
         if constexpr (!ETAONLY) {
-#pragma unroll
-        for (int c = 0; c < OPW; c += 4) {
-          uint32_t v[4], w[4];
-          mtc_ld4(addr + c, v);
-          mtc_ld4(addr + NT + c, w);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            eb[(c + j) * 32 + lane] = (mma0 ? __uint_as_float(v[j]) : 0.f) + ex0[c + j];
-            eb[(OPW + c + j) * 32 + lane] = (mma1 ? __uint_as_float(w[j]) : 0.f) + ex1[c + j];
-          }
-        }
-        if (lane < OPW) eb[2 * OPW * 32 + lane] = yreg;
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mtc_arrive(barC);
+        copy_eta(s, yreg, eb, tg & 1);
+        // the next tile's responses, requested a tile ahead
+        float ynext = 0.f;
+        if (s + 1 < ntiles && lane < OPW && base + NT + lane < o_end) ynext = a.y[base + NT + lane];
         float t_z2 = 0.f, t_ls = 0.f, t_gb0 = 0.f, t_gg0 = 0.f, t_ld = 0.f;
         const int cnt = (int)((o_end - base) < OPW ? (o_end - base) : OPW);
         auto eval_one = [&](int i) {
@@ -710,6 +722,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
           }
         }
         for (; i0 < cnt; ++i0) eval_one(i0);
+        yreg = ynext;
         // per-tile float sums -> double (a tile is at most 16 observations per warp)
         a_z2 += (double)t_z2;
         a_ls += (double)t_ls;
