@@ -22,6 +22,13 @@ hdr = rows[1]
 isrc, iex, ismp, iw = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("L1 Wavefronts Shared")
 data = [(int(r[iex]), int(r[ismp]), r[isrc].strip(), int(r[iw] or 0)) for r in rows[2:] if len(r) > iex]
 tot = sum(d[0] for d in data); ts = sum(d[1] for d in data)
+# the source page can count more than the kernel executed (it did by 1.42x on k_main_tc): scale the
+# per-instruction counts so that they add up to smsp__inst_executed.sum of the raw page
+ex_raw = float(m['smsp__inst_executed.sum'][1]) if 'smsp__inst_executed.sum' in m else tot
+scale = ex_raw / tot if tot else 1.0
+print(f"\nsmsp__inst_executed.sum {ex_raw:.4e}; source-page sum {tot:.4e} (counts below scaled by {scale:.3f})")
+data = [(e * scale, s_, srcl, w) for e, s_, srcl, w in data]
+tot = ex_raw
 print(f"\nwarp instructions per obs-row: {tot / rows_per:.1f}   shared wavefronts per obs-row: {sum(d[3] for d in data) / rows_per:.1f}")
 start = ex = sm = wf = 0
 for i, (e, s_, srcl, w) in enumerate(data):
