@@ -469,7 +469,7 @@ Plan make_plan(const PtmProblem* pr, long long C) {
       return (size_t)2 * nt * Kt * 4 + (size_t)(NCC + 4) * 128 * 4 + (size_t)ptm::kMtcEvalWarps * NGV * 32 * 4 +
              (size_t)T * 4 * ptm::kKnotStride * 4 +
              std::max((size_t)ptm::kMtcEvalWarps * ptm::kRegSlots * 32 * 8,            // reduction scratch, aliased
-                      (size_t)ptm::kMtcEvalWarps * (2 * (nt / 4) * 32 + 32) * 4) + 128;  // onto the eta buffers
+                      (size_t)ptm::kMtcEvalWarps * (2 * (nt / 4) * 32) * 4) + 128;  // onto the eta buffers
     };
     while (NT > 32 && fwd_smem(NT) > 227 * 1024 - 1280) NT -= 16;
     if (groups_ok && Kt <= ptm::kMtcMaxK && NT > 0 && K16t <= 256 && len > 0) {

@@ -398,12 +398,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
       const float* Ex1 = g.E[1] + eoff;
       float* Eout = g.E[mma0 ? 0 : 1] + eoff;  // eta-only launch: its one predictor
       const uint32_t addr = tmem + ((uint32_t)(q4 * 32) << 16) + etaCol + (uint32_t)(sub * OPW);
-      constexpr int EBS = 2 * OPW * 32 + 32;  // floats of the eta buffer: [2][OPW][32 chains] + the responses
+      constexpr int EBS = 2 * OPW * 32;  // floats of the eta buffer: [2 predictors][OPW][32 chains]
       float* eb = s_eta + warp * EBS;
       (void)eb;
-      // eta of tile s2 -> the warp's shared buffer (+ the external parts of the multi-pass form, + the
-      // responses), then the accumulators go back to the MMA warp
-      auto copy_eta = [&](int s2, float ynew, float* ebuf, uint32_t par) {
+      // eta of tile s2 -> the warp's shared buffer (+ the external parts of the multi-pass form), then
+      // the accumulators go back to the MMA warp
+      auto copy_eta = [&](int s2, float* ebuf, uint32_t par) {
         const long long b2 = o_begin + (long long)s2 * NT + sub * OPW;
         float ex0[OPW], ex1[OPW];
 #pragma unroll
@@ -430,7 +430,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
             ebuf[(OPW + c + j) * 32 + lane] = (mma1 ? __uint_as_float(w[j]) : 0.f) + ex1[c + j];
           }
         }
-        if (lane < OPW) ebuf[2 * OPW * 32 + lane] = ynew;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mtc_arrive(barC);
@@ -463,7 +462,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
           if (lane == 0) mtc_arrive(barC);
         }
         if constexpr (!ETAONLY) {
-        copy_eta(s, yreg, eb, tg & 1);
+        copy_eta(s, eb, tg & 1);
         // the next tile's responses, requested a tile ahead
         float ynext = 0.f;
         if (s + 1 < ntiles && lane < OPW && base + NT + lane < o_end) ynext = a.y[base + NT + lane];
@@ -472,7 +471,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
         auto eval_one = [&](int i) {
           const long long gi = base + i;
           {
-            const float yv = eb[2 * OPW * 32 + i];
+            const float yv = __shfl_sync(0xffffffffu, yreg, i);  // lane i holds the response of observation i
             const float em = beta0 + (hasq0 ? eb[i * 32 + lane] : 0.f);
             const float es = gamma0 + (hasq1 ? eb[(OPW + i) * 32 + lane] : 0.f);
             const float einv = mtc_exp(-es);
@@ -567,7 +566,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
           const float2 S1 = p1(ts.ratio), S3 = p1(3.f * ts.ratio), IDK = p1(ts.inv_dk);
           for (; i0 + 1 < cnt; i0 += 2) {
             const long long gi = base + i0;
-            const float2 yv = p2(eb[2 * OPW * 32 + i0], eb[2 * OPW * 32 + i0 + 1]);
+            const float2 yv = p2(__shfl_sync(0xffffffffu, yreg, i0), __shfl_sync(0xffffffffu, yreg, i0 + 1));
             const float2 em = padd(p1(beta0), hasq0 ? p2(eb[i0 * 32 + lane], eb[(i0 + 1) * 32 + lane]) : p1(0.f));
             const float2 es = padd(p1(gamma0), hasq1 ? p2(eb[(OPW + i0) * 32 + lane], eb[(OPW + i0 + 1) * 32 + lane]) : p1(0.f));
             // einv = exp(-es): 2^t (1 + e ln 2), t = fl(-es log2 e), e = the recovered rounding error
