@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
   const MainArgs<float>& a = g.a;
   constexpr int OPW = NT / 4;  // observations per eval warp and tile
   extern __shared__ __align__(128) unsigned char smem_mtc[];
-  __shared__ __align__(8) uint64_t s_bar[3];  // [0] eta ready (MMA commit), [1] eta consumed, [2] B tile filled
+  __shared__ __align__(8) uint64_t s_bar[5];  // [0] eta ready (all MMAs of the tile), [1] eta consumed,
+                                              // [2], [3] mu / sigma block of the B tile filled, [4] mu MMAs done
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = a.T, KK = a.KK, Kt = g.Kt, NSW = g.NSW;
@@ -206,6 +207,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[1])), "r"(kMtcEvalWarps));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[2])), "r"(NSW));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[3])), "r"(NSW));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[4])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -217,7 +220,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
-  const uint32_t barE = smem_u32(&s_bar[0]), barC = smem_u32(&s_bar[1]), barB = smem_u32(&s_bar[2]);
+  const uint32_t barE = smem_u32(&s_bar[0]), barC = smem_u32(&s_bar[1]), barB = smem_u32(&s_bar[2]);  // barB + 8: sigma block
+  const uint32_t barM0 = smem_u32(&s_bar[4]);
   const uint32_t etaCol = (uint32_t)(2 * Kt);
   const TrafoScal<float> ts = a.ts;
   uint32_t tg = 0;  // tiles this CTA has gone through (phase parity of all three barriers)
@@ -308,13 +312,22 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
 #pragma unroll
         for (int ti = 0; ti < 8; ++ti) { xc[ti][0] = xn[ti][0]; xc[ti][1] = xn[ti][1]; }
         if (s + 1 < ntiles) fetch_x(s + 1);
-        if (tg > 0) mtc_wait(barE, (tg - 1) & 1);  // the MMAs that read the tile have completed
         const long long base = o_begin + (long long)s * NT;
+        // the two predictor blocks of the tile are filled, multiplied and released one after the
+        // other: the MMAs of the mu block run while the sigma block is being written, and the mu
+        // block of the next tile is rewritten while the sigma MMAs of this one still run
+        // (logp-only sweep: there the fill -> MMA chain paces the tile, 9.4 -> 7.6 ms on c3; with the
+        //  gradient the eval warps pace it and the split costs 1.3 ms, so that form fills in one go)
+        constexpr int NPASS = GRAD ? 1 : 2;
+#pragma unroll 1
+        for (int q = 0; q < NPASS; ++q) {
+        if (tg > 0) mtc_wait((NPASS == 2 && q == 0) ? barM0 : barE, (tg - 1) & 1);  // the MMAs that read the block have completed
 #pragma unroll
         for (int ti = 0; ti < 8; ++ti) {
           const int t = sidx + ti * NSW;
           if (t >= T) break;
           if (g.kcol[t] < 0) continue;  // several-pass form: the term belongs to another launch
+          if (NPASS == 2 && (g.Kq[1] > 0 && g.kcol[t] >= g.kbase[1]) != (q == 1)) continue;  // the other block
           const float* kn = s_kn + t * 4 * kKnotStride;
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
@@ -352,17 +365,21 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mtc_arrive(barB);
+        if (lane == 0) {
+          if (NPASS == 2) mtc_arrive(barB + 8 * q);
+          else { mtc_arrive(barB); mtc_arrive(barB + 8); }
+        }
+        }
       }
     } else if (is_mma) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | (8u << 24);
       for (int s = 0; s < ntiles; ++s, ++tg) {
         if (lane == 0) {
-          mtc_wait(barB, tg & 1);                      // design tile written
           if (tg > 0) mtc_wait(barC, (tg - 1) & 1);    // eval warps have read the previous eta
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
+            mtc_wait(barB + 8 * q, tg & 1);            // this block of the design tile is written
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = tmem + etaCol + (uint32_t)(q * NT);
             const int nks = g.Kq[q] >> 3;
             for (int ks = 0; ks < nks; ++ks) {
@@ -374,8 +391,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
               mtc_mma_ts(d, a_hi, b_lo, idesc, 1u);
               mtc_mma_ts(d, a_lo, b_hi, idesc, 1u);
             }
+            mtc_commit(q == 0 ? barM0 : barE);
           }
-          mtc_commit(barE);
         }
         __syncwarp();
       }
