@@ -25,7 +25,7 @@
 //
 // TMEM budget (512 columns): 2 K (Gamma hi, lo) + 2 NT (eta)  and  2 K16 + 256 (G tiles), so the
 // single-launch form takes models with K = sum of bases <= 224 (c3: 5 + 5 terms x 20 -> 208,
-// NT = 32 by shared memory).  Larger models run in several passes (make_plan, ptm_capi.cu):
+// NT = 48 by shared memory).  Larger models run in several passes (make_plan, ptm_capi.cu):
 // groups of whole terms of one predictor (<= 224 coefficients) go through the ETAONLY
 // instantiation, which writes / accumulates its partial predictor to E[q] in HBM; the main launch
 // carries the remaining terms and adds the external parts (ext_mask); k_grad_tc runs once per
