@@ -316,18 +316,19 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
         // the two predictor blocks of the tile are filled, multiplied and released one after the
         // other: the MMAs of the mu block run while the sigma block is being written, and the mu
         // block of the next tile is rewritten while the sigma MMAs of this one still run
-        // (logp-only sweep: there the fill -> MMA chain paces the tile, 9.4 -> 7.6 ms on c3; with the
-        //  gradient the eval warps pace it and the split costs 1.3 ms, so that form fills in one go)
-        constexpr int NPASS = GRAD ? 1 : 2;
+        // (the logp-only sweep is paced by this chain: 9.4 -> 7.6 ms on c3.  With the gradient only
+        //  the fill side is split -- 14.7 -> 14.2 ms; rewriting the mu block of the next tile under
+        //  the running sigma MMAs costs that form 1.8 ms, so there both blocks wait for barE)
+        constexpr int NPASS = 2;
 #pragma unroll 1
         for (int q = 0; q < NPASS; ++q) {
-        if (tg > 0) mtc_wait((NPASS == 2 && q == 0) ? barM0 : barE, (tg - 1) & 1);  // the MMAs that read the block have completed
+        if (tg > 0) mtc_wait((!GRAD && q == 0) ? barM0 : barE, (tg - 1) & 1);  // the MMAs that read the block have completed
 #pragma unroll
         for (int ti = 0; ti < 8; ++ti) {
           const int t = sidx + ti * NSW;
           if (t >= T) break;
           if (g.kcol[t] < 0) continue;  // several-pass form: the term belongs to another launch
-          if (NPASS == 2 && (g.Kq[1] > 0 && g.kcol[t] >= g.kbase[1]) != (q == 1)) continue;  // the other block
+          if ((g.Kq[1] > 0 && g.kcol[t] >= g.kbase[1]) != (q == 1)) continue;  // the other block
           const float* kn = s_kn + t * 4 * kKnotStride;
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
@@ -366,8 +367,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_main_tc(const MainTcArgs g) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          if (NPASS == 2) mtc_arrive(barB + 8 * q);
-          else { mtc_arrive(barB); mtc_arrive(barB + 8); }
+          mtc_arrive(barB + 8 * q);
         }
         }
       }
