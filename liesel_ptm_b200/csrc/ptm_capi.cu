@@ -464,7 +464,22 @@ Plan make_plan(const PtmProblem* pr, long long C) {
     const bool two_pass = ngroups > 1;
     const int avail = (512 - 2 * Kt) / 2;
     int NT = avail >= 64 ? 64 : (avail >= 48 ? 48 : (avail >= 32 ? 32 : 0));
-    const int NSW = std::min(T, pr->tune.mtc_nsw > 0 ? std::min(pr->tune.mtc_nsw, 7) : 6);
+    // stager warps: the terms of a predictor block of a launch are dealt round-robin (term index
+    // modulo NSW) and the two blocks of a tile are filled one after the other, so the count that
+    // gives every warp the same number of terms per block is the one to take (c3: 5 + 5 terms -> 5,
+    // 14.2 -> 14.05 ms; c4: 7 location terms in the eta-only launch -> 7; tools/mtc_c5_nsw.py)
+    int nsw_auto = std::max(1, (T + 7) / 8);
+    for (int gi = 0; gi < ngroups; ++gi)
+      for (int q = 0; q < 2; ++q) {
+        int tq = 0;
+        for (int t = 0; t < T; ++t)
+          if ((groups[gi] >> t & 1u) && (pr->pred[t] == PTM_LOC ? 0 : 1) == q) ++tq;
+        if (tq > 0) {
+          const int rounds = (tq + 6) / 7;
+          nsw_auto = std::max(nsw_auto, (tq + rounds - 1) / rounds);
+        }
+      }
+    const int NSW = std::min(T, pr->tune.mtc_nsw > 0 ? std::min(pr->tune.mtc_nsw, 7) : nsw_auto);
     auto fwd_smem = [&](int nt) {
       return (size_t)2 * nt * Kt * 4 + (size_t)(NCC + 4) * 128 * 4 + (size_t)ptm::kMtcEvalWarps * NGV * 32 * 4 +
              (size_t)T * 4 * ptm::kKnotStride * 4 +
