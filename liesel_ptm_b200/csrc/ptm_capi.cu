@@ -832,13 +832,17 @@ int eval_impl(const PtmProblem* pr, const R* params, long long C, R* logp, R* gr
   po.add_priors = pr->add_priors;
   po.nc_dz = pr->nc_dz;
   for (int t = 0; t < pr->T; ++t) po.nc[t] = pr->nc[t];
-  const size_t smem_post = ((size_t)ma.NSLOT * 32 + (size_t)std::max(pr->T, 1) * 32) * sizeof(double);
+  size_t smem_post = ((size_t)ma.NSLOT * 32 + (size_t)std::max(pr->T, 1) * 32) * sizeof(double);
+  // the 32 parameter rows of a chain group next to the reduced partials when they fit
+  po.stage_par = smem_post + (size_t)32 * pr->P * sizeof(R) <= 200 * 1024 ? 1 : 0;
+  if (po.stage_par) smem_post += (size_t)32 * pr->P * sizeof(R);
   if (want_grad) {
     auto kp = ptm::k_post<R, true>;
     PTM_CUDA(ptm::ensure_smem(kp, smem_post));
     kp<<<pl.CG, 256, smem_post, st>>>(po);
   } else {
     auto kp = ptm::k_post<R, false>;
+    PTM_CUDA(ptm::ensure_smem(kp, smem_post));
     kp<<<pl.CG, 256, smem_post, st>>>(po);
   }
   PTM_CUDA(cudaGetLastError());

@@ -904,6 +904,7 @@ struct PostArgs {
   int dz_off, tau_off, taud_off;
   long long n_obs;
   int add_priors;
+  int stage_par;     // the 32 parameter rows of the chain group are staged in shared memory (coalesced load)
   int nc[kMaxTerms], nc_dz;  // non-centred parameterisations (see PreArgs)
 };
 
@@ -925,15 +926,25 @@ __global__ void k_post(const PostArgs<R> a) {
     for (int m = 0; m < a.M; ++m) v += pp[(long long)m * a.NSLOT * 32];
     red[idx] = v;
   }
+  // parameter rows of the group: read once, coalesced (the per-lane reads below stride by P)
+  R* s_par = reinterpret_cast<R*>(s_lp + (a.T > 0 ? a.T : 1) * 32);
+  if (a.stage_par) {
+    const long long row0 = (long long)cg * 32;
+    const int rows = a.C - cg * 32 < 32 ? a.C - cg * 32 : 32;
+    for (int idx = tid; idx < rows * a.P; idx += blockDim.x) s_par[idx] = a.params[row0 * a.P + idx];
+  }
   __syncthreads();
   const D half_log_2pi = 0.91893853320467274178;
+  auto par_of = [&](int lane_, int c_) -> const R* {
+    return a.stage_par ? s_par + (long long)lane_ * a.P : a.params + (long long)c_ * a.P;
+  };
 
   // smooth-term priors and gradients: one thread per (lane, term)
   for (int idx = tid; idx < 32 * a.T; idx += blockDim.x) {
     const int lane = idx & 31, t = idx >> 5;
     const int c = cg * 32 + lane;
     if (c >= a.C) continue;
-    const R* par = a.params + (long long)c * a.P;
+    const R* par = par_of(lane, c);
     const R* b = par + a.boff[t];
     const R* Kt = a.Kall + a.koff[t];
     const int p = a.p[t];
@@ -965,17 +976,19 @@ __global__ void k_post(const PostArgs<R> a) {
       a.grad[(long long)c * a.ld_grad + a.tau_off + t] = (R)gt;
     }
   }
-  if (GRAD) {
-    // grad beta_t[k] = sum_j Z_t[j][k] Ggamma_t[j] - (K_t beta_t)[k] / tau_t^2
+  __syncthreads();  // s_lp complete: the first warp goes on to the transformation block below
+  if (GRAD && tid >= 32) {
+    // grad beta_t[k] = sum_j Z_t[j][k] Ggamma_t[j] - (K_t beta_t)[k] / tau_t^2  (warps 1.., while
+    // warp 0 runs the per-chain transformation block)
     for (int t = 0; t < a.T; ++t) {
       const int p = a.p[t], nb = a.nb[t];
       const R* Zt = a.Zall + a.zoff[t];
       const R* Kt = a.Kall + a.koff[t];
-      for (int idx = tid; idx < 32 * p; idx += blockDim.x) {
+      for (int idx = tid - 32; idx < 32 * p; idx += blockDim.x - 32) {
         const int lane = idx & 31, k = idx >> 5;
         const int c = cg * 32 + lane;
         if (c >= a.C) continue;
-        const R* par = a.params + (long long)c * a.P;
+        const R* par = par_of(lane, c);
         const D* gg = red + (kRegSlots + KK + 4 + a.goff[t]) * 32 + lane;
         D v = 0.0;
         for (int j = 0; j < nb; ++j) v = fma((D)Zt[j * p + k], gg[j * 32], v);
@@ -991,7 +1004,6 @@ __global__ void k_post(const PostArgs<R> a) {
       }
     }
   }
-  __syncthreads();
   // transformation block + logp: one thread per chain
   if (tid < 32) {
     const int lane = tid;
@@ -999,7 +1011,7 @@ __global__ void k_post(const PostArgs<R> a) {
     if (c < a.C) {
       const TrafoConst<D>& tc = *a.tc;
       const int np_ = tc.nparam;
-      const R* par = a.params + (long long)c * a.P;
+      const R* par = par_of(lane, c);
       const R* dz = par + a.dz_off;
       const D taud = (D)par[a.taud_off];
       D ss = 0.0;
