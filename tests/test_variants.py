@@ -64,6 +64,20 @@ def test_oracle_onion_knots_coef_and_spline_match_reference_code():
     assert np.max(np.abs(z0 - v["r"])) < 1e-5 and np.max(np.abs(d0 - 1.0)) < 1e-12
 
 
+def test_oracle_onion_properties_of_the_reference_tests():
+    """tests/test_bspline/test_onion.py of the reference: OnionKnots(-4, 4, nparam=10), normal
+    coefficients, x on linspace(-8, 8): no NaN, h' > 0, h increasing."""
+    kn = o.OnionKnots(-4.0, 4.0, 10)
+    sp = o.OnionSpline(kn.knots)
+    rng = np.random.default_rng(1)
+    for x in (np.linspace(-8.0, 8.0, 300), np.linspace(-8.0, 8.0, 10_000)):
+        for coef in rng.normal(size=(3, 10)):
+            fx, fxd = sp.dot_and_deriv_n_fullbatch(x, coef)
+            assert fx.shape == x.shape and fxd.shape == x.shape
+            assert not np.isnan(fx).any() and not np.isnan(fxd).any()
+            assert np.all(fxd > 0.0) and np.all(np.diff(fx) > 0.0)
+
+
 @pytest.mark.parametrize("kind", ["onion", "identity"])
 def test_oracle_variant_logp_grad_match_reference_code(kind):
     d, v = _fixtures()
@@ -185,6 +199,43 @@ def test_cuda_variant_logp_grad_f32_both_routes(kind, monkeypatch):
         g = grad.cpu().numpy()
         for c in range(2):
             assert rel_err(g[c], g_ref[c]) < 1e-5, (tc, c)
+
+
+@pytest.mark.gpu
+def test_cuda_onion_transform_vs_reference_code_and_properties():
+    """ptm_transform_* / ptm_inverse_* on an onion problem: h, h' against the reference-run fixture
+    inside and outside the core, the properties the reference's test_onion.py asserts, and the
+    round trip through the inverse."""
+    import torch
+
+    _, v = _fixtures()
+    y = np.zeros(8)
+    model = lp.LocScalePTM(y, lp.OnionKnots(-4.0, 4.0, 20).knots, to_float32=False, device="cuda:0",
+                           bspline="onion").build()
+    z, dz = model.transform(torch.from_numpy(v["delta"]).cuda(), torch.from_numpy(v["r"]).cuda())
+    assert np.max(np.abs(z.cpu().numpy() - v["onion_z"])) < 2e-13
+    assert np.max(np.abs(dz.cpu().numpy() - v["onion_d"])) < 2e-12
+    # nparam = 10 like the reference's tests
+    m10 = lp.LocScalePTM(y, lp.OnionKnots(-4.0, 4.0, 10).knots, to_float32=False, device="cuda:0",
+                         bspline="onion").build()
+    rng = np.random.default_rng(1)
+    coef = torch.from_numpy(rng.normal(size=(3, 10))).cuda()
+    x = torch.linspace(-8.0, 8.0, 10_000, dtype=torch.float64, device="cuda")
+    fx, fxd = m10.transform(coef, x)
+    assert fx.shape == (3, 10_000) and fxd.shape == (3, 10_000)
+    assert not torch.isnan(fx).any() and not torch.isnan(fxd).any()
+    assert bool((fxd > 0.0).all()) and bool((fx[:, 1:] - fx[:, :-1] > 0.0).all())
+    sp = o.OnionSpline(o.OnionKnots(-4.0, 4.0, 10).knots)
+    for c in range(3):
+        rz, rd = sp.dot_and_deriv_n_fullbatch(x.cpu().numpy(), coef[c].cpu().numpy())
+        assert np.max(np.abs(fx[c].cpu().numpy() - rz)) < 1e-12 and np.max(np.abs(fxd[c].cpu().numpy() - rd)) < 1e-11
+    # inverse: h(h^-1(z)) = z (the reference's round-trip tests accept 1e-5 .. 1e-4,
+    # tests/test_bspline/test_ptm.py:167-301)
+    zq = torch.linspace(-7.0, 7.0, 4001, dtype=torch.float64, device="cuda")
+    for c in range(3):
+        r_inv = m10.inverse(coef[c], zq)
+        z_back, _ = m10.transform(coef[c], r_inv)
+        assert float((z_back - zq).abs().max()) < 1e-9
 
 
 @pytest.mark.gpu
