@@ -316,3 +316,39 @@ def test_cuda_new_gaussian_and_onion_at_size():
     assert rel_err(lp_.cpu().numpy(), lp_ref) < 1e-12
     for c in range(5):
         assert rel_err(g_[c].cpu().numpy(), g_ref[c]) < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["onion", "identity"])
+def test_cuda_variant_predictive_records_vs_oracle(kind):
+    """init_dist(samples, newdata=...) -> transformation / log_prob / cdf (model/model.py:698-790) and
+    the pointwise WAIC records of the training response for the onion and the Gaussian model."""
+    import torch
+
+    from tests.helpers import build_case
+
+    case = build_case(n=400, n_loc=2, n_scale=2, nbases=10, nparam=20, C=7, amp=0.3, bspline=kind)
+    rng = np.random.default_rng(31)
+    m = 333
+    newdata = {f"x{t}": rng.uniform(-1.99, 1.99, size=m) for t in range(4)}
+    grid = rng.normal(scale=2.5, size=m)
+    params = torch.from_numpy(case.params).cuda()
+    out = case.model.summarise_dist(params, grid=grid, newdata=newdata)
+    X = [newdata[f"x{t}"] for t in range(4)]
+    for c in range(7):
+        z, lp_, cdf, _, _ = case.omodel.predict(case.state, c, grid, X)
+        assert rel_err(out["z"][c].cpu().numpy(), z) < 1e-12
+        assert rel_err(out["log_prob"][c].cpu().numpy(), lp_) < 1e-12
+        assert rel_err(out["cdf"][c].cpu().numpy(), cdf) < 1e-12
+    ll = np.stack([case.omodel.loglik_terms(case.state, c)["ll"] for c in range(7)])
+    mx = ll.max(axis=0)
+    lppd_ref = mx + np.log(np.exp(ll - mx).sum(axis=0)) - np.log(7)
+    lppd, pwaic = case.model.pointwise(params)
+    assert rel_err(lppd.cpu().numpy(), lppd_ref) < 1e-12
+    assert rel_err(pwaic.cpu().numpy(), ll.var(axis=0)) < 1e-9
+    # quantile -> cdf round trip through the CUDA path
+    u = rng.uniform(0.01, 0.99, size=m)
+    yq = case.model.predict_quantile(params, u, newdata=newdata)
+    for c in range(2):
+        cdf = case.model.summarise_dist(params[c:c + 1], grid=yq[c].cpu().numpy(), newdata=newdata, which=("cdf",))["cdf"]
+        assert np.max(np.abs(cdf.cpu().numpy()[0] - u)) < 1e-10
