@@ -230,6 +230,14 @@ def update_intercepts(model: LocScalePTM, params: torch.Tensor) -> torch.Tensor:
     return out
 
 
+class _NoShapeBlock:
+    """Stand-in for the HMC block's record when the model has no shape parameters."""
+
+    def __init__(self, params):
+        self.log_alpha = torch.zeros(params.shape[0], dtype=params.dtype, device=params.device)
+        self.accepted = torch.ones(params.shape[0], dtype=torch.bool, device=params.device)
+
+
 def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: int, seed: int = 0,
                iwls_step: float = 1.0, dz_step: float = 0.05, target_accept: float = 0.8, n_leapfrog: int = 8,
                reuse_information: bool = True, use_graph: bool = True, sample_tau: bool = False,
@@ -252,7 +260,8 @@ def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: in
     step = torch.full((C,), float(dz_step), dtype=params.dtype, device=params.device)
     metric_chol = torch.eye(dz_w, dtype=params.dtype, device=params.device)
     adapt_t = 0
-    metric_updates = {(warmup * k) // 8 for k in (2, 3, 4, 5, 6, 7)}
+    has_shape = getattr(model, "bspline", "ptm") != "identity"
+    metric_updates = {(warmup * k) // 8 for k in (2, 3, 4, 5, 6, 7)} if has_shape else set()
     T = len(model.terms)
     is_loc = [pred == _lib.PTM_LOC for _, pred in model.terms]
     istep = torch.full((max(T, 1), C), float(iwls_step), dtype=params.dtype, device=params.device)
@@ -299,7 +308,10 @@ def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: in
                 istep[t] = torch.clamp(istep[t] * torch.exp((a - 0.8) * (10.0 / (it_warm + 10.0))), 1e-3, 2.0)
             else:
                 acc_i = acc_i + info.accepted.double().mean() / T
-        params, cache, info = hmc_transition(model, params, dz_lo, dz_w, step, n_leapfrog, metric_chol, gen, cache)
+        if has_shape:
+            params, cache, info = hmc_transition(model, params, dz_lo, dz_w, step, n_leapfrog, metric_chol, gen, cache)
+        else:  # Gaussian model (bspline="identity", model/model.py:386-417): no shape parameters to move
+            info = _NoShapeBlock(params)
         if sample_tau or pgibbs_intercepts:
             # Gibbs blocks of the reference's composition; the cached logp / gradient are stale after
             # them and are refreshed with one fused sweep
@@ -317,7 +329,7 @@ def run_chains(model: LocScalePTM, params0: torch.Tensor, warmup: int, draws: in
         a = torch.exp(torch.clamp(info.log_alpha, max=0.0))
         step = step * torch.exp((a - target_accept) * (10.0 / (adapt_t + 10.0)))
         adapt_t += 1
-        if it >= warmup // 8:
+        if has_shape and it >= warmup // 8:
             window.append(params[:, dz_lo: dz_lo + dz_w].clone())
         if window and (it + 1) in metric_updates and C * len(window) >= 10 * dz_w:
             cov = torch.cov(torch.cat(window, 0).T)
