@@ -135,3 +135,18 @@ def test_tc_route_matches_cuda_core_route_at_c3_size(monkeypatch):
     assert rel_err(lp.cpu().numpy(), lp0.cpu().numpy()) < 2e-6
     e = ((g.double() - g0.double()).abs().amax(dim=1) / g0.double().abs().amax(dim=1)).max().item()
     assert e < 2e-5, e
+
+
+def test_tc_route_random_shapes_fuzz():
+    """tools/fuzz_tc.py: 40 seeded random (n, chains, terms, nbases, transformation variant) models,
+    several-pass forms included -- the tensor-core route against the CUDA-core route (logp 5e-6,
+    gradient 3e-5 of its inf-norm) and, for the small ones, the float64 oracle at 1e-5."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_tc.py"), "40", "11"], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "failures: 0" in r.stdout, r.stdout[-3000:]
